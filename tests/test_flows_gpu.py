@@ -1,0 +1,180 @@
+"""GPU parity: CUDA flow kernels (through the C ABI, via the drop-in modules) vs the golden
+vectors recorded from the reference and vs the CPU oracle on larger seeded inputs.
+
+Tolerance (BASELINE.json north_star): rtol 1e-5 for fp32 flow outputs and log-dets; an
+absolute floor of 1e-5 x (typical magnitude) covers values near zero (log-dets of ~0 at
+the spline tails)."""
+
+import pytest
+import torch
+
+from oracle import flows_cpu
+from tests.helpers import golden_sd, golden_spec, load_flow_model, load_golden, random_flow_sd, t
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(a, b, what, rtol=RTOL, atol_scale=1e-5):
+    a = a.detach().float().cpu()
+    scale = max(1.0, float(b.abs().mean()))
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol_scale * scale, msg=lambda m: f"{what}: {m}")
+
+
+FLOW_CASES = ["rnvp9_moons", "nsfcl3_stack", "nsfcl_d4", "nsfar2_d3", "maf9_d64", "maf3_d8", "maf_iaf_d2",
+              "affine_misc_d4"]
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+@pytest.mark.parametrize("kernel", [None, "generic"])
+def test_stack_vs_golden(name, kernel):
+    g = load_golden(name)
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    x = t(g, "inv/x").cuda()
+    y, ld, inter, lp = prog.run(x, inverse=True, want_inter=True, want_base_lp=True, kernel=kernel)
+    close(y, t(g, "inv/z"), "z")
+    close(ld, t(g, "inv/ld"), "log_det")
+    n = len(specs) + 1
+    mid = n // 2
+    close(inter[mid - 1], t(g, "inv/z_mid"), "z_mid")
+    close(lp, t(g, "inv/base_log_prob"), "base_log_prob", atol_scale=2e-5)
+    if "fwd/z" in g:
+        z = t(g, "fwd/z").cuda()
+        y, ld, inter, _ = prog.run(z, inverse=False, want_inter=True, kernel=kernel)
+        close(y, t(g, "fwd/x"), "x")
+        close(ld, t(g, "fwd/ld"), "log_det fwd")
+        close(inter[mid - 1], t(g, "fwd/x_mid"), "x_mid")
+
+
+@pytest.mark.parametrize("name", ["rnvp9_moons", "nsfcl3_stack"])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_dim2_kernel_variants(name, variant):
+    g = load_golden(name)
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    assert prog.plan(torch.device("cuda"), 2) == 1, "BASELINE dim-2 stacks must take the register-resident kernel"
+    x = t(g, "inv/x").cuda()
+    y, ld, _, _ = prog.run(x, inverse=True, kernel=variant)
+    close(y, t(g, "inv/z"), "z")
+    close(ld, t(g, "inv/ld"), "log_det")
+    # odd row count exercises the half-filled last pair
+    y, ld, _, _ = prog.run(x[:101].contiguous(), inverse=True, kernel=variant)
+    close(y, t(g, "inv/z")[:101], "z odd")
+    close(ld, t(g, "inv/ld")[:101], "log_det odd")
+
+
+def test_module_api_matches_reference_contract():
+    """forward(z) -> (x, log_det), container -> (list incl. input, log_det[B]) (core.py:17-35)."""
+    g = load_golden("nsfcl3_stack")
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd)
+    x = t(g, "inv/x").cuda()
+    zs, ld = model.inverse(x)
+    assert isinstance(zs, list) and len(zs) == len(specs) + 1 and zs[0] is x
+    assert ld.shape == (x.size(0),) and ld.dtype == torch.float32 and ld.is_cuda
+    close(zs[-1], t(g, "inv/z"), "z")
+    close(model.base_log_prob(x), t(g, "inv/base_log_prob"), "base_log_prob", atol_scale=2e-5)
+    close(model.log_prob(x), t(g, "inv/ld") + t(g, "inv/base_log_prob"), "log_prob", atol_scale=2e-5)
+    # single-flow API and log_det shapes of the reference: [1] for affine-constant, [] for Glow
+    z1, ld1 = model.flows[0].inverse(x)
+    assert ld1.shape == (1,)
+    z2, ld2 = model.flows[1].inverse(z1)
+    assert ld2.shape == ()
+    z3, ld3 = model.flows[2].inverse(z2)
+    assert ld3.shape == (x.size(0),)
+    # round trip (encode -> decode), the size-independent property of the domain
+    xs, ld_f = model.forward(zs[-1])
+    torch.testing.assert_close(xs[-1], x, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(ld_f, -ld, rtol=1e-4, atol=5e-5)
+    with pytest.raises(RuntimeError):
+        model.inverse(x.cpu())  # no CPU fallback
+
+
+def test_actnorm_data_dependent_init():
+    import torch_mnf.flows as nf
+
+    g = load_golden("actnorm_init")
+    torch.manual_seed(0)
+    f = nf.ActNormFlow(3).cuda()
+    z, ld = f.inverse(t(g, "x").cuda())
+    assert f.data_dep_init_done
+    close(f.s, t(g, "s"), "s")
+    close(f.t, t(g, "t"), "t")
+    close(z, t(g, "z"), "z")
+    close(ld, t(g, "ld"), "ld")
+
+
+ORACLE_CASES = {
+    "cfg2_shape": [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}, {"type": "Glow", "dim": 2},
+                   {"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}] * 3,
+    "cfg1_shape": [{"type": "AffineHalfFlow", "dim": 2, "parity": bool(i % 2), "scale": True, "shift": True,
+                    "h_sizes": [24, 24, 24]} for i in range(9)],
+    "nsf_default": [{"type": "NSF_CL", "dim": 2, "K": 5, "B": 3, "n_h": 8}] * 2,
+    "nsf_wide_d6": [{"type": "Glow", "dim": 6}, {"type": "NSF_CL", "dim": 6, "K": 12, "B": 4, "n_h": 20},
+                    {"type": "NSF_AR", "dim": 6, "K": 6, "B": 2, "n_h": 12}],
+}
+
+
+@pytest.mark.parametrize("name", sorted(ORACLE_CASES))
+def test_stack_vs_oracle_seeded(name):
+    """Bigger seeded batches (incl. tail points and exact +-B) against the CPU oracle."""
+    specs = ORACLE_CASES[name]
+    sd = random_flow_sd(specs, seed=3, scale=0.6 if "cfg1" not in name else 0.3)
+    model = load_flow_model(specs, sd)
+    dim = specs[0]["dim"]
+    g = torch.Generator().manual_seed(11)
+    x = 1.5 * torch.randn(20001, dim, generator=g)
+    B = max([s.get("B", 3) for s in specs])
+    x[0, :] = float(B)
+    x[1, :] = -float(B)
+    x[2, :] = 0.0
+    for inverse in (True, False):
+        ref_list, ref_ld = flows_cpu.stack(sd, specs, x, inverse=inverse)
+        y, ld, _, _ = model._program().run(x.cuda(), inverse=inverse)
+        close(y, ref_list[-1], f"{name} out inverse={inverse}")
+        close(ld, ref_ld, f"{name} log_det inverse={inverse}", atol_scale=2e-5)
+
+
+def test_empty_and_single_row():
+    g = load_golden("nsfcl3_stack")
+    model = load_flow_model(golden_spec(g), golden_sd(g))
+    zs, ld = model.inverse(torch.empty(0, 2, device="cuda"))
+    assert zs[-1].shape == (0, 2) and ld.shape == (0,)
+    x = t(g, "inv/x")[:1].cuda()
+    zs, ld = model.inverse(x)
+    close(zs[-1], t(g, "inv/z")[:1], "single row")
+
+
+def test_all_points_outside_spline_domain_is_identity():
+    """The reference crashes here (spline_flow.py:85); the drop-in maps to identity."""
+    import torch_mnf.flows as nf
+
+    torch.manual_seed(0)
+    f = nf.NSF_CL(2, K=8, B=3, n_h=16).cuda()
+    x = torch.tensor([[4.0, -5.0], [100.0, 3.5]], device="cuda")
+    z, ld = f.inverse(x)
+    assert torch.equal(z, x) and torch.equal(ld, torch.zeros(2, device="cuda"))
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE config 2 at full size (2^24 points): round trip + log-det antisymmetry."""
+    specs = ORACLE_CASES["cfg2_shape"]
+    sd = random_flow_sd(specs, seed=0, scale=0.6)
+    model = load_flow_model(specs, sd, return_intermediates=False)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = 1.5 * torch.randn(1 << 24, 2, device="cuda", generator=g)
+    zs, ld = model.inverse(x)
+    xs, ld_f = model.forward(zs[-1])
+    err = (xs[-1] - x).abs().max().item()
+    assert err < 5e-4, err
+    assert (ld + ld_f).abs().max().item() < 1e-3
+    assert torch.isfinite(ld).all()
+    # checksum against the oracle on a strided sample
+    idx = torch.arange(0, 1 << 24, 4099, device="cuda")
+    ref_list, ref_ld = flows_cpu.stack(sd, specs, x[idx].cpu(), inverse=True)
+    close(zs[-1][idx], ref_list[-1], "sampled z")
+    close(ld[idx], ref_ld, "sampled log_det", atol_scale=2e-5)

@@ -1,0 +1,59 @@
+// abi.cu -- version / error / device-info entry points of libmnf_b200.so.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace mnf {
+
+char *err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+const DeviceProps *device_props() {
+    static DeviceProps props[64];
+    static bool ready[64] = {false};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ready[dev]) {
+        DeviceProps p;
+        if (cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return nullptr;
+        if (cudaDeviceGetAttribute(&p.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+            return nullptr;
+        cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+        props[dev] = p;
+        ready[dev] = true;
+    }
+    return &props[dev];
+}
+
+}  // namespace mnf
+
+extern "C" {
+
+int mnf_abi_version(void) { return MNF_ABI_VERSION; }
+
+const char *mnf_last_error(void) { return mnf::err_buf(); }
+
+int mnf_device_info(int *sm_count, int *smem_optin, int *cc_major, int *cc_minor) {
+    const mnf::DeviceProps *p = mnf::device_props();
+    if (!p) return mnf::fail(MNF_E_DEVICE, "no CUDA device available");
+    if (sm_count) *sm_count = p->sm_count;
+    if (smem_optin) *smem_optin = p->smem_optin;
+    if (cc_major) *cc_major = p->cc_major;
+    if (cc_minor) *cc_minor = p->cc_minor;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""Host-side flow-program builder: turns a list of flow modules into the descriptor array +
+packed parameter blob that ``mnf_flow_stack_run`` consumes (include/mnf_b200.h), caches it
+until a parameter changes, and launches it.
+
+Layout of the blob (fp32, device): every group starts on a 4-float boundary; a conditioner
+net is stored per Linear layer as weight ``[out][in]`` (torch order) followed by bias.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+class ParamPacker:
+    def __init__(self, device):
+        self.device = device
+        self.parts: list[torch.Tensor] = []
+        self.n = 0
+        self.post = []  # callables(blob) run after the blob exists (e.g. Glow assembly)
+
+    def _pad(self):
+        pad = (-self.n) % 4
+        if pad:
+            self.parts.append(torch.zeros(pad, device=self.device))
+            self.n += pad
+
+    def add(self, *tensors) -> int:
+        """Append tensors back to back (one group); returns the group's float offset."""
+        self._pad()
+        off = self.n
+        for t in tensors:
+            t = t.detach()
+            if t.device != self.device:
+                raise RuntimeError(f"parameter on {t.device}, input on {self.device}")
+            self.parts.append(t.reshape(-1).to(torch.float32))
+            self.n += t.numel()
+        return off
+
+    def reserve(self, n: int, fill=None) -> int:
+        self._pad()
+        off = self.n
+        self.parts.append(torch.zeros(n, device=self.device))
+        self.n += n
+        if fill is not None:
+            self.post.append(lambda blob, off=off: fill(blob, off))
+        return off
+
+    def finish(self) -> torch.Tensor:
+        self._pad()
+        blob = torch.cat(self.parts) if self.parts else torch.zeros(4, device=self.device)
+        for fn in self.post:
+            fn(blob)
+        return blob
+
+
+def net_tensors(linears, masks=None):
+    """[w0, b0, w1, b1, ...] for a chain of nn.Linear; MADE masks ([in,out]) folded into the weights."""
+    out = []
+    for i, lin in enumerate(linears):
+        w = lin.weight
+        if masks is not None:
+            w = w * masks[i].to(w.dtype).T  # made.py:23: x @ (W.T * mask)
+        out += [w, lin.bias]
+    return out
+
+
+def new_op(type_, flags=0, K=0, bound=0.0, sizes=(), net_off=(0, 0), aux_off=0, edge_deriv=0.0):
+    if len(sizes) - 1 > _lib.MAX_LIN:
+        raise ValueError(f"conditioner has {len(sizes) - 1} Linear layers; at most {_lib.MAX_LIN} supported")
+    op = _lib.FlowOp()
+    op.type, op.flags, op.K, op.bound = type_, flags, K, float(bound)
+    op.n_lin = max(len(sizes) - 1, 0)
+    for i, s in enumerate(sizes):
+        op.sizes[i] = int(s)
+    op.net_off[0], op.net_off[1] = int(net_off[0]), int(net_off[1])
+    op.aux_off, op.edge_deriv = int(aux_off), float(edge_deriv)
+    return op
+
+
+def spline_edge_derivative(min_deriv: float = 1e-3) -> float:
+    """min_d + softplus(log(exp(1 - min_d) - 1)) evaluated in fp32 (spline_flow.py:46-49,104)."""
+    c = torch.tensor(math.log(math.exp(1 - min_deriv) - 1), dtype=torch.float32)
+    return float(min_deriv + torch.nn.functional.softplus(c))
+
+
+def _state_key(flows, device):
+    key = [str(device)]
+    for f in flows:
+        for t in list(f.parameters()) + list(f.buffers()):
+            key.append((t.data_ptr(), t._version))
+        key.append(getattr(f, "_program_salt", 0))
+    return tuple(key)
+
+
+class FlowProgram:
+    """Cached (descriptors, blob) for a sequence of flow modules."""
+
+    def __init__(self, flows):
+        self.flows = list(flows)
+        self._key = None
+        self._ops = None
+        self._blob = None
+
+    def _build(self, device):
+        key = _state_key(self.flows, device)
+        if key == self._key:
+            return
+        pk = ParamPacker(device)
+        ops = [f._emit(pk) for f in self.flows]
+        with torch.no_grad():
+            blob = pk.finish()
+        self._ops = (_lib.FlowOp * max(len(ops), 1))(*ops)
+        self._n_ops = len(ops)
+        self._blob = blob
+        self._key = key
+
+    def plan(self, device, dim) -> int:
+        """1 if the dim-2 register-resident kernel will run this program, else 0 (generic)."""
+        self._build(device)
+        n = min(self._n_ops, _lib.MAX_OPS)
+        return _lib.lib().mnf_flow_stack_plan(self._ops, n, dim, self._blob.numel())
+
+    @torch.no_grad()
+    def run(self, x, inverse: bool, want_inter: bool = False, want_base_lp: bool = False, out=None,
+            log_det=None, kernel=None):
+        """kernel: None = library default, "generic" = interpreter, 0/1/2 = dim-2 kernel variant."""
+        x = _lib.require_cuda_f32(x, "input")
+        if x.dim() != 2:
+            raise ValueError(f"flows take [batch, dim] inputs, got shape {tuple(x.shape)}")
+        B, D = x.shape
+        dev = x.device
+        self._build(dev)
+        lib = _lib.lib()
+        y = out if out is not None else torch.empty_like(x)
+        ld = log_det if log_det is not None else torch.empty(B, device=dev, dtype=torch.float32)
+        lp = torch.empty(B, device=dev, dtype=torch.float32) if want_base_lp else None
+        n = self._n_ops
+        inter = torch.empty((n, B, D), device=dev, dtype=torch.float32) if want_inter else None
+        if n == 0:
+            y.copy_(x)
+            ld.zero_()
+        stream = _lib.stream_ptr(dev)
+        flags = _lib.RUN_INVERSE if inverse else 0
+        if kernel == "generic":
+            flags |= _lib.RUN_GENERIC
+        elif kernel is not None:
+            flags |= ((int(kernel) + 1) << 4) & 0x30
+        with torch.cuda.device(dev):
+            # stacks longer than MNF_MAX_OPS run in chunks, log-dets summed across chunks
+            done, src, first = 0, x, True
+            order = list(range(0, n, _lib.MAX_OPS))
+            if inverse:
+                order = order[::-1]
+            for start in order:
+                cnt = min(_lib.MAX_OPS, n - start)
+                ops_ptr = C.cast(C.byref(self._ops, start * C.sizeof(_lib.FlowOp)), C.POINTER(_lib.FlowOp))
+                last = done + cnt == n
+                ld_chunk = ld if first else torch.empty_like(ld)
+                rc = lib.mnf_flow_stack_run(
+                    ops_ptr, cnt, self._blob.data_ptr(), self._blob.numel(), src.data_ptr(), y.data_ptr(),
+                    ld_chunk.data_ptr(), _lib.ptr(lp) if last else None,
+                    inter[done:].data_ptr() if inter is not None else None, B, D, flags, stream,
+                )
+                _lib.check(rc, "mnf_flow_stack_run")
+                if not first:
+                    ld += ld_chunk
+                first, src, done = False, y, done + cnt
+        return y, ld, inter, lp

@@ -1,0 +1,145 @@
+"""Flow containers (reference: flows/core.py:10-55), fused into one CUDA launch per call."""
+
+from __future__ import annotations
+
+from collections.abc import Sequence
+
+import torch
+from torch import Tensor, nn
+from torch.distributions import Distribution, Independent, MultivariateNormal, Normal
+
+from .. import _lib
+from .._program import FlowProgram
+from ._base import Flow
+
+
+class NormalizingFlow(nn.Module):
+    """A sequence of flows.  ``forward`` / ``inverse`` return ``(list, log_det[B])`` where the
+    list holds the input followed by the output of every flow (core.py:17-35).
+
+    All flows run in ONE kernel launch: the point stays in registers from the first flow to
+    the last and the log-det is accumulated on chip.  ``return_intermediates=False`` (an
+    additive option) skips writing the per-flow outputs to HBM; the list is then
+    ``[input, final]`` so ``xs[-1]`` / ``zs[-1]`` keep working.
+
+    Stacks made only of ``RNVP`` flows (the MNF q/r flows) go through the MNF RNVP kernel and
+    accept a ``noise`` tape for their Bernoulli masks.
+    """
+
+    def __init__(self, flows: Sequence[nn.Module], return_intermediates: bool = True) -> None:
+        super().__init__()
+        self.flows = nn.ModuleList(flows)
+        self.return_intermediates = return_intermediates
+        self.__dict__["_prog"] = None
+
+    def _program(self) -> FlowProgram:
+        prog = self.__dict__.get("_prog")
+        if prog is None or len(prog.flows) != len(self.flows) or any(
+            a is not b for a, b in zip(prog.flows, self.flows)
+        ):
+            for f in self.flows:
+                if not isinstance(f, Flow):
+                    raise TypeError(f"{type(f).__name__} is not a torch_mnf flow")
+            prog = FlowProgram(list(self.flows))
+            self.__dict__["_prog"] = prog
+        return prog
+
+    def _is_rnvp_stack(self) -> bool:
+        from .rnvp import RNVP
+
+        return len(self.flows) > 0 and all(isinstance(f, RNVP) for f in self.flows)
+
+    def _run(self, v: Tensor, inverse: bool, want_lp: bool = False):
+        for f in self.flows:
+            hook = getattr(f, "_before_run", None)
+            if hook is not None:
+                hook(v, inverse)
+        y, ld, inter, lp = self._program().run(
+            v, inverse, want_inter=self.return_intermediates, want_base_lp=want_lp
+        )
+        outs = [v] + (list(inter.unbind(0)) if inter is not None else [y])
+        if inter is not None and len(self.flows) == 0:
+            outs = [v]
+        return outs, ld, lp
+
+    def forward(self, z: Tensor, noise=None) -> tuple[list[Tensor], Tensor]:  # z -> x
+        if self._is_rnvp_stack():
+            from .rnvp import rnvp_stack_forward
+
+            return rnvp_stack_forward(list(self.flows), z, noise, self.return_intermediates)
+        outs, ld, _ = self._run(z, inverse=False)
+        return outs, ld
+
+    def inverse(self, x: Tensor) -> tuple[list[Tensor], Tensor]:  # x -> z
+        if self._is_rnvp_stack():
+            raise NotImplementedError("RNVP has no inverse (reference: flows/rnvp.py)")
+        outs, ld, _ = self._run(x, inverse=True)
+        return outs, ld
+
+
+def _is_std_normal(base, dim: int) -> bool:
+    try:
+        if isinstance(base, MultivariateNormal):
+            return (
+                base.loc.numel() == dim
+                and bool((base.loc == 0).all())
+                and bool((base.covariance_matrix == torch.eye(dim, device=base.loc.device)).all())
+            )
+        if isinstance(base, Independent) and isinstance(base.base_dist, Normal):
+            n = base.base_dist
+            return n.loc.numel() == dim and bool((n.loc == 0).all()) and bool((n.scale == 1).all())
+    except Exception:
+        return False
+    return False
+
+
+class NormalizingFlowModel(NormalizingFlow):
+    """(base distribution, flows) pair (core.py:38-55)."""
+
+    def __init__(self, base: Distribution, flows: Sequence[nn.Module], return_intermediates: bool = True) -> None:
+        super().__init__(flows, return_intermediates)
+        self.base = base
+        self.__dict__["_std_base"] = {}
+
+    def _base_is_std(self, dim):
+        cache = self.__dict__["_std_base"]
+        if dim not in cache:
+            cache[dim] = _is_std_normal(self.base, dim)
+        return cache[dim]
+
+    def base_log_prob(self, x: Tensor) -> Tensor:
+        """base.log_prob(inverse(x)[-1]) (core.py:46-49).  For a standard-normal base the
+        density is evaluated inside the flow kernel (no second pass over z)."""
+        if self._base_is_std(x.size(-1)):
+            keep, self.return_intermediates = self.return_intermediates, False
+            try:
+                _, _, lp = self._run(x, inverse=True, want_lp=True)
+            finally:
+                self.return_intermediates = keep
+            return lp
+        zs, _ = self.inverse(x)
+        z = zs[-1]
+        loc = getattr(self.base, "loc", None)
+        return self.base.log_prob(z if loc is None or loc.device == z.device else z.to(loc.device)).to(z.device)
+
+    def log_prob(self, x: Tensor) -> Tensor:
+        """log p(x) = log_det(inverse) + base_log_prob in ONE pass (the reference's callers
+        run the inverse twice, tests/test_flows.py:22-24)."""
+        if self._base_is_std(x.size(-1)):
+            keep, self.return_intermediates = self.return_intermediates, False
+            try:
+                _, ld, lp = self._run(x, inverse=True, want_lp=True)
+            finally:
+                self.return_intermediates = keep
+            return ld.add_(lp)
+        zs, ld = self.inverse(x)
+        return ld + self.base_log_prob(x)
+
+    def sample(self, *num_samples: int) -> Tensor:
+        """core.py:51-55.  Base samples are drawn by torch and moved to the flows' device."""
+        z = self.base.sample(*num_samples)
+        p = next(self.parameters(), None)
+        if p is not None and z.device != p.device:
+            z = z.to(p.device)
+        xs, _ = self.forward(z.float())
+        return xs[-1]
