@@ -77,8 +77,9 @@ def made_masks(n_in: int, hidden: list[int], n_out: int, natural: bool, seed: in
 # ---------------------------------------------------------------------------
 def _const_st(p: dict, spec: dict):
     d = spec["dim"]
-    s = p["s"] if "s" in p else torch.zeros(1, d)  # affine_constant_flow.py:15
-    t = p["t"] if "t" in p else torch.zeros(1, d)  # affine_constant_flow.py:16
+    ref = next(iter(p.values())) if p else torch.zeros(())
+    s = p["s"] if "s" in p else torch.zeros(1, d, dtype=ref.dtype)  # affine_constant_flow.py:15
+    t = p["t"] if "t" in p else torch.zeros(1, d, dtype=ref.dtype)  # affine_constant_flow.py:16
     return s, t
 
 
@@ -123,7 +124,7 @@ def affine_half(p, spec, v, inverse: bool):
 def glow_W(p):
     """glow.py:20-24."""
     n = len(p["L"])
-    L = torch.tril(p["L"], diagonal=-1) + torch.eye(n)
+    L = torch.tril(p["L"], diagonal=-1) + torch.eye(n, dtype=p["L"].dtype)
     U = torch.triu(p["U"], diagonal=1)
     return p["P"] @ L @ (U + p["S"].diag())
 
@@ -152,7 +153,7 @@ def maf_sample(p, spec, z):
     """maf.py:39-51 (MAF.forward): D sequential MADE passes."""
     B, d = z.shape
     x = torch.zeros_like(z)
-    ld = torch.zeros(B)
+    ld = torch.zeros(B, dtype=z.dtype)
     if spec["parity"]:
         z = z.flip(dims=[1])
     net = sub(p, "net.")
@@ -271,7 +272,7 @@ def nsf_cl(p, spec, v, inverse: bool):
     """spline_flow.py:249-285."""
     d, K, B = spec["dim"], spec["K"], spec["B"]
     h = d // 2
-    ld = torch.zeros(v.shape[0])
+    ld = torch.zeros(v.shape[0], dtype=v.dtype)
     lower, upper = v[:, :h], v[:, h:]
     f1, f2 = sub(p, "f1."), sub(p, "f2.")
     if not inverse:
@@ -296,7 +297,7 @@ def nsf_ar(p, spec, v, inverse: bool):
     d, K, B = spec["dim"], spec["K"], spec["B"]
     n = v.shape[0]
     out = torch.zeros_like(v)
-    ld = torch.zeros(n)
+    ld = torch.zeros(n, dtype=v.dtype)
     for i in range(d):
         if i == 0:
             raw = p["init_param"].expand(n, 3 * K - 1)
@@ -338,7 +339,7 @@ def apply_flow(p, spec, v, inverse: bool, mask=None):
 
 def stack(sd: dict, specs: list[dict], v, inverse: bool, tape=None, prefix="flows."):
     """core.py:17-35 -- returns (list of intermediates incl. the input, log_det[B])."""
-    ld = torch.zeros(v.size(0))
+    ld = torch.zeros(v.size(0), dtype=v.dtype)
     outs = [v]
     order = list(enumerate(specs))
     if inverse:

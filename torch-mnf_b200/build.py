@@ -16,9 +16,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+SUFFIX = os.environ.get("MNF_LIB_SUFFIX", "")  # experiment builds: separate objects and .so name
+OBJ = os.path.join(HERE, "build" + SUFFIX)
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libmnf_b200.so")
+LIB = os.path.join(LIBDIR, f"libmnf_b200{SUFFIX}.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

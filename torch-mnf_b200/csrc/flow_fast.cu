@@ -17,7 +17,7 @@ struct FastPlan {
     FastLayout lay;
 };
 
-static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim) {
+static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int variant) {
     FastPlan p;
     if (dim != 2 || n_ops < 1) return p;
     int H = 0, K = 0, slots = 0;
@@ -38,7 +38,7 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim) {
             n_out = 3 * K - 1;
         }
         if (op.sizes[4] != n_out) return p;
-        const int per_net = 2 * h + 2 * (h * h + h) + n_out * h + ((n_out + 3) / 4) * 4;
+        const int per_net = fast_net_slots(h, n_out, variant);
         for (int which = 0; which < 2; ++which) {
             p.lay.net_slot[k][which] = slots;
             slots += per_net;
@@ -61,11 +61,11 @@ constexpr int kDefaultVariant = 2;
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int variant, cudaStream_t stream, bool plan_only) {
-    const FastPlan p = plan_fast(ops, n_ops, dim);
+    const int mode = (variant >= 0 && variant <= 2) ? variant : kDefaultVariant;
+    const FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
     const DeviceProps *dp = plan_only ? nullptr : device_props();
-    const int mode = (variant >= 0 && variant <= 2) ? variant : kDefaultVariant;
-    const size_t smem_bytes = (size_t)p.lay.total_slots * sizeof(float) * (mode == 2 ? 2 : 1);
+    const size_t smem_bytes = (size_t)p.lay.total_slots * sizeof(float);
     if (plan_only) return smem_bytes <= 227 * 1024 ? 0 : 1;
     MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
     if (smem_bytes > (size_t)dp->smem_optin) return 1;

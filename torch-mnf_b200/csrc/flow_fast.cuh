@@ -1,34 +1,49 @@
-// flow_fast.cu -- register-resident flow-stack kernel for 2-D points (BASELINE configs 1, 2).
+// flow_fast.cuh -- register-resident flow-stack kernel for 2-D points (BASELINE configs 1, 2).
 //
-// Whole stack in one launch: a thread owns TWO points as an fp32x2 pair, keeps both points and
-// their log-dets in registers across every flow, and evaluates the coupling conditioners
-// (MLP 1 -> H -> H -> H -> n_out, LeakyReLU 0.2) fully unrolled with the weights broadcast
-// from shared memory (staged once per CTA; the grid is persistent, a multiple of the SM
-// count).  The two points share every weight load and are multiplied with Blackwell's packed
-// FFMA2 (fma.rn.f32x2).  HBM traffic is the algorithmic minimum: 8 B in, 8 B out, 4 B log-det
-// per point (+4 B when the fused base log-density is requested).
+// Whole stack in one launch: a thread owns TWO points, keeps both points and their log-dets in
+// registers across every flow, and evaluates the coupling conditioners (MLP 1 -> H -> H -> H ->
+// n_out, LeakyReLU 0.2) fully unrolled with the weights broadcast from shared memory (staged
+// once per CTA; the grid is persistent, a multiple of the SM count).  The two points share every
+// weight load; the multiplies use Blackwell's packed FFMA2 (fma.rn.f32x2).  HBM traffic is the
+// algorithmic minimum: 8 B in, 8 B out, 4 B log-det per point (+4 B for the fused base
+// log-density).
 //
 // Supported ops (all with dim == 2): AffineConstantFlow/ActNormFlow, Glow, AffineHalfFlow with
 // h_sizes (H,H,H), NSF_CL with n_h = H and K bins.  Anything else -> flow_generic.cu.
 //
-// MODE selects how the packed multiply gets its (w,w) operand:
-//   0: scalar FFMA (two per weight), plain smem      1: FFMA2, pair built with a MOV
-//   2: FFMA2, weights stored duplicated in smem (one LDS.128 = two ready pairs)
+// VARIANT selects how the MLP is mapped onto the packed FMA:
+//   0: point-packed, scalar FFMA (two per weight)           -- reference variant
+//   1: point-packed FFMA2, (w,w) operand built with a MOV per weight
+//   2: output-packed FFMA2: weights stored transposed ([in][out]) so one LDS.128 delivers two
+//      ready (w_j, w_j+1) operands; the activation is duplicated once per input instead
 #pragma once
 #include "flow_math.cuh"
 
 namespace mnf {
+
+#ifndef MNF_SPLINE_FAST
+#define MNF_SPLINE_FAST 1
+#endif
 
 struct FlowProgram {
     int n_ops;
     mnf_flow_op ops[MNF_MAX_OPS];
 };
 
-// shared-memory offsets (in weight slots) of each op's nets, computed on the host
+// shared-memory offsets (in floats) of each op's nets, computed on the host
 struct FastLayout {
     int net_slot[MNF_MAX_OPS][2];
     int total_slots;
 };
+
+constexpr int round4(int n) { return (n + 3) / 4 * 4; }
+
+// floats one staged net occupies in shared memory
+constexpr int fast_net_slots(int H, int n_out, int variant) {
+    const int hidden = 2 * H + 2 * (H * H + H);
+    if (variant == 2) return hidden + (n_out == 1 ? H + 4 : H * round4(n_out) + round4(n_out));
+    return hidden + n_out * H + round4(n_out);
+}
 
 __device__ __forceinline__ float2 fma2_packed(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
@@ -38,78 +53,66 @@ __device__ __forceinline__ float2 fma2_packed(float2 a, float2 b, float2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
     return *reinterpret_cast<float2 *>(&rd);
 }
+__device__ __forceinline__ float2 mul2_packed(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
 
-template <int MODE>
+template <int VARIANT>
 __device__ __forceinline__ float2 fma2(float2 w, float2 x, float2 c) {
-    if constexpr (MODE == 0)
+    if constexpr (VARIANT == 0)
         return make_float2(fmaf(w.x, x.x, c.x), fmaf(w.y, x.y, c.y));
     else
         return fma2_packed(w, x, c);
 }
 
-__device__ __forceinline__ float2 leaky2(float2 v) { return make_float2(leaky02(v.x), leaky02(v.y)); }
+__device__ __forceinline__ float2 leaky2(float2 v) {
+    const float2 s = mul2_packed(v, make_float2(0.2f, 0.2f));
+    return make_float2(fmaxf(v.x, s.x), fmaxf(v.y, s.y));
+}
 
-// Weight slot accessors.  Slot i of a net holds weight i; in MODE 2 a slot is a float2 (w,w).
-template <int MODE>
-struct Wts {
-    const float *base;
-    // four consecutive slots starting at compile-time-constant i (multiple of 4 relative to an
-    // aligned net start), as four (w,w) pairs
-    __device__ __forceinline__ void load4(int i, float2 (&w)[4]) const {
-        if constexpr (MODE == 2) {
-            const float4 *p = reinterpret_cast<const float4 *>(base) + (i >> 1);
-            const float4 a = p[0], b = p[1];
-            w[0] = make_float2(a.x, a.y);
-            w[1] = make_float2(a.z, a.w);
-            w[2] = make_float2(b.x, b.y);
-            w[3] = make_float2(b.z, b.w);
-        } else {
-            const float4 a = reinterpret_cast<const float4 *>(base)[i >> 2];
-            w[0] = make_float2(a.x, a.x);
-            w[1] = make_float2(a.y, a.y);
-            w[2] = make_float2(a.z, a.z);
-            w[3] = make_float2(a.w, a.w);
-        }
-    }
-    __device__ __forceinline__ float2 load1(int i) const {
-        if constexpr (MODE == 2) return reinterpret_cast<const float2 *>(base)[i];
-        const float w = base[i];
-        return make_float2(w, w);
-    }
-};
+__device__ __forceinline__ float4 lds4(const float *base, int i) {  // i: compile-time multiple of 4
+    return reinterpret_cast<const float4 *>(base)[i >> 2];
+}
 
-// Hidden part of the conditioner for a scalar input: 1 -> H -> H -> H.  Result in h.
-template <int H, int MODE>
-__device__ __forceinline__ void mlp_hidden3(const Wts<MODE> W, float2 x, float2 (&h)[H]) {
+// =====================================================================================
+// point-packed engine (variants 0, 1): float2 = (value for point A, value for point B)
+// smem net layout = blob layout: per Linear weight[out][in], bias[out]
+// =====================================================================================
+template <int H, int VARIANT>
+__device__ __forceinline__ void pp_hidden(const float *W, float2 x, float2 (&h)[H]) {
     static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
     float2 g[H];
-    // layer 0: weight[H][1], bias[H]
 #pragma unroll
-    for (int j = 0; j < H; j += 4) {
-        float2 w[4], b[4];
-        W.load4(j, w);
-        W.load4(H + j, b);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) g[j + u] = leaky2(fma2<MODE>(w[u], x, b[u]));
+    for (int j = 0; j < H; j += 4) {  // layer 0: weight[H][1], bias[H]
+        const float4 w = lds4(W, j), b = lds4(W, H + j);
+        g[j + 0] = leaky2(fma2<VARIANT>(make_float2(w.x, w.x), x, make_float2(b.x, b.x)));
+        g[j + 1] = leaky2(fma2<VARIANT>(make_float2(w.y, w.y), x, make_float2(b.y, b.y)));
+        g[j + 2] = leaky2(fma2<VARIANT>(make_float2(w.z, w.z), x, make_float2(b.z, b.z)));
+        g[j + 3] = leaky2(fma2<VARIANT>(make_float2(w.w, w.w), x, make_float2(b.w, b.w)));
     }
-    // layers 1, 2: weight[H][H], bias[H]
 #pragma unroll
-    for (int layer = 0; layer < 2; ++layer) {
+    for (int layer = 0; layer < 2; ++layer) {  // layers 1, 2: weight[H][H], bias[H]
         const int wo = 2 * H + layer * (H * H + H);
         float2(&src)[H] = layer == 0 ? g : h;
         float2(&dst)[H] = layer == 0 ? h : g;
 #pragma unroll
         for (int j = 0; j < H; j += 4) {
-            float2 acc[4];
-            W.load4(wo + H * H + j, acc);
+            const float4 b = lds4(W, wo + H * H + j);
+            float2 acc[4] = {make_float2(b.x, b.x), make_float2(b.y, b.y), make_float2(b.z, b.z),
+                             make_float2(b.w, b.w)};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
 #pragma unroll
                 for (int i = 0; i < H; i += 4) {
-                    float2 w[4];
-                    W.load4(wo + (j + u) * H + i, w);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[u] = fma2<MODE>(w[q], src[i + q], acc[u]);
+                    const float4 w = lds4(W, wo + (j + u) * H + i);
+                    acc[u] = fma2<VARIANT>(make_float2(w.x, w.x), src[i + 0], acc[u]);
+                    acc[u] = fma2<VARIANT>(make_float2(w.y, w.y), src[i + 1], acc[u]);
+                    acc[u] = fma2<VARIANT>(make_float2(w.z, w.z), src[i + 2], acc[u]);
+                    acc[u] = fma2<VARIANT>(make_float2(w.w, w.w), src[i + 3], acc[u]);
                 }
             }
 #pragma unroll
@@ -120,76 +123,212 @@ __device__ __forceinline__ void mlp_hidden3(const Wts<MODE> W, float2 x, float2 
     for (int j = 0; j < H; ++j) h[j] = g[j];
 }
 
-// Last Linear layer: n_out outputs from the H hidden units.
-template <int H, int NO, int MODE>
-__device__ __forceinline__ void mlp_last(const Wts<MODE> W, const float2 (&h)[H], float2 (&out)[NO]) {
+template <int H, int NO, int VARIANT>
+__device__ __forceinline__ void pp_last(const float *W, const float2 (&h)[H], float2 (&out)[NO]) {
     const int wo = 2 * H + 2 * (H * H + H);
 #pragma unroll
     for (int j = 0; j < NO; ++j) {
-        float2 acc = W.load1(wo + NO * H + j);
+        const float b = W[wo + NO * H + j];
+        float2 acc = make_float2(b, b);
 #pragma unroll
         for (int i = 0; i < H; i += 4) {
-            float2 w[4];
-            W.load4(wo + j * H + i, w);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc = fma2<MODE>(w[q], h[i + q], acc);
+            const float4 w = lds4(W, wo + j * H + i);
+            acc = fma2<VARIANT>(make_float2(w.x, w.x), h[i + 0], acc);
+            acc = fma2<VARIANT>(make_float2(w.y, w.y), h[i + 1], acc);
+            acc = fma2<VARIANT>(make_float2(w.z, w.z), h[i + 2], acc);
+            acc = fma2<VARIANT>(make_float2(w.w, w.w), h[i + 3], acc);
         }
         out[j] = acc;
     }
 }
 
-template <int H>
-constexpr int net_slots(int n_out) {
-    return 2 * H + 2 * (H * H + H) + n_out * H + ((n_out + 3) / 4) * 4;
+// =====================================================================================
+// output-packed engine (variant 2): float2 = (unit j, unit j+1) of ONE point; two points A, B
+// smem net layout: w0[H] b0[H] | Wt1[in][out] b1[H] | Wt2[in][out] b2[H] | Wt3[in][NOP] b3[NOP]
+// (n_out == 1: w3[H] b3[4])
+// =====================================================================================
+template <int H, int NOUT2>
+__device__ __forceinline__ void op_dense(const float *Wt, const float *bias, const float2 (&inA)[H / 2],
+                                         const float2 (&inB)[H / 2], float2 (&outA)[NOUT2],
+                                         float2 (&outB)[NOUT2]) {
+    // out[j] = bias[j] + sum_i Wt[i][j] * in[i]; NOUT2 pairs of outputs, row stride 2*NOUT2
+#pragma unroll
+    for (int j = 0; j < NOUT2; j += 2) {
+        const float4 b = lds4(bias, 2 * j);
+        outA[j] = outB[j] = make_float2(b.x, b.y);
+        if (j + 1 < NOUT2) outA[j + 1] = outB[j + 1] = make_float2(b.z, b.w);
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const float a = (i & 1) ? inA[i >> 1].y : inA[i >> 1].x;
+        const float b = (i & 1) ? inB[i >> 1].y : inB[i >> 1].x;
+        const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+#pragma unroll
+        for (int j = 0; j < NOUT2; j += 2) {
+            const float4 w = lds4(Wt, i * 2 * NOUT2 + 2 * j);
+            outA[j] = fma2_packed(make_float2(w.x, w.y), aa, outA[j]);
+            outB[j] = fma2_packed(make_float2(w.x, w.y), bb, outB[j]);
+            if (j + 1 < NOUT2) {
+                outA[j + 1] = fma2_packed(make_float2(w.z, w.w), aa, outA[j + 1]);
+                outB[j + 1] = fma2_packed(make_float2(w.z, w.w), bb, outB[j + 1]);
+            }
+        }
+    }
 }
 
-// conditioner on `cond`, spline on `trans` (both points of the pair)
-template <int H, int K, int MODE>
-__device__ __forceinline__ void spline_half(const Wts<MODE> W, const mnf_flow_op &op, float2 cond, float2 &trans,
+template <int H>
+__device__ __forceinline__ void op_hidden(const float *W, float xA, float xB, float2 (&hA)[H / 2],
+                                          float2 (&hB)[H / 2]) {
+    static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
+    float2 gA[H / 2], gB[H / 2];
+    const float2 xa = make_float2(xA, xA), xb = make_float2(xB, xB);
+#pragma unroll
+    for (int j = 0; j < H / 2; j += 2) {  // layer 0
+        const float4 w = lds4(W, 2 * j), b = lds4(W, H + 2 * j);
+        gA[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xa, make_float2(b.x, b.y)));
+        gB[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xb, make_float2(b.x, b.y)));
+        gA[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xa, make_float2(b.z, b.w)));
+        gB[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xb, make_float2(b.z, b.w)));
+    }
+    const int l1 = 2 * H, l2 = 2 * H + H * H + H;
+    op_dense<H, H / 2>(W + l1, W + l1 + H * H, gA, gB, hA, hB);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+        hA[j] = leaky2(hA[j]);
+        hB[j] = leaky2(hB[j]);
+    }
+    op_dense<H, H / 2>(W + l2, W + l2 + H * H, hA, hB, gA, gB);
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+        hA[j] = leaky2(gA[j]);
+        hB[j] = leaky2(gB[j]);
+    }
+}
+
+// single output (AffineHalfFlow s / t): dot product packed over input pairs
+template <int H>
+__device__ __forceinline__ void op_last1(const float *W, const float2 (&hA)[H / 2], const float2 (&hB)[H / 2],
+                                         float &oA, float &oB) {
+    const int wo = 2 * H + 2 * (H * H + H);
+    float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < H / 2; i += 2) {
+        const float4 w = lds4(W, wo + 2 * i);
+        accA = fma2_packed(make_float2(w.x, w.y), hA[i], accA);
+        accB = fma2_packed(make_float2(w.x, w.y), hB[i], accB);
+        accA = fma2_packed(make_float2(w.z, w.w), hA[i + 1], accA);
+        accB = fma2_packed(make_float2(w.z, w.w), hB[i + 1], accB);
+    }
+    const float b = W[wo + H];
+    oA = (accA.x + accA.y) + b;
+    oB = (accB.x + accB.y) + b;
+}
+
+// =====================================================================================
+// conditioner -> spline for both points
+// =====================================================================================
+template <int H, int K, int VARIANT>
+__device__ __forceinline__ void spline_half(const float *W, const mnf_flow_op &op, float2 cond, float2 &trans,
                                             bool rqs_inverse, float2 &ld) {
     constexpr int NB = 3 * K - 1;
-    float2 raw2[NB];
-    {
-        float2 h[H];
-        mlp_hidden3<H, MODE>(W, cond, h);
-        mlp_last<H, NB, MODE>(W, h, raw2);
-    }
+    constexpr bool FAST = MNF_SPLINE_FAST != 0;
+    if constexpr (VARIANT == 2) {
+        constexpr int NP2 = round4(NB) / 2;
+        float2 rA[NP2], rB[NP2];
+        {
+            float2 hA[H / 2], hB[H / 2];
+            op_hidden<H>(W, cond.x, cond.y, hA, hB);
+            const int wo = 2 * H + 2 * (H * H + H);
+            op_dense<H, NP2>(W + wo, W + wo + H * 2 * NP2, hA, hB, rA, rB);
+        }
 #pragma unroll 1
-    for (int pt = 0; pt < 2; ++pt) {
-        float raw[NB];
+        for (int pt = 0; pt < 2; ++pt) {
+            float raw[NB];
 #pragma unroll
-        for (int o = 0; o < NB; ++o) raw[o] = pt ? raw2[o].y : raw2[o].x;
-        float v = pt ? trans.y : trans.x;
-        float l = 0.f;
-        rq_spline<K>(raw, K, op.bound, op.edge_deriv, rqs_inverse, v, l);
-        if (pt) { trans.y = v; ld.y += l; } else { trans.x = v; ld.x += l; }
+            for (int o = 0; o < NB; ++o) {
+                const float2 q = pt ? rB[o >> 1] : rA[o >> 1];
+                raw[o] = (o & 1) ? q.y : q.x;
+            }
+            float v = pt ? trans.y : trans.x;
+            float l = 0.f;
+            rq_spline<K, FAST>(raw, K, op.bound, op.edge_deriv, rqs_inverse, v, l);
+            if (pt) { trans.y = v; ld.y += l; } else { trans.x = v; ld.x += l; }
+        }
+    } else {
+        float2 raw2[NB];
+        {
+            float2 h[H];
+            pp_hidden<H, VARIANT>(W, cond, h);
+            pp_last<H, NB, VARIANT>(W, h, raw2);
+        }
+#pragma unroll 1
+        for (int pt = 0; pt < 2; ++pt) {
+            float raw[NB];
+#pragma unroll
+            for (int o = 0; o < NB; ++o) raw[o] = pt ? raw2[o].y : raw2[o].x;
+            float v = pt ? trans.y : trans.x;
+            float l = 0.f;
+            rq_spline<K, FAST>(raw, K, op.bound, op.edge_deriv, rqs_inverse, v, l);
+            if (pt) { trans.y = v; ld.y += l; } else { trans.x = v; ld.x += l; }
+        }
     }
 }
 
-template <int H, int K, int MODE>
+// scalar-output conditioner (s or t of AffineHalfFlow) for both points
+template <int H, int VARIANT>
+__device__ __forceinline__ float2 affine_net(const float *W, float2 cond) {
+    if constexpr (VARIANT == 2) {
+        float2 hA[H / 2], hB[H / 2];
+        op_hidden<H>(W, cond.x, cond.y, hA, hB);
+        float2 o;
+        op_last1<H>(W, hA, hB, o.x, o.y);
+        return o;
+    } else {
+        float2 h[H], o[1];
+        pp_hidden<H, VARIANT>(W, cond, h);
+        pp_last<H, 1, VARIANT>(W, h, o);
+        return o[0];
+    }
+}
+
+// stage one net from the parameter blob into shared memory in the variant's layout
+template <int H, int VARIANT>
+__device__ __forceinline__ void stage_net(const float *__restrict__ src, float *dst, int n_out) {
+    const int hidden = 2 * H + 2 * (H * H + H);
+    const int n = hidden + n_out * H + n_out;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const float w = src[e];
+        int d = e;
+        if constexpr (VARIANT == 2) {
+            if (e >= 2 * H && e < hidden) {  // the two H x H layers: transpose weight blocks
+                const int r = (e - 2 * H) % (H * H + H), base = e - r;
+                if (r < H * H) d = base + (r % H) * H + (r / H);
+            } else if (e >= hidden && n_out > 1) {
+                const int nop = round4(n_out), r = e - hidden;
+                d = r < n_out * H ? hidden + (r % H) * nop + (r / H) : hidden + H * nop + (r - n_out * H);
+            }
+        }
+        dst[d] = w;
+    }
+}
+
+template <int H, int K, int VARIANT>
 __global__ void __launch_bounds__(128, 4)
 flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant__ FastLayout lay,
                  const float *__restrict__ params, const float *__restrict__ x, float *__restrict__ y,
                  float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
                  long long n_rows, int inverse) {
     extern __shared__ __align__(16) float smem[];
-    // ---- stage every net of the program into shared memory (once per CTA) ----
+    if constexpr (VARIANT == 2) {  // padding lanes of the last layers must read zeros
+        for (int e = threadIdx.x; e < lay.total_slots; e += blockDim.x) smem[e] = 0.f;
+        __syncthreads();
+    }
     for (int k = 0; k < prog.n_ops; ++k) {
         const mnf_flow_op &op = prog.ops[k];
         if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
-        const int n_out = op.sizes[op.n_lin];
-        const int n = 2 * H + 2 * (H * H + H) + n_out * H + n_out;
         for (int which = 0; which < 2; ++which) {
             if (op.type == MNF_OP_AFFINE_HALF && !(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
-            const float *src = params + op.net_off[which];
-            const int slot0 = lay.net_slot[k][which];
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const float w = src[i];
-                if constexpr (MODE == 2)
-                    reinterpret_cast<float2 *>(smem)[slot0 + i] = make_float2(w, w);
-                else
-                    smem[slot0 + i] = w;
-            }
+            stage_net<H, VARIANT>(params + op.net_off[which], smem + lay.net_slot[k][which], op.sizes[op.n_lin]);
         }
     }
     __syncthreads();
@@ -198,7 +337,7 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
     for (long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x; pair < n_pairs;
          pair += (long long)gridDim.x * blockDim.x) {
         const bool has_b = 2 * pair + 1 < n_rows;
-        float2 v0, v1;  // v0 = (x_A, x_B) first coordinate of both points, v1 = second coordinate
+        float2 v0, v1;  // v0 = first coordinate of points (A, B), v1 = second coordinate
         if (has_b) {
             const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
             v0 = make_float2(q.x, q.z);
@@ -210,6 +349,7 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
         }
         float2 ld = make_float2(0.f, 0.f);
 
+#pragma unroll 1
         for (int kk = 0; kk < prog.n_ops; ++kk) {
             const int k = inverse ? prog.n_ops - 1 - kk : kk;
             const mnf_flow_op &op = prog.ops[k];
@@ -247,11 +387,8 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
 #pragma unroll 1
                 for (int which = 0; which < 2; ++which) {
                     if (!(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
-                    Wts<MODE> W{smem + (MODE == 2 ? 2 : 1) * lay.net_slot[k][which]};
-                    float2 h[H], o[1];
-                    mlp_hidden3<H, MODE>(W, cond, h);
-                    mlp_last<H, 1, MODE>(W, h, o);
-                    if (which) st[1] = o[0]; else st[0] = o[0];
+                    const float2 o = affine_net<H, VARIANT>(smem + lay.net_slot[k][which], cond);
+                    if (which) st[1] = o; else st[0] = o;
                 }
                 const float2 s = st[0], t = st[1];
                 if (inverse) {  // affine_half_flow.py:54-56
@@ -271,10 +408,10 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
 #pragma unroll 1
                 for (int step = 0; step < 2; ++step) {
                     const bool use_f1 = (step == 0) != (inverse != 0);
-                    Wts<MODE> W{smem + (MODE == 2 ? 2 : 1) * lay.net_slot[k][use_f1 ? 0 : 1]};
+                    const float *W = smem + lay.net_slot[k][use_f1 ? 0 : 1];
                     const float2 cond = use_f1 ? v0 : v1;
                     float2 tr = use_f1 ? v1 : v0;
-                    spline_half<H, K, MODE>(W, op, cond, tr, inverse != 0, ld);
+                    spline_half<H, K, VARIANT>(W, op, cond, tr, inverse != 0, ld);
                     if (use_f1) v1 = tr; else v0 = tr;
                 }
             }
@@ -302,19 +439,25 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
     }
 }
 
-template <int H, int K, int MODE>
+template <int H, int K, int VARIANT>
 int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,
-                       const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows,
-                       int inverse, const DeviceProps *dp, cudaStream_t stream) {
-    auto kern = flow_fast_kernel<H, K, MODE>;
-    if (smem_bytes > 48 * 1024)
-        MNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    int occ = 0;
-    MNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem_bytes));
-    if (occ < 1) return fail(MNF_E_SHAPE, "flow_fast_kernel does not fit on an SM (smem %zu B)", smem_bytes);
+                const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows,
+                int inverse, const DeviceProps *dp, cudaStream_t stream) {
+    auto kern = flow_fast_kernel<H, K, VARIANT>;
+    static thread_local int occ_cache = -1;
+    static thread_local size_t occ_smem = 0;
+    if (occ_cache < 0 || occ_smem != smem_bytes) {
+        if (smem_bytes > 48 * 1024)
+            MNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int occ = 0;
+        MNF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem_bytes));
+        if (occ < 1) return fail(MNF_E_SHAPE, "flow_fast_kernel does not fit on an SM (smem %zu B)", smem_bytes);
+        occ_cache = occ;
+        occ_smem = smem_bytes;
+    }
     const long long n_pairs = (n_rows + 1) / 2;
     long long blocks = (n_pairs + 127) / 128;
-    const long long cap = (long long)dp->sm_count * occ;  // persistent: one wave, a multiple of the SM count
+    const long long cap = (long long)dp->sm_count * occ_cache;  // persistent: one wave, a multiple of the SM count
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, 128, smem_bytes, stream>>>(prog, lay, params, x, y, log_det, base_lp, inter, n_rows,
@@ -322,18 +465,17 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
     return launch_status("flow_fast_kernel");
 }
 
-
-#define MNF_FLOW_FAST_ARGS                                                                                     \
-    int mode, const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,          \
-        const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int inverse,   \
+#define MNF_FLOW_FAST_ARGS                                                                                    \
+    int variant, const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,      \
+        const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int inverse,  \
         const DeviceProps *dp, cudaStream_t stream
 
 #define MNF_FLOW_FAST_DEFINE(HH, KK)                                                                            \
     int launch_fast_##HH##_##KK(MNF_FLOW_FAST_ARGS) {                                                           \
-        if (mode == 0)                                                                                          \
+        if (variant == 0)                                                                                       \
             return launch_inst<HH, KK, 0>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, \
                                           inverse, dp, stream);                                                 \
-        if (mode == 1)                                                                                          \
+        if (variant == 1)                                                                                       \
             return launch_inst<HH, KK, 1>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, \
                                           inverse, dp, stream);                                                 \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \

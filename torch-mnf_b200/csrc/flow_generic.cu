@@ -131,7 +131,7 @@ __device__ void spline_block(const mnf_flow_op &op, const float *net_w, const fl
     const int n_out = op.sizes[op.n_lin];
     for (int j = 0; j < n_t; ++j) {
         for (int o = 0; o < nb; ++o) raw[o] = mlp_out(lw, width, n_out, a, j * nb + o);
-        rq_spline<0>(raw, op.K, op.bound, op.edge_deriv, rqs_inverse, trans[j], ld);
+        rq_spline<0, false>(raw, op.K, op.bound, op.edge_deriv, rqs_inverse, trans[j], ld);
     }
 }
 
@@ -169,7 +169,7 @@ __device__ void op_nsf_ar(const mnf_flow_op &op, const float *P, float *v, float
             for (int o = 0; o < nb; ++o) raw[o] = mlp_out(lw, width, nb, a, o);
             w += net_floats(sizes, op.n_lin);
         }
-        rq_spline<0>(raw, op.K, op.bound, op.edge_deriv, !inverse, x, ld);
+        rq_spline<0, false>(raw, op.K, op.bound, op.edge_deriv, !inverse, x, ld);
         out[i] = x;
     }
     for (int i = 0; i < D; ++i) v[i] = out[i];

@@ -20,17 +20,48 @@ __device__ __forceinline__ float leaky02(float x) { return fmaxf(x, 0.2f * x); }
 // F.softplus(beta=1, threshold=20)
 __device__ __forceinline__ float softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-// exp used inside the softmaxes.  MNF_FAST_EXP swaps in ex2.approx(x*log2e): arguments are
-// <= 0 after max subtraction and the terms that matter have |x| <= 2B.
-#ifdef MNF_FAST_EXP
-__device__ __forceinline__ float sm_exp(float x) { return exp2f(x * 1.4426950408889634f); }
-#else
-__device__ __forceinline__ float sm_exp(float x) { return expf(x); }
-#endif
+// Math flavour.  FAST = false: libdevice expf/logf/log1pf and IEEE division (generic
+// interpreter).  FAST = true (register-resident kernel): MUFU-based forms whose error stays
+// ~1e-6 relative on the ranges that occur here, an order below the 1e-5 parity tolerance:
+//   exp(x)      -> ex2.approx(x*log2e)      x <= 0 after max subtraction, |x| <= 2B where it matters
+//   a / b       -> a * rcp.approx(b)        (__fdividef, 2 ulp)
+//   log(n)-2log(d) -> lg2.approx(n * rcp(d)^2) * ln2   (one MUFU.LG2 instead of two)
+//   softplus(softplus(r)) -> log(2 + exp(r))           (exact identity below the threshold 20)
+template <bool FAST>
+__device__ __forceinline__ float sm_exp(float x) {
+    if constexpr (FAST) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+        return r;
+    } else {
+        return expf(x);
+    }
+}
+template <bool FAST>
+__device__ __forceinline__ float fdiv(float a, float b) {
+    if constexpr (FAST) return __fdividef(a, b);
+    else return a / b;
+}
+template <bool FAST>
+__device__ __forceinline__ float frcp(float a) {
+    if constexpr (FAST) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+        return r;
+    } else {
+        return 1.f / a;
+    }
+}
+// interior knot derivative: min_d + softplus(softplus(raw)) (spline_flow.py:256,104)
+template <bool FAST>
+__device__ __forceinline__ float knot_derivative(float r) {
+    if constexpr (FAST) return kMinDeriv + (r > 20.f ? r : __logf(2.f + __expf(r)));
+    else return kMinDeriv + softplus(softplus(r));
+}
 
 // knots[0..K] of one axis from K raw conditioner outputs: both softmaxes, floor, cumsum, pin.
 // KC > 0: compile-time K (registers); KC == 0: runtime K (local memory).
-template <int KC>
+template <int KC, bool FAST>
 __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, float *knots) {
     constexpr int KA = KC > 0 ? KC : MNF_MAX_BINS;
     const int Kn = KC > 0 ? KC : K;
@@ -41,21 +72,21 @@ __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, f
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < Kn; ++k) {
-        e[k] = sm_exp(raw[k] - m);
+        e[k] = sm_exp<FAST>(raw[k] - m);
         sum += e[k];
     }
     // first softmax scaled by 2B (spline_flow.py:254-255); its maximum element is 2B/sum
     const float twoB = 2.f * B;
-    const float inv = 1.f / sum;
+    const float inv = frcp<FAST>(sum);
     const float m2 = twoB * inv;  // e == 1 at the arg-max
     float sum2 = 0.f;
 #pragma unroll
     for (int k = 0; k < Kn; ++k) {
         const float w = twoB * (e[k] * inv);
-        e[k] = sm_exp(w - m2);  // second softmax (spline_flow.py:95)
+        e[k] = sm_exp<FAST>(w - m2);  // second softmax (spline_flow.py:95)
         sum2 += e[k];
     }
-    const float inv2 = 1.f / sum2;
+    const float inv2 = frcp<FAST>(sum2);
     const float span = 1.f - kMinBin * (float)Kn;
     float cum = 0.f;
     knots[0] = -B;
@@ -69,7 +100,7 @@ __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, f
 
 // One spline evaluation.  raw = [K widths | K heights | K-1 derivatives] as produced by the
 // conditioner.  Updates v in place and ADDS the log|det| contribution to ld.
-template <int KC>
+template <int KC, bool FAST = false>
 __device__ __forceinline__ void rq_spline(const float *raw, int K, float B, float edge_deriv, bool inverse,
                                           float &v, float &ld) {
     constexpr int KA = KC > 0 ? KC : MNF_MAX_BINS;
@@ -77,8 +108,8 @@ __device__ __forceinline__ void rq_spline(const float *raw, int K, float B, floa
     if (!(v >= -B && v <= B)) return;  // identity tails (also NaN), spline_flow.py:40,51-52
 
     float cw[KA + 1], ch[KA + 1];
-    spline_knots<KC>(raw, Kn, B, cw);
-    spline_knots<KC>(raw + Kn, Kn, B, ch);
+    spline_knots<KC, FAST>(raw, Kn, B, cw);
+    spline_knots<KC, FAST>(raw + Kn, Kn, B, ch);
 
     // bin search (spline_flow.py:22-24,115-118)
     const float *sk = inverse ? ch : cw;
@@ -104,9 +135,9 @@ __device__ __forceinline__ void rq_spline(const float *raw, int K, float B, floa
     const float hk = yk1 - yk;  // spline_flow.py:113
     // interior derivatives: min_d + softplus(softplus(raw)) (spline_flow.py:256,104); the two
     // boundary derivatives are the padded constant (:46-49)
-    const float dk = (idx > 0) ? kMinDeriv + softplus(softplus(r0)) : edge_deriv;
-    const float dk1 = (idx < Kn - 1) ? kMinDeriv + softplus(softplus(r1)) : edge_deriv;
-    const float sk_ = hk / wk;  // delta, spline_flow.py:123
+    const float dk = (idx > 0) ? knot_derivative<FAST>(r0) : edge_deriv;
+    const float dk1 = (idx < Kn - 1) ? knot_derivative<FAST>(r1) : edge_deriv;
+    const float sk_ = fdiv<FAST>(hk, wk);  // delta, spline_flow.py:123
     const float dsum = dk + dk1 - 2.f * sk_;
 
     if (inverse) {  // spline_flow.py:133-162
@@ -115,22 +146,33 @@ __device__ __forceinline__ void rq_spline(const float *raw, int K, float B, floa
         const float b = hk * dk - dy * dsum;
         const float c = -sk_ * dy;
         const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
-        const float root = (2.f * c) / (-b - sqrtf(disc));
+        const float root = fdiv<FAST>(2.f * c, -b - sqrtf(disc));
         v = root * wk + xk;
         const float tt = root * (1.f - root);
         const float den = sk_ + dsum * tt;
         const float omr = 1.f - root;
         const float num = (sk_ * sk_) * (dk1 * (root * root) + 2.f * sk_ * tt + dk * (omr * omr));
-        ld -= logf(num) - 2.f * logf(den);
+        if constexpr (FAST) {
+            const float rd = frcp<true>(den);
+            ld -= __logf(num * rd * rd);
+        } else {
+            ld -= logf(num) - 2.f * logf(den);
+        }
     } else {  // spline_flow.py:163-179
-        const float th = (v - xk) / wk;
+        const float th = fdiv<FAST>(v - xk, wk);
         const float tt = th * (1.f - th);
         const float numer = hk * (sk_ * (th * th) + dk * tt);
         const float den = sk_ + dsum * tt;
-        v = yk + numer / den;
         const float omt = 1.f - th;
         const float num = (sk_ * sk_) * (dk1 * (th * th) + 2.f * sk_ * tt + dk * (omt * omt));
-        ld += logf(num) - 2.f * logf(den);
+        if constexpr (FAST) {
+            const float rd = frcp<true>(den);
+            v = fmaf(numer, rd, yk);
+            ld += __logf(num * rd * rd);
+        } else {
+            v = yk + numer / den;
+            ld += logf(num) - 2.f * logf(den);
+        }
     }
 }
 

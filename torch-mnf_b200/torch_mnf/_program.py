@@ -107,6 +107,9 @@ class FlowProgram:
         self._blob = None
 
     def _build(self, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         key = _state_key(self.flows, device)
         if key == self._key:
             return
