@@ -88,7 +88,8 @@ typedef struct mnf_flow_op {
 /* Runs `n_ops` flows over `n_rows` points of dimension `dim`.
  *   ops_host     : host array of descriptors, in module order (flows[0] first).
  *   params       : device fp32 blob the offsets refer to, `n_params` floats.
- *   x            : input  [n_rows, dim];   y: output [n_rows, dim] (may alias x).
+ *   x            : input  [n_rows, dim];   y: output [n_rows, dim] (may alias x; NULL = do not
+ *                  store the transformed points, e.g. when only log-probabilities are wanted).
  *   log_det      : output [n_rows] -- sum of the flows' log|det J| (core.py:19,23).
  *   base_log_prob: optional output [n_rows]: standard-normal log-density of y
  *                  (NormalizingFlowModel.base_log_prob, core.py:46-49, for a N(0,I) base).
@@ -96,7 +97,9 @@ typedef struct mnf_flow_op {
  *                  execution order (core.py:20-25 returns them as a list).
  *   flags        : MNF_RUN_INVERSE = inverse direction (flows[n-1] first), else forward;
  *                  MNF_RUN_GENERIC forces the generic interpreter; MNF_RUN_VARIANT(v) picks a
- *                  code variant of the dim-2 kernel (tests / tuning; 0 = library default).
+ *                  code variant of the dim-2 kernel (tests / tuning; 0 = library default);
+ *                  MNF_RUN_LOGPROB makes base_log_prob receive log_det + base log-density, i.e.
+ *                  log p(x) of tests/test_flows.py:22-24 in one pass.
  * Replaces NormalizingFlow.forward/inverse (flows/core.py:17-35). */
 int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *params,
                        int64_t n_params, const float *x, float *y, float *log_det,
@@ -105,6 +108,7 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
 
 #define MNF_RUN_INVERSE 1
 #define MNF_RUN_GENERIC 2
+#define MNF_RUN_LOGPROB 4
 #define MNF_RUN_VARIANT_MASK 0x30
 #define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2} */
 

@@ -69,7 +69,7 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     if (plan_only) return smem_bytes <= 227 * 1024 ? 0 : 1;
     MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
     if (smem_bytes > (size_t)dp->smem_optin) return 1;
-    MNF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, MNF_E_ALIGN,
+    MNF_REQUIRE(((uintptr_t)x % 16) == 0 && (!y || ((uintptr_t)y % 16) == 0), MNF_E_ALIGN,
                 "x and y must be 16-byte aligned for the dim-2 kernel");
     MNF_REQUIRE(!log_det || ((uintptr_t)log_det % 8) == 0, MNF_E_ALIGN, "log_det must be 8-byte aligned");
     MNF_REQUIRE(!base_lp || ((uintptr_t)base_lp % 8) == 0, MNF_E_ALIGN, "base_log_prob must be 8-byte aligned");

@@ -317,8 +317,10 @@ __global__ void __launch_bounds__(128, 4)
 flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant__ FastLayout lay,
                  const float *__restrict__ params, const float *__restrict__ x, float *__restrict__ y,
                  float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
-                 long long n_rows, int inverse) {
+                 long long n_rows, int dir_flags) {
     extern __shared__ __align__(16) float smem[];
+    const int inverse = dir_flags & 1;
+    const bool sum_lp = dir_flags & 2;
     if constexpr (VARIANT == 2) {  // padding lanes of the last layers must read zeros
         for (int e = threadIdx.x; e < lay.total_slots; e += blockDim.x) smem[e] = 0.f;
         __syncthreads();
@@ -425,14 +427,15 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
         }
 
         const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
-        const float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
-                                      fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
+        float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
+                                fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
+        if (sum_lp) lp = make_float2(lp.x + ld.x, lp.y + ld.y);
         if (has_b) {
-            st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
+            if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
             if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
             if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
         } else {
-            st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
+            if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
             if (log_det) log_det[2 * pair] = ld.x;
             if (base_lp) base_lp[2 * pair] = lp.x;
         }

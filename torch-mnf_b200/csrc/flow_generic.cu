@@ -213,8 +213,10 @@ __global__ void __launch_bounds__(128)
 flow_generic_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params, int n_params,
                     int params_in_smem, const float *__restrict__ x, float *__restrict__ y,
                     float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
-                    long long n_rows, int D, int inverse) {
+                    long long n_rows, int D, int dir_flags) {
     extern __shared__ float smem[];
+    const int inverse = dir_flags & 1;
+    const bool sum_lp = dir_flags & 2;
     const float *P = params;
     if (params_in_smem) {
         for (int i = threadIdx.x; i < n_params; i += blockDim.x) smem[i] = params[i];
@@ -245,12 +247,14 @@ flow_generic_kernel(const __grid_constant__ FlowProgram prog, const float *__res
                 for (int d = 0; d < D; ++d) dst[d] = v[d];
             }
         }
-        for (int d = 0; d < D; ++d) y[row * D + d] = v[d];
+        if (y)
+            for (int d = 0; d < D; ++d) y[row * D + d] = v[d];
         if (log_det) log_det[row] = ld;
         if (base_lp) {
             float ss = 0.f;
             for (int d = 0; d < D; ++d) ss = fmaf(v[d], v[d], ss);
-            base_lp[row] = -0.5f * ss - 0.5f * (float)D * 1.8378770664093453f;  // log(2 pi)
+            const float lp = -0.5f * ss - 0.5f * (float)D * 1.8378770664093453f;  // log(2 pi)
+            base_lp[row] = sum_lp ? lp + ld : lp;
         }
     }
 }

@@ -103,12 +103,13 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
     int rc = validate_program(ops_host, n_ops, dim, n_params);
     if (rc) return rc;
     MNF_REQUIRE(n_rows >= 0, MNF_E_ARG, "n_rows=%lld is negative", (long long)n_rows);
-    MNF_REQUIRE((flags & ~(MNF_RUN_INVERSE | MNF_RUN_GENERIC | MNF_RUN_VARIANT_MASK)) == 0, MNF_E_ARG,
+    MNF_REQUIRE((flags & ~(MNF_RUN_INVERSE | MNF_RUN_GENERIC | MNF_RUN_LOGPROB | MNF_RUN_VARIANT_MASK)) == 0, MNF_E_ARG,
                 "unknown bits in flags=0x%x", flags);
-    const int inverse = flags & MNF_RUN_INVERSE;
+    const int inverse = (flags & MNF_RUN_INVERSE) | ((flags & MNF_RUN_LOGPROB) ? 2 : 0);  // bit1: sum into base_lp
     const int variant = ((flags & MNF_RUN_VARIANT_MASK) >> 4) - 1;  // -1 = library default
     if (n_rows == 0) return 0;
-    MNF_REQUIRE(x && y, MNF_E_ARG, "x / y is NULL");
+    MNF_REQUIRE(x != nullptr, MNF_E_ARG, "x is NULL");
+    MNF_REQUIRE(y || log_det || base_log_prob, MNF_E_ARG, "no output requested");
     MNF_REQUIRE(params || n_params == 0, MNF_E_ARG, "params is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & MNF_RUN_GENERIC)) {

@@ -22,7 +22,9 @@ MAX_OPS, MAX_LIN, MAX_DIM, MAX_HIDDEN, MAX_BINS = 32, 6, 64, 128, 32
 
 OP_AFFINE_CONST, OP_GLOW, OP_AFFINE_HALF, OP_NSF_CL, OP_NSF_AR, OP_MADE = 1, 2, 3, 4, 5, 6
 FLAG_PARITY, FLAG_SCALE, FLAG_SHIFT, FLAG_MADE_SEQ = 1, 2, 4, 8
-RUN_INVERSE, RUN_GENERIC = 1, 2
+RUN_INVERSE, RUN_GENERIC, RUN_LOGPROB = 1, 2, 4
+
+launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
 
 class FlowOp(C.Structure):

@@ -130,8 +130,10 @@ class FlowProgram:
 
     @torch.no_grad()
     def run(self, x, inverse: bool, want_inter: bool = False, want_base_lp: bool = False, out=None,
-            log_det=None, kernel=None):
-        """kernel: None = library default, "generic" = interpreter, 0/1/2 = dim-2 kernel variant."""
+            log_det=None, kernel=None, log_prob_only=False, log_prob_out=None):
+        """kernel: None = library default, "generic" = interpreter, 0/1/2 = dim-2 kernel variant.
+        log_prob_only: return (None, None, None, log_det + standard-normal log-density) without
+        storing the transformed points (single-chunk programs only)."""
         x = _lib.require_cuda_f32(x, "input")
         if x.dim() != 2:
             raise ValueError(f"flows take [batch, dim] inputs, got shape {tuple(x.shape)}")
@@ -139,10 +141,23 @@ class FlowProgram:
         dev = x.device
         self._build(dev)
         lib = _lib.lib()
+        n = self._n_ops
+        if log_prob_only and 0 < n <= _lib.MAX_OPS:
+            lp = log_prob_out if log_prob_out is not None else torch.empty(B, device=dev, dtype=torch.float32)
+            flags = (_lib.RUN_INVERSE if inverse else 0) | _lib.RUN_LOGPROB
+            if kernel == "generic":
+                flags |= _lib.RUN_GENERIC
+            elif kernel is not None:
+                flags |= ((int(kernel) + 1) << 4) & 0x30
+            with torch.cuda.device(dev):
+                rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
+                                            None, None, lp.data_ptr(), None, B, D, flags, _lib.stream_ptr(dev))
+            _lib.check(rc, "mnf_flow_stack_run")
+            _lib.launch_count += 1
+            return None, None, None, lp
         y = out if out is not None else torch.empty_like(x)
         ld = log_det if log_det is not None else torch.empty(B, device=dev, dtype=torch.float32)
         lp = torch.empty(B, device=dev, dtype=torch.float32) if want_base_lp else None
-        n = self._n_ops
         inter = torch.empty((n, B, D), device=dev, dtype=torch.float32) if want_inter else None
         if n == 0:
             y.copy_(x)
@@ -170,6 +185,7 @@ class FlowProgram:
                     inter[done:].data_ptr() if inter is not None else None, B, D, flags, stream,
                 )
                 _lib.check(rc, "mnf_flow_stack_run")
+                _lib.launch_count += 1
                 if not first:
                     ld += ld_chunk
                 first, src, done = False, y, done + cnt
