@@ -129,6 +129,84 @@ int mnf_glow_assemble(const float *P, const float *L, const float *U, const floa
 int mnf_actnorm_init(const float *x, int64_t n_rows, int dim, float *s, float *t, int do_s,
                      int do_t, double *workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * MNF layers.  Noise convention: every noise tensor pointer may be NULL, in which case the
+ * kernel draws from Philox4x32-10 keyed by `seed`, with `noise_stream` distinguishing the
+ * draws of one call and the GLOBAL element index (row_offset + local row) as counter, so a
+ * batch sharded over GPUs sees the same numbers as a single-device call.  Injected tensors
+ * follow the reference's draw order for parity tests.
+ * ---------------------------------------------------------------------------------- */
+
+/* z0 = q0_mean + sqrt(exp(q0_log_var)) * eps, eps ~ N(0,1) [n_rows, dim]
+ * (MNFLinear.sample_z mnf_linear.py:58-62; MNFConv2d.sample_z mnf_conv.py:80-84 with n_rows = 1). */
+int mnf_sample_z0(const float *q0_mean, const float *q0_log_var, const float *eps, uint64_t seed,
+                  uint32_t noise_stream, uint64_t row_offset, float *z, int64_t n_rows, int dim,
+                  void *stream);
+
+#define MNF_RNVP_MAX_NET 4
+/* One RNVP flow (flows/rnvp.py:19-23): net = MLP(dim, *h_sizes) (Linear/LeakyReLU(0.2), last
+ * activation dropped), t, s = Linear(h_sizes[-1], dim).  Device pointers, torch [out][in] layout. */
+typedef struct mnf_rnvp_flow {
+    int32_t n_net;                       /* Linear layers in `net` (= len(h_sizes))          */
+    int32_t net_sizes[MNF_RNVP_MAX_NET]; /* their output widths                               */
+    const float *net_w[MNF_RNVP_MAX_NET];
+    const float *net_b[MNF_RNVP_MAX_NET];
+    const float *t_w, *t_b, *s_w, *s_b;
+} mnf_rnvp_flow;
+
+/* NormalizingFlow([RNVP...]).forward (core.py:17-25 over rnvp.py:25-39), in place on z [n_rows, dim]:
+ *   mask ~ Bernoulli(.5); y = net(mask*z); g = sigmoid(s(y)); z <- (1-mask) z g + (1-g) t(y) + mask z;
+ *   log_det[r] = sum over flows and dims of (1-mask) log g   (written, not accumulated).
+ * masks_host: host array of n_flows device pointers [n_rows, dim] of 0/1 floats, or NULL (Philox,
+ * flow f uses noise stream first_noise_stream + f).  workspace: 2 * n_rows * max(net_sizes) floats.
+ * intermediates: optional [n_flows, n_rows, dim]. */
+int mnf_rnvp_forward(const mnf_rnvp_flow *flows_host, int n_flows, float *z, float *log_det,
+                     const float *const *masks_host, uint64_t seed, uint32_t first_noise_stream,
+                     uint64_t row_offset, int64_t n_rows, int dim, float *workspace,
+                     float *intermediates, void *stream);
+
+/* MNFLinear.forward after sample_z (mnf_linear.py:46-56):
+ *   out = (x*z) W_mean^T + b_mean + sqrt(x^2 exp(W_log_var)^T + exp(b_log_var)) * eps
+ * x: [x_rows, n_in]; output row r reads x[r % x_rows], i.e. x.repeat(n_rows / x_rows, 1) without
+ * materialising it (Monte-Carlo replication, mnf_mnist.ipynb:316-318).  z: [n_rows, n_in],
+ * eps: [n_rows, n_out] or NULL, out: [n_rows, n_out]; relu = 1 applies the nn.ReLU that follows
+ * the layer in MNFLeNet / MNFFeedForward in the epilogue. */
+int mnf_linear_forward(const float *x, int64_t x_rows, const float *z, const float *W_mean,
+                       const float *W_log_var, const float *b_mean, const float *b_log_var,
+                       const float *eps, uint64_t seed, uint32_t noise_stream, uint64_t row_offset,
+                       float *out, int64_t n_rows, int n_in, int n_out, int relu, void *stream);
+
+/* MNFConv2d.forward after sample_z (mnf_conv.py:67-78), stride 1, no padding, NCHW:
+ *   out = conv2d(x, W_mean * z[:,None,None,None]) + sqrt(conv2d(x^2, exp(W_log_var)) + exp(b_log_var)) * eps
+ * x: [x_imgs, c_in, H, W], image r reads x[r % x_imgs]; z: [c_out] (one draw shared by the batch);
+ * eps: [n_imgs, c_out, OH, OW] or NULL.  relu_pool = 1 fuses the nn.ReLU + nn.MaxPool2d(2) that
+ * follow each MNFConv2d in MNFLeNet (mnf_lenet.py:16-21): out is then [n_imgs, c_out, OH/2, OW/2]. */
+int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const float *W_mean,
+                       const float *W_log_var, const float *b_log_var, const float *eps, uint64_t seed,
+                       uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_imgs, int c_in,
+                       int height, int width, int c_out, int ksize, int relu_pool, void *stream);
+
+/* Weight-space part of MNFLinear.kl_div (mnf_linear.py:66-90, conv = 0) and MNFConv2d.kl_div
+ * (mnf_conv.py:90-133, conv = 1).  z / ld_q come from sample_z (flow_q), zT / ld_r from
+ * flow_r.forward(z); both are produced by mnf_rnvp_forward with one row.  out[0] is the KL
+ * estimate; out[1..4] = kl_W, kl_b, log_q, log_r.  workspace: 2 * max(n_out, n_in*k*k) floats. */
+typedef struct mnf_kl_args {
+    int32_t conv, n_out, n_in, ksize; /* linear: ksize = 1                                     */
+    const float *W_mean, *W_log_var;  /* [n_out, n_in, k, k]                                   */
+    const float *b_mean;              /* linear only (conv: the reference's b_mean is zero)    */
+    const float *b_log_var;           /* [n_out]                                               */
+    const float *q0_log_var, *r0_c, *r0_b1, *r0_b2; /* [n_in] linear / [n_out] conv            */
+    const float *z, *zT;              /* [n_in] linear / [n_out] conv                          */
+    const float *ld_q, *ld_r;         /* device scalars                                        */
+    const float *eps_w;               /* linear: [n_out, n_in]; conv: [n_in*k*k]; NULL = Philox */
+    const float *eps_b;               /* conv: scalar; NULL = Philox                           */
+    uint64_t seed;
+    uint32_t noise_stream;
+    float *workspace;
+    float *out;                       /* [5]                                                   */
+} mnf_kl_args;
+int mnf_kl_div(const mnf_kl_args *args_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,256 @@
+"""Host-side wrappers of the MNF entry points of libmnf_b200.so (include/mnf_b200.h):
+noise bookkeeping (injected tape or in-kernel Philox), RNVP stacks, and the struct marshalling."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+RNVP_MAX_NET = 4
+_vp, _u64, _u32, _i64, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int
+
+
+class RnvpFlow(C.Structure):
+    """struct mnf_rnvp_flow."""
+
+    _fields_ = [
+        ("n_net", C.c_int32),
+        ("net_sizes", C.c_int32 * RNVP_MAX_NET),
+        ("net_w", C.c_void_p * RNVP_MAX_NET),
+        ("net_b", C.c_void_p * RNVP_MAX_NET),
+        ("t_w", C.c_void_p), ("t_b", C.c_void_p), ("s_w", C.c_void_p), ("s_b", C.c_void_p),
+    ]
+
+
+class KlArgs(C.Structure):
+    """struct mnf_kl_args."""
+
+    _fields_ = [
+        ("conv", C.c_int32), ("n_out", C.c_int32), ("n_in", C.c_int32), ("ksize", C.c_int32),
+        ("W_mean", _vp), ("W_log_var", _vp), ("b_mean", _vp), ("b_log_var", _vp),
+        ("q0_log_var", _vp), ("r0_c", _vp), ("r0_b1", _vp), ("r0_b2", _vp),
+        ("z", _vp), ("zT", _vp), ("ld_q", _vp), ("ld_r", _vp), ("eps_w", _vp), ("eps_b", _vp),
+        ("seed", C.c_uint64), ("noise_stream", C.c_uint32),
+        ("workspace", _vp), ("out", _vp),
+    ]
+
+
+_lib.register({
+    "mnf_sample_z0": (_int, [_vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _vp]),
+    "mnf_rnvp_forward": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64,
+                                _i64, _int, _vp, _vp, _vp]),
+    "mnf_linear_forward": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int,
+                                  _int, _int, _vp]),
+    "mnf_conv2d_forward": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int,
+                                  _int, _int, _int, _int, _vp]),
+    "mnf_kl_div": (_int, [C.POINTER(KlArgs), _vp]),
+})
+
+
+class Noise:
+    """Noise source of ONE layer call.  With a tape (any object with ``normal(shape)`` /
+    ``bernoulli(shape)``, e.g. oracle.noise.NoiseTape) every draw is taken from it in the
+    reference's order; without one the kernels draw from Philox and ``draw`` only hands out the
+    per-draw stream ids."""
+
+    def __init__(self, tape, device, row_offset: int = 0, seed: int | None = None):
+        self.tape, self.device, self.row_offset = tape, device, int(row_offset)
+        self.streams = 0
+        if tape is None and seed is None:
+            seed = int(torch.randint(0, 2**62, (1,)).item())  # follows torch.manual_seed
+        self.seed = seed or 0
+        self.keep = []  # injected tensors must outlive the asynchronous launches
+
+    def _next_stream(self):
+        s = self.streams
+        self.streams += 1
+        return s
+
+    def normal(self, shape):
+        """-> (device tensor or None, noise stream id)."""
+        sid = self._next_stream()
+        if self.tape is None:
+            return None, sid
+        t = self.tape.normal(tuple(shape)).to(self.device, torch.float32).contiguous()
+        self.keep.append(t)
+        return t, sid
+
+    def bernoulli(self, shape):
+        sid = self._next_stream()
+        if self.tape is None:
+            return None, sid
+        t = self.tape.bernoulli(tuple(shape)).to(self.device, torch.float32).contiguous()
+        self.keep.append(t)
+        return t, sid
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _param(t, device, name):
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device} but the input is on {device}")
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def sample_z0(q0_mean, q0_log_var, n_rows, noise: Noise):
+    dev = noise.device
+    dim = q0_mean.numel()
+    eps, sid = noise.normal((n_rows, dim) if n_rows != -1 else (dim,))
+    rows = max(n_rows, 1)
+    z = torch.empty((rows, dim), device=dev, dtype=torch.float32)
+    qm, qv = _param(q0_mean, dev, "q0_mean"), _param(q0_log_var, dev, "q0_log_var")
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mnf_sample_z0(qm.data_ptr(), qv.data_ptr(), _p(eps), noise.seed, sid, noise.row_offset,
+                                      z.data_ptr(), rows, dim, _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_sample_z0")
+    _lib.launch_count += 1
+    return z
+
+
+def _rnvp_struct(flow, dev, keep):
+    lin = flow.net.linears()
+    if len(lin) > RNVP_MAX_NET:
+        raise ValueError(f"RNVP conditioner with {len(lin)} layers; at most {RNVP_MAX_NET} supported")
+    st = RnvpFlow()
+    st.n_net = len(lin)
+    for i, m in enumerate(lin):
+        w, b = _param(m.weight, dev, "net.weight"), _param(m.bias, dev, "net.bias")
+        keep += [w, b]
+        st.net_sizes[i], st.net_w[i], st.net_b[i] = m.out_features, w.data_ptr(), b.data_ptr()
+    for name, mod in (("t", flow.t), ("s", flow.s)):
+        w, b = _param(mod.weight, dev, name + ".weight"), _param(mod.bias, dev, name + ".bias")
+        keep += [w, b]
+        setattr(st, name + "_w", w.data_ptr())
+        setattr(st, name + "_b", b.data_ptr())
+    return st, max(m.out_features for m in lin)
+
+
+@torch.no_grad()
+def rnvp_stack_inplace(flows, z, noise: Noise, want_inter=False):
+    """Runs the RNVP flows in place on z [R, dim]; returns (log_det [R], intermediates or None)."""
+    dev = z.device
+    R, dim = z.shape
+    n = len(flows)
+    keep = []
+    structs, maxh = [], 1
+    for f in flows:
+        st, h = _rnvp_struct(f, dev, keep)
+        structs.append(st)
+        maxh = max(maxh, h)
+    arr = (RnvpFlow * max(n, 1))(*structs)
+    masks, first_sid = [], None
+    for _ in range(n):
+        m, sid = noise.bernoulli((R, dim))
+        masks.append(m)
+        first_sid = sid if first_sid is None else first_sid
+    mask_arr = None
+    if n and masks[0] is not None:
+        mask_arr = (C.c_void_p * n)(*[m.data_ptr() for m in masks])
+    ld = torch.empty(R, device=dev, dtype=torch.float32)
+    ws = torch.empty(2 * R * maxh, device=dev, dtype=torch.float32)
+    inter = torch.empty((n, R, dim), device=dev, dtype=torch.float32) if want_inter else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mnf_rnvp_forward(arr, n, z.data_ptr(), ld.data_ptr(), mask_arr, noise.seed, first_sid or 0,
+                                         noise.row_offset, R, dim, ws.data_ptr(), _p(inter), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_rnvp_forward")
+    _lib.launch_count += 2 * n
+    return ld, inter
+
+
+def rnvp_stack(flows, z, tape, want_inter):
+    """NormalizingFlow([RNVP...]).forward: returns (list incl. the input, log_det[B])."""
+    z = _lib.require_cuda_f32(z, "input")
+    noise = tape if isinstance(tape, Noise) else Noise(tape, z.device)
+    out = z.clone()
+    ld, inter = rnvp_stack_inplace(list(flows), out, noise, want_inter)
+    xs = [z] + (list(inter.unbind(0)) if inter is not None else [out])
+    return xs, ld
+
+
+@torch.no_grad()
+def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False):
+    dev = x.device
+    R = z.size(0)
+    n_in, n_out = layer.W_mean.shape[1], layer.W_mean.shape[0]
+    eps, sid = noise.normal((R, n_out))
+    out = torch.empty((R, n_out), device=dev, dtype=torch.float32)
+    args = [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
+                                           (layer.b_mean, "b_mean"), (layer.b_log_var, "b_log_var"))]
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mnf_linear_forward(x.data_ptr(), x_rows or x.size(0), z.data_ptr(), *(a.data_ptr() for a in args),
+                                           _p(eps), noise.seed, sid, noise.row_offset, out.data_ptr(), R, n_in, n_out,
+                                           int(relu), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_linear_forward")
+    _lib.launch_count += 1
+    return out
+
+
+@torch.no_grad()
+def conv_forward(layer, x, z, noise: Noise, n_imgs=None, relu_pool=False):
+    dev = x.device
+    x_imgs, c_in, H, W = x.shape
+    R = n_imgs or x_imgs
+    c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
+    OH, OW = H - ks + 1, W - ks + 1
+    eps, sid = noise.normal((R, c_out, OH, OW))
+    shape = (R, c_out, OH // 2, OW // 2) if relu_pool else (R, c_out, OH, OW)
+    out = torch.empty(shape, device=dev, dtype=torch.float32)
+    args = [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
+                                           (layer.b_log_var, "b_log_var"))]
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mnf_conv2d_forward(x.data_ptr(), x_imgs, z.data_ptr(), *(a.data_ptr() for a in args), _p(eps),
+                                           noise.seed, sid, noise.row_offset, out.data_ptr(), R, c_in, H, W, c_out, ks,
+                                           int(relu_pool), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_conv2d_forward")
+    _lib.launch_count += 1
+    return out
+
+
+@torch.no_grad()
+def kl_div(layer, conv: bool, tape=None):
+    """Shared driver of MNFLinear.kl_div / MNFConv2d.kl_div (draw order: SURVEY.md 8c)."""
+    dev = layer.W_mean.device
+    if dev.type != "cuda":
+        raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
+    noise = Noise(tape, dev)
+    n_out = layer.W_mean.shape[0]
+    n_in = layer.W_mean.shape[1]
+    ks = layer.W_mean.shape[2] if conv else 1
+    dim = n_out if conv else n_in
+    z = sample_z0(layer.q0_mean, layer.q0_log_var, -1 if conv else 1, noise)  # conv draws randn_like[n_out]
+    ld_q, _ = rnvp_stack_inplace(list(layer.flow_q.flows), z, noise)
+    fan = n_in * ks * ks
+    eps_w, sid = noise.normal((fan,) if conv else (n_out, n_in))
+    eps_b = None
+    if conv:
+        eps_b, _ = noise.normal(())
+    else:
+        noise._next_stream()  # keep stream numbering identical between the two layer kinds
+    zT = z.clone()
+    ld_r, _ = rnvp_stack_inplace(list(layer.flow_r.flows), zT, noise)
+    rows = max(n_out, fan)
+    ws = torch.empty(2 * rows, device=dev, dtype=torch.float32)
+    out = torch.empty(5, device=dev, dtype=torch.float32)
+    keep = [_param(getattr(layer, n), dev, n) for n in
+            ("W_mean", "W_log_var", "b_log_var", "q0_log_var", "r0_c", "r0_b1", "r0_b2")]
+    a = KlArgs()
+    a.conv, a.n_out, a.n_in, a.ksize = int(conv), n_out, n_in, ks
+    a.W_mean, a.W_log_var, a.b_log_var, a.q0_log_var, a.r0_c, a.r0_b1, a.r0_b2 = (t.data_ptr() for t in keep)
+    bm = None if conv else _param(layer.b_mean, dev, "b_mean")
+    a.b_mean = _p(bm)
+    a.z, a.zT, a.ld_q, a.ld_r = z.data_ptr(), zT.data_ptr(), ld_q.data_ptr(), ld_r.data_ptr()
+    a.eps_w, a.eps_b = _p(eps_w), _p(eps_b)
+    a.seed, a.noise_stream = noise.seed, sid
+    a.workspace, a.out = ws.data_ptr(), out.data_ptr()
+    with torch.cuda.device(dev):
+        rc = _lib.lib().mnf_kl_div(C.byref(a), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_kl_div")
+    _lib.launch_count += 2
+    layer.__dict__["_last_kl_terms"] = out  # kl, kl_W, kl_b, log_q, log_r
+    return out[0]

@@ -1,0 +1,46 @@
+"""Bayesian LeNet built from MNF layers (reference: models/mnf_lenet.py:8-32)."""
+
+from typing import Any
+
+import torch
+from torch import nn
+
+from .. import _lib
+from ..layers import MNFConv2d, MNFLinear
+from ..layers import _mnf_ops as ops
+
+
+class MNFLeNet(nn.Sequential):
+    """MNFConv2d(1,20,5) -> ReLU -> MaxPool2 -> MNFConv2d(20,50,5) -> ReLU -> MaxPool2 -> Flatten ->
+    MNFLinear(800,50) -> ReLU -> MNFLinear(50,10) -> LogSoftmax, with the reference's Sequential
+    indices (MNF layers at 0, 3, 7, 9) so its state_dict loads unchanged.
+
+    ``forward`` runs the CUDA pipeline: each conv kernel applies its noise, ReLU and 2x2 max-pool in
+    the epilogue (the un-pooled activations never reach HBM), the linear kernels fuse bias, noise and
+    ReLU.  ``noise`` injects a tape (16 draws in the reference's order); ``n_samples`` evaluates
+    ``forward(x.repeat(n_samples, 1, 1, 1))`` -- the Monte-Carlo prediction of mnf_mnist.ipynb:316-318
+    -- without materialising the repeat."""
+
+    def __init__(self, **kwargs: Any) -> None:
+        super().__init__(
+            MNFConv2d(1, 20, kernel_size=5, **kwargs), nn.ReLU(), nn.MaxPool2d(kernel_size=2),
+            MNFConv2d(20, 50, kernel_size=5, **kwargs), nn.ReLU(), nn.MaxPool2d(kernel_size=2),
+            nn.Flatten(),
+            MNFLinear(50 * 16, 50, **kwargs), nn.ReLU(),
+            MNFLinear(50, 10, **kwargs), nn.LogSoftmax(dim=-1),
+        )
+
+    def forward(self, x, noise=None, n_samples: int = 1, row_offset: int = 0, seed=None):
+        x = _lib.require_cuda_f32(x, "input")
+        R = x.size(0) * n_samples
+        nz = ops.Noise(noise, x.device, row_offset, seed=seed)
+        h = self[0].forward(x, nz, relu_pool=True, n_imgs=R)
+        h = self[3].forward(h, nz, relu_pool=True)
+        h = h.view(R, -1)
+        h = self[7].forward(h, nz, relu=True)
+        h = self[9].forward(h, nz)
+        return torch.log_softmax(h, dim=-1)
+
+    def kl_div(self, noise=None):
+        """Sum of the MNF layers' KL estimates (mnf_lenet.py:28-32)."""
+        return sum(layer.kl_div(noise) for layer in self if hasattr(layer, "kl_div"))
