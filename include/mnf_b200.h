@@ -95,6 +95,7 @@ typedef struct mnf_flow_op {
  *                  (NormalizingFlowModel.base_log_prob, core.py:46-49, for a N(0,I) base).
  *   intermediates: optional output [n_ops, n_rows, dim]: the output of every flow in
  *                  execution order (core.py:20-25 returns them as a list).
+ *   workspace    : mnf_flow_stack_workspace() floats of scratch (caller-owned), or NULL if that is 0.
  *   flags        : MNF_RUN_INVERSE = inverse direction (flows[n-1] first), else forward;
  *                  MNF_RUN_GENERIC forces the generic interpreter; MNF_RUN_VARIANT(v) picks a
  *                  code variant of the dim-2 kernel (tests / tuning; 0 = library default);
@@ -104,13 +105,18 @@ typedef struct mnf_flow_op {
 int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *params,
                        int64_t n_params, const float *x, float *y, float *log_det,
                        float *base_log_prob, float *intermediates, int64_t n_rows, int dim,
-                       int flags, void *stream);
+                       int flags, float *workspace, void *stream);
+
+/* Floats of scratch `workspace` must provide for a run of this shape (0 = none needed; NULL is then
+ * accepted).  The constant-bank variant of the dim-2 kernel parks points and log-dets there between
+ * stack segments. */
+int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 
 #define MNF_RUN_INVERSE 1
 #define MNF_RUN_GENERIC 2
 #define MNF_RUN_LOGPROB 4
-#define MNF_RUN_VARIANT_MASK 0x30
-#define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2} */
+#define MNF_RUN_VARIANT_MASK 0x70
+#define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2,3} */
 
 /* Which kernel mnf_flow_stack_run would pick: 0 = generic interpreter, 1 = specialised
  * D=2 register-resident kernel.  Host-only, no launch. */

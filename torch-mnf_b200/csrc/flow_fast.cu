@@ -55,20 +55,24 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
     return p;
 }
 
-constexpr int kDefaultVariant = 2;
+// default: constant-bank weights for large batches (3 segment launches + copies amortise), the
+// single-launch shared-memory variant for small ones
+constexpr long long kCbankMinRows = 1 << 16;
+constexpr int kNumVariants = 4;
 
 // returns 1 if the program is not eligible (caller falls back to the generic kernel)
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
-                     int variant, cudaStream_t stream, bool plan_only) {
-    const int mode = (variant >= 0 && variant <= 2) ? variant : kDefaultVariant;
-    const FastPlan p = plan_fast(ops, n_ops, dim, mode);
+                     int variant, float *workspace, cudaStream_t stream, bool plan_only) {
+    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows ? 3 : 2);
+    FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
+    if (mode == 3 && inter && (n_rows % 2)) return 1;
     const DeviceProps *dp = plan_only ? nullptr : device_props();
     const size_t smem_bytes = (size_t)p.lay.total_slots * sizeof(float);
-    if (plan_only) return smem_bytes <= 227 * 1024 ? 0 : 1;
+    if (plan_only) return (mode == 3 || smem_bytes <= 227 * 1024) ? 0 : 1;
     MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
-    if (smem_bytes > (size_t)dp->smem_optin) return 1;
+    if (mode != 3 && smem_bytes > (size_t)dp->smem_optin) return 1;
     MNF_REQUIRE(((uintptr_t)x % 16) == 0 && (!y || ((uintptr_t)y % 16) == 0), MNF_E_ALIGN,
                 "x and y must be 16-byte aligned for the dim-2 kernel");
     MNF_REQUIRE(!log_det || ((uintptr_t)log_det % 8) == 0, MNF_E_ALIGN, "log_det must be 8-byte aligned");
@@ -81,13 +85,13 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     (void)n_params;
     if (p.H == 16 && p.K == 8)
         return launch_fast_16_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                dp, stream);
+                                workspace, dp, stream);
     if (p.H == 24 && p.K == 8)
         return launch_fast_24_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                dp, stream);
+                                workspace, dp, stream);
     if (p.H == 8 && p.K == 5)
         return launch_fast_8_5(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                               dp, stream);
+                               workspace, dp, stream);
     return 1;
 }
 

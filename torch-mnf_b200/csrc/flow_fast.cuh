@@ -16,7 +16,12 @@
 //   1: point-packed FFMA2, (w,w) operand built with a MOV per weight
 //   2: output-packed FFMA2: weights stored transposed ([in][out]) so one LDS.128 delivers two
 //      ready (w_j, w_j+1) operands; the activation is duplicated once per input instead
+//   3: as 2, but the weights sit in the CONSTANT bank: they reach the FMA pipe through uniform
+//      registers (LDCU.128 -> FFMA2 R, R.F32, UR.F32x2, R), no shared-memory -> register-file
+//      traffic at all.  Needs the staged nets to fit in 64 KB (config 2: 23 KB).
 #pragma once
+#include <mutex>
+
 #include "flow_math.cuh"
 
 namespace mnf {
@@ -41,7 +46,7 @@ constexpr int round4(int n) { return (n + 3) / 4 * 4; }
 // floats one staged net occupies in shared memory
 constexpr int fast_net_slots(int H, int n_out, int variant) {
     const int hidden = 2 * H + 2 * (H * H + H);
-    if (variant == 2) return hidden + (n_out == 1 ? H + 4 : H * round4(n_out) + round4(n_out));
+    if (variant >= 2) return hidden + (n_out == 1 ? H + 4 : H * round4(n_out) + round4(n_out));
     return hidden + n_out * H + round4(n_out);
 }
 
@@ -77,6 +82,27 @@ __device__ __forceinline__ float2 leaky2(float2 v) {
 __device__ __forceinline__ float4 lds4(const float *base, int i) {  // i: compile-time multiple of 4
     return reinterpret_cast<const float4 *>(base)[i >> 2];
 }
+
+// constant-bank staging area of this translation unit's kernels (variant 3) and the global
+// scratch the nets are re-laid-out into before the device-to-device copy into the bank
+constexpr int kConstFloats = 16384 - 64;
+__constant__ float c_flow_w[kConstFloats];
+
+// weight accessors: offsets are in floats from the start of the staged net
+struct WShared {
+    const float *p;
+    __device__ __forceinline__ float4 ld4(int i) const { return reinterpret_cast<const float4 *>(p)[i >> 2]; }
+    __device__ __forceinline__ float ld1(int i) const { return p[i]; }
+};
+// constant-bank accessor with a COMPILE-TIME base: every load becomes LDCU c[0x3][imm] into uniform
+// registers (ptxas keeps a run-time base in vector registers and falls back to per-thread LDC)
+template <int BASE>
+struct WConstAt {
+    __device__ __forceinline__ float4 ld4(int i) const {
+        return reinterpret_cast<const float4 *>(c_flow_w)[(BASE + i) >> 2];
+    }
+    __device__ __forceinline__ float ld1(int i) const { return c_flow_w[BASE + i]; }
+};
 
 // =====================================================================================
 // point-packed engine (variants 0, 1): float2 = (value for point A, value for point B)
@@ -147,14 +173,14 @@ __device__ __forceinline__ void pp_last(const float *W, const float2 (&h)[H], fl
 // smem net layout: w0[H] b0[H] | Wt1[in][out] b1[H] | Wt2[in][out] b2[H] | Wt3[in][NOP] b3[NOP]
 // (n_out == 1: w3[H] b3[4])
 // =====================================================================================
-template <int H, int NOUT2>
-__device__ __forceinline__ void op_dense(const float *Wt, const float *bias, const float2 (&inA)[H / 2],
+template <int H, int NOUT2, class WT>
+__device__ __forceinline__ void op_dense(const WT W, int wt_off, int bias_off, const float2 (&inA)[H / 2],
                                          const float2 (&inB)[H / 2], float2 (&outA)[NOUT2],
                                          float2 (&outB)[NOUT2]) {
     // out[j] = bias[j] + sum_i Wt[i][j] * in[i]; NOUT2 pairs of outputs, row stride 2*NOUT2
 #pragma unroll
     for (int j = 0; j < NOUT2; j += 2) {
-        const float4 b = lds4(bias, 2 * j);
+        const float4 b = W.ld4(bias_off + 2 * j);
         outA[j] = outB[j] = make_float2(b.x, b.y);
         if (j + 1 < NOUT2) outA[j + 1] = outB[j + 1] = make_float2(b.z, b.w);
     }
@@ -165,7 +191,7 @@ __device__ __forceinline__ void op_dense(const float *Wt, const float *bias, con
         const float2 aa = make_float2(a, a), bb = make_float2(b, b);
 #pragma unroll
         for (int j = 0; j < NOUT2; j += 2) {
-            const float4 w = lds4(Wt, i * 2 * NOUT2 + 2 * j);
+            const float4 w = W.ld4(wt_off + i * 2 * NOUT2 + 2 * j);
             outA[j] = fma2_packed(make_float2(w.x, w.y), aa, outA[j]);
             outB[j] = fma2_packed(make_float2(w.x, w.y), bb, outB[j]);
             if (j + 1 < NOUT2) {
@@ -176,28 +202,28 @@ __device__ __forceinline__ void op_dense(const float *Wt, const float *bias, con
     }
 }
 
-template <int H>
-__device__ __forceinline__ void op_hidden(const float *W, float xA, float xB, float2 (&hA)[H / 2],
+template <int H, class WT>
+__device__ __forceinline__ void op_hidden(const WT W, float xA, float xB, float2 (&hA)[H / 2],
                                           float2 (&hB)[H / 2]) {
     static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
     float2 gA[H / 2], gB[H / 2];
     const float2 xa = make_float2(xA, xA), xb = make_float2(xB, xB);
 #pragma unroll
     for (int j = 0; j < H / 2; j += 2) {  // layer 0
-        const float4 w = lds4(W, 2 * j), b = lds4(W, H + 2 * j);
+        const float4 w = W.ld4(2 * j), b = W.ld4(H + 2 * j);
         gA[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xa, make_float2(b.x, b.y)));
         gB[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xb, make_float2(b.x, b.y)));
         gA[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xa, make_float2(b.z, b.w)));
         gB[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xb, make_float2(b.z, b.w)));
     }
     const int l1 = 2 * H, l2 = 2 * H + H * H + H;
-    op_dense<H, H / 2>(W + l1, W + l1 + H * H, gA, gB, hA, hB);
+    op_dense<H, H / 2>(W, l1, l1 + H * H, gA, gB, hA, hB);
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) {
         hA[j] = leaky2(hA[j]);
         hB[j] = leaky2(hB[j]);
     }
-    op_dense<H, H / 2>(W + l2, W + l2 + H * H, hA, hB, gA, gB);
+    op_dense<H, H / 2>(W, l2, l2 + H * H, hA, hB, gA, gB);
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) {
         hA[j] = leaky2(gA[j]);
@@ -206,20 +232,20 @@ __device__ __forceinline__ void op_hidden(const float *W, float xA, float xB, fl
 }
 
 // single output (AffineHalfFlow s / t): dot product packed over input pairs
-template <int H>
-__device__ __forceinline__ void op_last1(const float *W, const float2 (&hA)[H / 2], const float2 (&hB)[H / 2],
+template <int H, class WT>
+__device__ __forceinline__ void op_last1(const WT W, const float2 (&hA)[H / 2], const float2 (&hB)[H / 2],
                                          float &oA, float &oB) {
     const int wo = 2 * H + 2 * (H * H + H);
     float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < H / 2; i += 2) {
-        const float4 w = lds4(W, wo + 2 * i);
+        const float4 w = W.ld4(wo + 2 * i);
         accA = fma2_packed(make_float2(w.x, w.y), hA[i], accA);
         accB = fma2_packed(make_float2(w.x, w.y), hB[i], accB);
         accA = fma2_packed(make_float2(w.z, w.w), hA[i + 1], accA);
         accB = fma2_packed(make_float2(w.z, w.w), hB[i + 1], accB);
     }
-    const float b = W[wo + H];
+    const float b = W.ld1(wo + H);
     oA = (accA.x + accA.y) + b;
     oB = (accB.x + accB.y) + b;
 }
@@ -227,19 +253,27 @@ __device__ __forceinline__ void op_last1(const float *W, const float2 (&hA)[H / 
 // =====================================================================================
 // conditioner -> spline for both points
 // =====================================================================================
+template <int VARIANT>
+struct WSel {
+    using type = WShared;
+    static __device__ __forceinline__ WShared make(const float *smem, int slot) { return WShared{smem + slot}; }
+};
+
 template <int H, int K, int VARIANT>
-__device__ __forceinline__ void spline_half(const float *W, const mnf_flow_op &op, float2 cond, float2 &trans,
-                                            bool rqs_inverse, float2 &ld) {
+__device__ __forceinline__ void spline_half(const float *smem, int slot, const mnf_flow_op &op, float2 cond,
+                                            float2 &trans, bool rqs_inverse, float2 &ld) {
     constexpr int NB = 3 * K - 1;
     constexpr bool FAST = MNF_SPLINE_FAST != 0;
-    if constexpr (VARIANT == 2) {
+    const float *W = smem + slot;
+    if constexpr (VARIANT >= 2) {
         constexpr int NP2 = round4(NB) / 2;
         float2 rA[NP2], rB[NP2];
         {
+            const auto Wa = WSel<VARIANT>::make(smem, slot);
             float2 hA[H / 2], hB[H / 2];
-            op_hidden<H>(W, cond.x, cond.y, hA, hB);
+            op_hidden<H>(Wa, cond.x, cond.y, hA, hB);
             const int wo = 2 * H + 2 * (H * H + H);
-            op_dense<H, NP2>(W + wo, W + wo + H * 2 * NP2, hA, hB, rA, rB);
+            op_dense<H, NP2>(Wa, wo, wo + H * 2 * NP2, hA, hB, rA, rB);
         }
 #pragma unroll 1
         for (int pt = 0; pt < 2; ++pt) {
@@ -276,12 +310,14 @@ __device__ __forceinline__ void spline_half(const float *W, const mnf_flow_op &o
 
 // scalar-output conditioner (s or t of AffineHalfFlow) for both points
 template <int H, int VARIANT>
-__device__ __forceinline__ float2 affine_net(const float *W, float2 cond) {
-    if constexpr (VARIANT == 2) {
+__device__ __forceinline__ float2 affine_net(const float *smem, int slot, float2 cond) {
+    const float *W = smem + slot;
+    if constexpr (VARIANT >= 2) {
+        const auto Wa = WSel<VARIANT>::make(smem, slot);
         float2 hA[H / 2], hB[H / 2];
-        op_hidden<H>(W, cond.x, cond.y, hA, hB);
+        op_hidden<H>(Wa, cond.x, cond.y, hA, hB);
         float2 o;
-        op_last1<H>(W, hA, hB, o.x, o.y);
+        op_last1<H>(Wa, hA, hB, o.x, o.y);
         return o;
     } else {
         float2 h[H], o[1];
@@ -299,7 +335,7 @@ __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const float w = src[e];
         int d = e;
-        if constexpr (VARIANT == 2) {
+        if constexpr (VARIANT >= 2) {
             if (e >= 2 * H && e < hidden) {  // the two H x H layers: transpose weight blocks
                 const int r = (e - 2 * H) % (H * H + H), base = e - r;
                 if (r < H * H) d = base + (r % H) * H + (r / H);
@@ -309,6 +345,117 @@ __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *
             }
         }
         dst[d] = w;
+    }
+}
+
+// everything that happens to one pair of points: load, all flows, store
+template <int H, int K, int VARIANT>
+__device__ __forceinline__ void process_pair(const FlowProgram &prog, const FastLayout &lay,
+                                             const float *__restrict__ params, const float *smem,
+                                             const float *__restrict__ x, float *__restrict__ y,
+                                             float *__restrict__ log_det, float *__restrict__ base_lp,
+                                             float *__restrict__ inter, long long n_rows, int inverse, bool sum_lp,
+                                             long long pair, bool live) {
+    const bool has_b = 2 * pair + 1 < n_rows;
+    float2 v0, v1;  // v0 = first coordinate of points (A, B), v1 = second coordinate
+    if (has_b) {
+        const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
+        v0 = make_float2(q.x, q.z);
+        v1 = make_float2(q.y, q.w);
+    } else {
+        const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + 2 * pair);
+        v0 = make_float2(q.x, q.x);
+        v1 = make_float2(q.y, q.y);
+    }
+    float2 ld = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int kk = 0; kk < prog.n_ops; ++kk) {
+        const int k = inverse ? prog.n_ops - 1 - kk : kk;
+        const mnf_flow_op &op = prog.ops[k];
+        if (op.type == MNF_OP_AFFINE_CONST) {
+            const float s0 = params[op.aux_off], s1 = params[op.aux_off + 1];
+            const float t0 = params[op.aux_off + 2], t1 = params[op.aux_off + 3];
+            if (inverse) {  // affine_constant_flow.py:24
+                const float e0 = expf(-s0), e1 = expf(-s1);
+                v0 = make_float2((v0.x - t0) * e0, (v0.y - t0) * e0);
+                v1 = make_float2((v1.x - t1) * e1, (v1.y - t1) * e1);
+                ld.x -= s0 + s1;
+                ld.y -= s0 + s1;
+            } else {  // affine_constant_flow.py:19
+                const float e0 = expf(s0), e1 = expf(s1);
+                v0 = make_float2(v0.x * e0 + t0, v0.y * e0 + t0);
+                v1 = make_float2(v1.x * e1 + t1, v1.y * e1 + t1);
+                ld.x += s0 + s1;
+                ld.y += s0 + s1;
+            }
+        } else if (op.type == MNF_OP_GLOW) {
+            const float *W = params + op.aux_off + (inverse ? 4 : 0);  // glow.py:28,36: v @ W
+            const float w00 = W[0], w01 = W[1], w10 = W[2], w11 = W[3];
+            const float lg = params[op.aux_off + 8];
+            const float2 n0 = make_float2(fmaf(v1.x, w10, v0.x * w00), fmaf(v1.y, w10, v0.y * w00));
+            const float2 n1 = make_float2(fmaf(v1.x, w11, v0.x * w01), fmaf(v1.y, w11, v0.y * w01));
+            v0 = n0;
+            v1 = n1;
+            ld.x += inverse ? -lg : lg;
+            ld.y += inverse ? -lg : lg;
+        } else if (op.type == MNF_OP_AFFINE_HALF) {
+            const bool parity = op.flags & MNF_FLAG_PARITY;
+            const float2 cond = parity ? v1 : v0;  // affine_half_flow.py:46-50
+            float2 tr = parity ? v0 : v1;
+            float2 st[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll 1
+            for (int which = 0; which < 2; ++which) {
+                if (!(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
+                const float2 o = affine_net<H, VARIANT>(smem, lay.net_slot[k][which], cond);
+                if (which) st[1] = o; else st[0] = o;
+            }
+            const float2 s = st[0], t = st[1];
+            if (inverse) {  // affine_half_flow.py:54-56
+                tr = make_float2((tr.x - t.x) / expf(s.x), (tr.y - t.y) / expf(s.y));
+                ld.x -= s.x;
+                ld.y -= s.y;
+            } else {  // affine_half_flow.py:58
+                tr = make_float2(expf(s.x) * tr.x + t.x, expf(s.y) * tr.y + t.y);
+                ld.x += s.x;
+                ld.y += s.y;
+            }
+            if (parity) v0 = tr; else v1 = tr;
+        } else if (op.type == MNF_OP_NSF_CL) {
+            // forward: f1 on (lower -> upper) then f2 on (upper -> lower) (spline_flow.py:249-266);
+            // inverse: f2 first, then f1, both with the spline inverse (spline_flow.py:268-285).
+            // One call site, two trips: keeps the unrolled body in the instruction cache.
+#pragma unroll 1
+            for (int step = 0; step < 2; ++step) {
+                const bool use_f1 = (step == 0) != (inverse != 0);
+                const float2 cond = use_f1 ? v0 : v1;
+                float2 tr = use_f1 ? v1 : v0;
+                spline_half<H, K, VARIANT>(smem, lay.net_slot[k][use_f1 ? 0 : 1], op, cond, tr, inverse != 0, ld);
+                if (use_f1) v1 = tr; else v0 = tr;
+            }
+        }
+        if (inter && live) {
+            float *dst = inter + ((size_t)kk * n_rows + 2 * pair) * 2;
+            if (has_b)
+                st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
+            else
+                st_stream2(reinterpret_cast<float2 *>(dst), make_float2(v0.x, v1.x));
+        }
+    }
+
+    const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
+    float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
+                            fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
+    if (sum_lp) lp = make_float2(lp.x + ld.x, lp.y + ld.y);
+    if (!live) return;
+    if (has_b) {
+        if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
+        if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
+        if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
+    } else {
+        if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
+        if (log_det) log_det[2 * pair] = ld.x;
+        if (base_lp) base_lp[2 * pair] = lp.x;
     }
 }
 
@@ -336,110 +483,11 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
     __syncthreads();
 
     const long long n_pairs = (n_rows + 1) >> 1;
-    for (long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x; pair < n_pairs;
-         pair += (long long)gridDim.x * blockDim.x) {
-        const bool has_b = 2 * pair + 1 < n_rows;
-        float2 v0, v1;  // v0 = first coordinate of points (A, B), v1 = second coordinate
-        if (has_b) {
-            const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
-            v0 = make_float2(q.x, q.z);
-            v1 = make_float2(q.y, q.w);
-        } else {
-            const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + 2 * pair);
-            v0 = make_float2(q.x, q.x);
-            v1 = make_float2(q.y, q.y);
-        }
-        float2 ld = make_float2(0.f, 0.f);
-
-#pragma unroll 1
-        for (int kk = 0; kk < prog.n_ops; ++kk) {
-            const int k = inverse ? prog.n_ops - 1 - kk : kk;
-            const mnf_flow_op &op = prog.ops[k];
-            if (op.type == MNF_OP_AFFINE_CONST) {
-                const float s0 = params[op.aux_off], s1 = params[op.aux_off + 1];
-                const float t0 = params[op.aux_off + 2], t1 = params[op.aux_off + 3];
-                if (inverse) {  // affine_constant_flow.py:24
-                    const float e0 = expf(-s0), e1 = expf(-s1);
-                    v0 = make_float2((v0.x - t0) * e0, (v0.y - t0) * e0);
-                    v1 = make_float2((v1.x - t1) * e1, (v1.y - t1) * e1);
-                    ld.x -= s0 + s1;
-                    ld.y -= s0 + s1;
-                } else {  // affine_constant_flow.py:19
-                    const float e0 = expf(s0), e1 = expf(s1);
-                    v0 = make_float2(v0.x * e0 + t0, v0.y * e0 + t0);
-                    v1 = make_float2(v1.x * e1 + t1, v1.y * e1 + t1);
-                    ld.x += s0 + s1;
-                    ld.y += s0 + s1;
-                }
-            } else if (op.type == MNF_OP_GLOW) {
-                const float *W = params + op.aux_off + (inverse ? 4 : 0);  // glow.py:28,36: v @ W
-                const float w00 = W[0], w01 = W[1], w10 = W[2], w11 = W[3];
-                const float lg = params[op.aux_off + 8];
-                const float2 n0 = make_float2(fmaf(v1.x, w10, v0.x * w00), fmaf(v1.y, w10, v0.y * w00));
-                const float2 n1 = make_float2(fmaf(v1.x, w11, v0.x * w01), fmaf(v1.y, w11, v0.y * w01));
-                v0 = n0;
-                v1 = n1;
-                ld.x += inverse ? -lg : lg;
-                ld.y += inverse ? -lg : lg;
-            } else if (op.type == MNF_OP_AFFINE_HALF) {
-                const bool parity = op.flags & MNF_FLAG_PARITY;
-                const float2 cond = parity ? v1 : v0;  // affine_half_flow.py:46-50
-                float2 tr = parity ? v0 : v1;
-                float2 st[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll 1
-                for (int which = 0; which < 2; ++which) {
-                    if (!(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
-                    const float2 o = affine_net<H, VARIANT>(smem + lay.net_slot[k][which], cond);
-                    if (which) st[1] = o; else st[0] = o;
-                }
-                const float2 s = st[0], t = st[1];
-                if (inverse) {  // affine_half_flow.py:54-56
-                    tr = make_float2((tr.x - t.x) / expf(s.x), (tr.y - t.y) / expf(s.y));
-                    ld.x -= s.x;
-                    ld.y -= s.y;
-                } else {  // affine_half_flow.py:58
-                    tr = make_float2(expf(s.x) * tr.x + t.x, expf(s.y) * tr.y + t.y);
-                    ld.x += s.x;
-                    ld.y += s.y;
-                }
-                if (parity) v0 = tr; else v1 = tr;
-            } else if (op.type == MNF_OP_NSF_CL) {
-                // forward: f1 on (lower -> upper) then f2 on (upper -> lower) (spline_flow.py:249-266);
-                // inverse: f2 first, then f1, both with the spline inverse (spline_flow.py:268-285).
-                // One call site, two trips: keeps the unrolled body in the instruction cache.
-#pragma unroll 1
-                for (int step = 0; step < 2; ++step) {
-                    const bool use_f1 = (step == 0) != (inverse != 0);
-                    const float *W = smem + lay.net_slot[k][use_f1 ? 0 : 1];
-                    const float2 cond = use_f1 ? v0 : v1;
-                    float2 tr = use_f1 ? v1 : v0;
-                    spline_half<H, K, VARIANT>(W, op, cond, tr, inverse != 0, ld);
-                    if (use_f1) v1 = tr; else v0 = tr;
-                }
-            }
-            if (inter) {
-                float *dst = inter + ((size_t)kk * n_rows + 2 * pair) * 2;
-                if (has_b)
-                    st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
-                else
-                    st_stream2(reinterpret_cast<float2 *>(dst), make_float2(v0.x, v1.x));
-            }
-        }
-
-        const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
-        float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
-                                fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
-        if (sum_lp) lp = make_float2(lp.x + ld.x, lp.y + ld.y);
-        if (has_b) {
-            if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
-            if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
-            if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
-        } else {
-            if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
-            if (log_det) log_det[2 * pair] = ld.x;
-            if (base_lp) base_lp[2 * pair] = lp.x;
-        }
-    }
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // persistent grid-stride loop: the nets are staged once per CTA
+    for (long long pair = first; pair < n_pairs; pair += (long long)gridDim.x * blockDim.x)
+        process_pair<H, K, VARIANT>(prog, lay, params, smem, x, y, log_det, base_lp, inter, n_rows, inverse, sum_lp,
+                                    pair, true);
 }
 
 template <int H, int K, int VARIANT>
@@ -468,10 +516,270 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
     return launch_status("flow_fast_kernel");
 }
 
+
+// =====================================================================================
+// VARIANT 3: constant-bank weights.  The stack is cut into segments with at most one
+// net-bearing flow each; a segment's two nets are copied (device to device, stream ordered) to
+// FIXED offsets of the constant bank, so every weight load is LDCU c[0x3][imm] -> uniform register
+// -> FFMA2, with no shared-memory or register-file traffic for weights.  Between segments the points
+// and the running log-det make one round trip through HBM (20 B/point, noise next to the FMA time).
+// =====================================================================================
+template <int H, int K>
+struct CbankLayout {
+    static constexpr int kSpline = fast_net_slots(H, 3 * K - 1, 2);  // floats per staged spline conditioner
+    static constexpr int kAffine = fast_net_slots(H, 1, 2);
+    static constexpr int kSegStride = 2 * (kSpline > kAffine ? kSpline : kAffine);
+};
+static_assert(CbankLayout<24, 8>::kSegStride <= kConstFloats, "segment nets must fit the constant bank");
+
+__device__ float g_flow_stage[MNF_MAX_OPS * 2 * 1900];  // staged nets of a whole program, execution order
+static_assert(CbankLayout<24, 8>::kSegStride <= 2 * 1900 && CbankLayout<16, 8>::kSegStride <= 2 * 1900, "stage size");
+
+// one CTA per (segment, net): re-lay-out the net from the parameter blob into the stage
+template <int H>
+__global__ void cbank_stage_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
+                                   int seg_stride, int second_off_spline, int second_off_affine, int inverse) {
+    // prog is in EXECUTION order; segment index = number of net-bearing ops before this one
+    int target = blockIdx.x >> 1, which_exec = blockIdx.x & 1, seg = 0;
+    for (int k = 0; k < prog.n_ops; ++k) {
+        const mnf_flow_op &op = prog.ops[k];
+        if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
+        if (seg++ != target) continue;
+        int which = which_exec;  // AffineHalf: s then t.  NSF_CL: f1,f2 forward; f2,f1 inverse
+        if (op.type == MNF_OP_NSF_CL && inverse) which = 1 - which_exec;
+        if (op.type == MNF_OP_AFFINE_HALF && !(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) return;
+        const int second = op.type == MNF_OP_NSF_CL ? second_off_spline : second_off_affine;
+        stage_net<H, 3>(params + op.net_off[which], g_flow_stage + target * seg_stride + (which_exec ? second : 0),
+                        op.sizes[op.n_lin]);
+        return;
+    }
+}
+
+template <int H, int K, int BASE>
+__device__ __forceinline__ void cb_spline_half(const mnf_flow_op &op, float2 cond, float2 &trans, bool rqs_inverse,
+                                               float2 &ld) {
+    constexpr int NB = 3 * K - 1, NP2 = round4(NB) / 2;
+    constexpr bool FAST = MNF_SPLINE_FAST != 0;
+    float2 rA[NP2], rB[NP2];
+    {
+        const WConstAt<BASE> W;
+        float2 hA[H / 2], hB[H / 2];
+        op_hidden<H>(W, cond.x, cond.y, hA, hB);
+        const int wo = 2 * H + 2 * (H * H + H);
+        op_dense<H, NP2>(W, wo, wo + H * 2 * NP2, hA, hB, rA, rB);
+    }
+#pragma unroll 1
+    for (int pt = 0; pt < 2; ++pt) {
+        float raw[NB];
+#pragma unroll
+        for (int o = 0; o < NB; ++o) {
+            const float2 q = pt ? rB[o >> 1] : rA[o >> 1];
+            raw[o] = (o & 1) ? q.y : q.x;
+        }
+        float v = pt ? trans.y : trans.x;
+        float l = 0.f;
+        rq_spline<K, FAST>(raw, K, op.bound, op.edge_deriv, rqs_inverse, v, l);
+        if (pt) { trans.y = v; ld.y += l; } else { trans.x = v; ld.x += l; }
+    }
+}
+
+template <int H, int BASE>
+__device__ __forceinline__ float2 cb_affine_net(float2 cond) {
+    const WConstAt<BASE> W;
+    float2 hA[H / 2], hB[H / 2];
+    op_hidden<H>(W, cond.x, cond.y, hA, hB);
+    float2 o;
+    op_last1<H>(W, hA, hB, o.x, o.y);
+    return o;
+}
+
+// one segment of the stack (ops in execution order, <= 1 net-bearing op); one pair of points per thread
+template <int H, int K>
+__global__ void __launch_bounds__(128, 4)
+flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
+                  const float *__restrict__ x, const float *__restrict__ ld_in, float *__restrict__ y,
+                  float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
+                  long long n_rows, int dir_flags) {
+    using L = CbankLayout<H, K>;
+    const int inverse = dir_flags & 1;
+    const bool sum_lp = dir_flags & 2;
+    const long long n_pairs = (n_rows + 1) >> 1;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = first < n_pairs;
+    const long long pair = live ? first : n_pairs - 1;  // idle threads redo the last pair, stores predicated off
+    const bool has_b = 2 * pair + 1 < n_rows;
+    float2 v0, v1, ld = make_float2(0.f, 0.f);
+    if (has_b) {
+        const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
+        v0 = make_float2(q.x, q.z);
+        v1 = make_float2(q.y, q.w);
+        if (ld_in) ld = ld_stream2(reinterpret_cast<const float2 *>(ld_in) + pair);
+    } else {
+        const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + 2 * pair);
+        v0 = make_float2(q.x, q.x);
+        v1 = make_float2(q.y, q.y);
+        if (ld_in) ld.x = ld.y = ld_in[2 * pair];
+    }
+#pragma unroll 1
+    for (int kk = 0; kk < prog.n_ops; ++kk) {
+        const mnf_flow_op &op = prog.ops[kk];
+        if (op.type == MNF_OP_AFFINE_CONST) {
+            const float s0 = params[op.aux_off], s1 = params[op.aux_off + 1];
+            const float t0 = params[op.aux_off + 2], t1 = params[op.aux_off + 3];
+            if (inverse) {  // affine_constant_flow.py:24
+                const float e0 = expf(-s0), e1 = expf(-s1);
+                v0 = make_float2((v0.x - t0) * e0, (v0.y - t0) * e0);
+                v1 = make_float2((v1.x - t1) * e1, (v1.y - t1) * e1);
+                ld.x -= s0 + s1;
+                ld.y -= s0 + s1;
+            } else {  // affine_constant_flow.py:19
+                const float e0 = expf(s0), e1 = expf(s1);
+                v0 = make_float2(v0.x * e0 + t0, v0.y * e0 + t0);
+                v1 = make_float2(v1.x * e1 + t1, v1.y * e1 + t1);
+                ld.x += s0 + s1;
+                ld.y += s0 + s1;
+            }
+        } else if (op.type == MNF_OP_GLOW) {
+            const float *W = params + op.aux_off + (inverse ? 4 : 0);  // glow.py:28,36: v @ W
+            const float w00 = W[0], w01 = W[1], w10 = W[2], w11 = W[3];
+            const float lg = params[op.aux_off + 8];
+            const float2 n0 = make_float2(fmaf(v1.x, w10, v0.x * w00), fmaf(v1.y, w10, v0.y * w00));
+            const float2 n1 = make_float2(fmaf(v1.x, w11, v0.x * w01), fmaf(v1.y, w11, v0.y * w01));
+            v0 = n0;
+            v1 = n1;
+            ld.x += inverse ? -lg : lg;
+            ld.y += inverse ? -lg : lg;
+        } else if (op.type == MNF_OP_AFFINE_HALF) {
+            const bool parity = op.flags & MNF_FLAG_PARITY;
+            const float2 cond = parity ? v1 : v0;  // affine_half_flow.py:46-50
+            float2 tr = parity ? v0 : v1;
+            float2 s = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
+            if (op.flags & MNF_FLAG_SCALE) s = cb_affine_net<H, 0>(cond);
+            if (op.flags & MNF_FLAG_SHIFT) t = cb_affine_net<H, L::kAffine>(cond);
+            if (inverse) {  // affine_half_flow.py:54-56
+                tr = make_float2((tr.x - t.x) / expf(s.x), (tr.y - t.y) / expf(s.y));
+                ld.x -= s.x;
+                ld.y -= s.y;
+            } else {  // affine_half_flow.py:58
+                tr = make_float2(expf(s.x) * tr.x + t.x, expf(s.y) * tr.y + t.y);
+                ld.x += s.x;
+                ld.y += s.y;
+            }
+            if (parity) v0 = tr; else v1 = tr;
+        } else if (op.type == MNF_OP_NSF_CL) {
+            // the stage holds the two conditioners in execution order: forward f1 (lower -> upper) then f2
+            // (upper -> lower), spline_flow.py:249-266; inverse f2 then f1, spline_flow.py:268-285
+            // step A conditions on v0 going forward (f1) and on v1 going backward (f2); step B the reverse
+            {
+                const float2 cond = inverse ? v1 : v0;
+                float2 tr = inverse ? v0 : v1;
+                cb_spline_half<H, K, 0>(op, cond, tr, inverse != 0, ld);
+                if (inverse) v0 = tr; else v1 = tr;
+            }
+            {
+                const float2 cond = inverse ? v0 : v1;
+                float2 tr = inverse ? v1 : v0;
+                cb_spline_half<H, K, L::kSpline>(op, cond, tr, inverse != 0, ld);
+                if (inverse) v1 = tr; else v0 = tr;
+            }
+        }
+        if (inter && live) {
+            float *dst = inter + ((size_t)kk * n_rows + 2 * pair) * 2;
+            if (has_b)
+                st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
+            else
+                st_stream2(reinterpret_cast<float2 *>(dst), make_float2(v0.x, v1.x));
+        }
+    }
+    if (!live) return;
+    const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
+    float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
+                            fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
+    if (sum_lp) lp = make_float2(lp.x + ld.x, lp.y + ld.y);
+    if (has_b) {
+        if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
+        if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
+        if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
+    } else {
+        if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
+        if (log_det) log_det[2 * pair] = ld.x;
+        if (base_lp) base_lp[2 * pair] = lp.x;
+    }
+}
+
+struct ConstBankGuard {  // the bank and the stage are shared by every launch of this TU's kernels on a device
+    std::mutex mu;
+    cudaEvent_t done[64] = {};
+};
+
+// prog: ops in MODULE order.  workspace: 3 * n_rows floats (points + log-det between segments).
+template <int H, int K>
+int launch_cbank(const FlowProgram &prog, const float *params, const float *x, float *y, float *log_det,
+                 float *base_lp, float *inter, int64_t n_rows, int dir_flags, float *workspace,
+                 cudaStream_t stream) {
+    using L = CbankLayout<H, K>;
+    const int inverse = dir_flags & 1;
+    FlowProgram exec;  // execution order
+    exec.n_ops = prog.n_ops;
+    for (int k = 0; k < prog.n_ops; ++k) exec.ops[k] = prog.ops[inverse ? prog.n_ops - 1 - k : k];
+    // segments: cut before every net-bearing op except the first
+    int seg_begin[MNF_MAX_OPS + 1], n_seg = 0, nets_seen = 0;
+    seg_begin[n_seg++] = 0;
+    for (int k = 0; k < exec.n_ops; ++k) {
+        const bool net = exec.ops[k].type == MNF_OP_AFFINE_HALF || exec.ops[k].type == MNF_OP_NSF_CL;
+        if (net && nets_seen++ > 0) seg_begin[n_seg++] = k;
+    }
+    seg_begin[n_seg] = exec.n_ops;
+    MNF_REQUIRE(n_seg == 1 || workspace != nullptr, MNF_E_ARG,
+                "multi-segment constant-bank run needs a workspace of 3*n_rows floats");
+
+    static ConstBankGuard guard;
+    int dev = 0;
+    MNF_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(guard.mu);
+    if (!guard.done[dev]) MNF_CUDA(cudaEventCreateWithFlags(&guard.done[dev], cudaEventDisableTiming));
+    else MNF_CUDA(cudaStreamWaitEvent(stream, guard.done[dev], 0));  // other streams: wait, no host sync
+
+    if (nets_seen > 0) {
+        cbank_stage_kernel<H><<<2 * nets_seen, 128, 0, stream>>>(exec, params, L::kSegStride, L::kSpline, L::kAffine,
+                                                                  inverse);
+        int rc = launch_status("cbank_stage_kernel");
+        if (rc) return rc;
+    }
+    void *stage_ptr = nullptr;
+    MNF_CUDA(cudaGetSymbolAddress(&stage_ptr, g_flow_stage));
+    const long long n_pairs = (n_rows + 1) / 2;
+    const unsigned blocks = (unsigned)((n_pairs + 127) / 128);
+    float *z_tmp = workspace, *ld_tmp = workspace ? workspace + 2 * n_rows : nullptr;
+    int net_idx = 0, rc = 0;
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+        FlowProgram sp;
+        sp.n_ops = seg_begin[sgm + 1] - seg_begin[sgm];
+        bool has_net = false;
+        for (int k = 0; k < sp.n_ops; ++k) {
+            sp.ops[k] = exec.ops[seg_begin[sgm] + k];
+            has_net |= sp.ops[k].type == MNF_OP_AFFINE_HALF || sp.ops[k].type == MNF_OP_NSF_CL;
+        }
+        if (has_net) {
+            MNF_CUDA(cudaMemcpyToSymbolAsync(c_flow_w, (const float *)stage_ptr + (size_t)net_idx * L::kSegStride,
+                                             sizeof(float) * L::kSegStride, 0, cudaMemcpyDeviceToDevice, stream));
+            ++net_idx;
+        }
+        const bool first = sgm == 0, last = sgm == n_seg - 1;
+        flow_cbank_kernel<H, K><<<blocks, 128, 0, stream>>>(
+            sp, params, first ? x : z_tmp, first ? nullptr : ld_tmp, last ? y : z_tmp, last ? log_det : ld_tmp,
+            last ? base_lp : nullptr, inter ? inter + (size_t)seg_begin[sgm] * n_rows * 2 : nullptr, n_rows, dir_flags);
+        rc = launch_status("flow_cbank_kernel");
+        if (rc) break;
+    }
+    MNF_CUDA(cudaEventRecord(guard.done[dev], stream));
+    return rc;
+}
+
 #define MNF_FLOW_FAST_ARGS                                                                                    \
     int variant, const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,      \
         const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int inverse,  \
-        const DeviceProps *dp, cudaStream_t stream
+        float *workspace, const DeviceProps *dp, cudaStream_t stream
 
 #define MNF_FLOW_FAST_DEFINE(HH, KK)                                                                            \
     int launch_fast_##HH##_##KK(MNF_FLOW_FAST_ARGS) {                                                           \
@@ -481,6 +789,9 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
         if (variant == 1)                                                                                       \
             return launch_inst<HH, KK, 1>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, \
                                           inverse, dp, stream);                                                 \
+        if (variant == 3)                                                                                       \
+            return launch_cbank<HH, KK>(prog, params, x, y, log_det, base_lp, inter, n_rows, inverse, workspace, \
+                                        stream);                                                                \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \
                                       inverse, dp, stream);                                                     \
     }

@@ -88,13 +88,25 @@ def spline_edge_derivative(min_deriv: float = 1e-3) -> float:
     return float(min_deriv + torch.nn.functional.softplus(c))
 
 
-def _state_key(flows, device):
-    key = [str(device)]
+_version_of = __import__("operator").attrgetter("_version")
+
+
+def _tensors_of(flows):
+    out = []
     for f in flows:
-        for t in list(f.parameters()) + list(f.buffers()):
-            key.append((t.data_ptr(), t._version))
-        key.append(getattr(f, "_program_salt", 0))
-    return tuple(key)
+        out += list(f.parameters()) + list(f.buffers())
+    return out
+
+
+def _state_key(flows, device, tensors):
+    """Cheap per-call fingerprint of everything the packed blob depends on: in-place updates bump
+    ``_version``; re-assigned storage (``.to()``, ``.data = ...``) shows in the data pointers; kernels
+    that write parameters behind autograd's back (ActNorm init) bump ``_program_salt``."""
+    return (
+        str(device), tuple(map(_version_of, tensors)),
+        tensors[0].data_ptr() if tensors else 0, tensors[-1].data_ptr() if tensors else 0,
+        tuple(f.__dict__.get("_program_salt", 0) for f in flows),
+    )
 
 
 class FlowProgram:
@@ -102,6 +114,7 @@ class FlowProgram:
 
     def __init__(self, flows):
         self.flows = list(flows)
+        self._tensors = _tensors_of(self.flows)
         self._key = None
         self._ops = None
         self._blob = None
@@ -110,9 +123,11 @@ class FlowProgram:
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
-        key = _state_key(self.flows, device)
+        key = _state_key(self.flows, device, self._tensors)
         if key == self._key:
             return
+        self._tensors = _tensors_of(self.flows)  # buffers are re-created by Module.to(): refresh
+        key = _state_key(self.flows, device, self._tensors)
         pk = ParamPacker(device)
         ops = [f._emit(pk) for f in self.flows]
         with torch.no_grad():
@@ -121,6 +136,11 @@ class FlowProgram:
         self._n_ops = len(ops)
         self._blob = blob
         self._key = key
+
+    @staticmethod
+    def _workspace(lib, n_ops, n_rows, dim, dev):
+        need = lib.mnf_flow_stack_workspace(n_ops, n_rows, dim)
+        return torch.empty(need, device=dev, dtype=torch.float32) if need > 0 else None
 
     def plan(self, device, dim) -> int:
         """1 if the dim-2 register-resident kernel will run this program, else 0 (generic)."""
@@ -148,10 +168,12 @@ class FlowProgram:
             if kernel == "generic":
                 flags |= _lib.RUN_GENERIC
             elif kernel is not None:
-                flags |= ((int(kernel) + 1) << 4) & 0x30
+                flags |= ((int(kernel) + 1) << 4) & 0x70
+            ws = self._workspace(lib, n, B, D, dev)
             with torch.cuda.device(dev):
                 rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
-                                            None, None, lp.data_ptr(), None, B, D, flags, _lib.stream_ptr(dev))
+                                            None, None, lp.data_ptr(), None, B, D, flags, _lib.ptr(ws),
+                                            _lib.stream_ptr(dev))
             _lib.check(rc, "mnf_flow_stack_run")
             _lib.launch_count += 1
             return None, None, None, lp
@@ -163,11 +185,12 @@ class FlowProgram:
             y.copy_(x)
             ld.zero_()
         stream = _lib.stream_ptr(dev)
+        ws = self._workspace(lib, min(n, _lib.MAX_OPS), B, D, dev)
         flags = _lib.RUN_INVERSE if inverse else 0
         if kernel == "generic":
             flags |= _lib.RUN_GENERIC
         elif kernel is not None:
-            flags |= ((int(kernel) + 1) << 4) & 0x30
+            flags |= ((int(kernel) + 1) << 4) & 0x70
         with torch.cuda.device(dev):
             # stacks longer than MNF_MAX_OPS run in chunks, log-dets summed across chunks
             done, src, first = 0, x, True
@@ -182,7 +205,7 @@ class FlowProgram:
                 rc = lib.mnf_flow_stack_run(
                     ops_ptr, cnt, self._blob.data_ptr(), self._blob.numel(), src.data_ptr(), y.data_ptr(),
                     ld_chunk.data_ptr(), _lib.ptr(lp) if last else None,
-                    inter[done:].data_ptr() if inter is not None else None, B, D, flags, stream,
+                    inter[done:].data_ptr() if inter is not None else None, B, D, flags, _lib.ptr(ws), stream,
                 )
                 _lib.check(rc, "mnf_flow_stack_run")
                 _lib.launch_count += 1

@@ -13,10 +13,11 @@ class MaskedLinear(nn.Linear):
 
     def __init__(self, n_in, n_out, bias=True):
         super().__init__(n_in, n_out, bias)
-        self.register_buffer("mask", torch.ones(n_in, n_out))
+        self.register_buffer("mask", torch.ones(n_in, n_out, dtype=torch.bool))
 
     def set_mask(self, mask: np.ndarray) -> None:
-        self.mask = torch.from_numpy(np.ascontiguousarray(mask)).to(self.weight.device)
+        # in place: bumps the buffer's version so cached flow programs re-fold the mask
+        self.mask.copy_(torch.from_numpy(np.ascontiguousarray(mask)).to(self.mask.device, torch.bool))
 
     def forward(self, x):
         raise RuntimeError(
