@@ -182,6 +182,22 @@ int mnf_linear_forward(const float *x, int64_t x_rows, const float *z, const flo
                        const float *eps, uint64_t seed, uint32_t noise_stream, uint64_t row_offset,
                        float *out, int64_t n_rows, int n_in, int n_out, int relu, void *stream);
 
+/* Tensor-core (tcgen05, TF32 inputs, fp32 accumulation in TMEM, TMA-fed) variant of mnf_linear_forward
+ * for n_in % 4 == 0 and 16-byte aligned operands; results agree with the fp32 path to the 2e-3 relative
+ * tolerance BASELINE.json states for tensor-core GEMM outputs.  workspace: mnf_linear_tc_workspace()
+ * floats.  The variance GEMM runs once per DISTINCT input row (x_rows), not per Monte-Carlo sample. */
+int64_t mnf_linear_tc_workspace(int64_t x_rows, int64_t n_rows, int n_in, int n_out);
+int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const float *W_mean,
+                          const float *W_log_var, const float *b_mean, const float *b_log_var,
+                          const float *eps, uint64_t seed, uint32_t noise_stream, uint64_t row_offset,
+                          float *out, int64_t n_rows, int n_in, int n_out, int relu, float *workspace,
+                          void *stream);
+/* out = A W^T (+ bias) (+ ReLU) on the tensor cores: A [M,K], W [N,K] (torch Linear layout). */
+int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K,
+                  int relu, void *stream);
+/* 1 if (A, W, M, N, K) can take the tensor-core path (alignment / shape), else 0.  Host-only. */
+int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K);
+
 /* MNFConv2d.forward after sample_z (mnf_conv.py:67-78), stride 1, no padding, NCHW:
  *   out = conv2d(x, W_mean * z[:,None,None,None]) + sqrt(conv2d(x^2, exp(W_log_var)) + exp(b_log_var)) * eps
  * x: [x_imgs, c_in, H, W], image r reads x[r % x_imgs]; z: [c_out] (one draw shared by the batch);

@@ -1,0 +1,74 @@
+"""Tensor-core (tcgen05 / TF32 / TMA) path: plain linear and the MNFLinear forward, against an fp32
+reference with the rtol 2e-3 BASELINE.json states for tensor-core GEMM outputs (the absolute floor is
+2e-3 x the row's typical magnitude: TF32 rounds each product to 10 mantissa bits)."""
+
+import pytest
+import torch
+
+from tests.helpers import golden_sd, golden_tape, load_golden, t
+
+pytestmark = pytest.mark.gpu
+
+
+def tc_linear(A, W, bias=None, relu=False):
+    import torch_mnf.layers  # noqa: F401
+    from torch_mnf import _lib
+
+    out = torch.empty(A.size(0), W.size(0), device=A.device)
+    rc = _lib.lib().mnf_tc_linear(A.data_ptr(), W.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(),
+                                  A.size(0), W.size(0), A.size(1), int(relu), _lib.stream_ptr(A.device))
+    _lib.check(rc, "mnf_tc_linear")
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (256, 256, 64), (1000, 320, 132), (77, 8, 36), (4096, 512, 1024),
+                                   (130, 1000, 4096)])
+def test_tc_linear_matches_fp32(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K**0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    pre = A.double() @ W.double().T
+    # the raw entry point feeds unrounded fp32: the tensor core truncates both operands to TF32 (up to 2^-10
+    # each, biased), so the bound is 4e-3 of the typical |a.w|; the MNF path pre-rounds to nearest (2e-3 below)
+    atol = 4e-3 * float(pre.pow(2).mean().sqrt())
+    ref = (pre + b.double()).float()
+    out = tc_linear(A, W, b)
+    torch.testing.assert_close(out, ref, rtol=4e-3, atol=atol)
+    out = tc_linear(A, W, None, relu=True)
+    torch.testing.assert_close(out, torch.relu(pre).float(), rtol=4e-3, atol=atol)
+
+
+def test_mnf_linear_tf32_vs_golden():
+    from torch_mnf.layers import MNFLinear
+
+    g = load_golden("mnf_linear_256x128")
+    layer = MNFLinear(256, 128, n_flows_r=1)
+    layer.load_state_dict(golden_sd(g), strict=True)
+    layer.cuda()
+    layer.precision = "tf32"
+    y = layer(t(g, "x").cuda(), noise=golden_tape(g, "fwd_noise/"))
+    ref = t(g, "fwd/y")
+    torch.testing.assert_close(y.cpu(), ref, rtol=2e-3, atol=2e-3 * float(ref.pow(2).mean().sqrt()))
+    layer.precision = "fp32"
+    y32 = layer(t(g, "x").cuda(), noise=golden_tape(g, "fwd_noise/"))
+    torch.testing.assert_close(y32.cpu(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().mean()))
+
+
+def test_mnf_linear_tf32_mc_replication_wide():
+    """Config-5 shape in small: 64 input rows x 32 MC samples, n_in = n_out = 512, Philox noise; the tensor-core
+    result must match the fp32 SIMT path (same Philox draws) to 2e-3."""
+    from torch_mnf.layers import MNFLinear
+    from torch_mnf.layers._mnf_ops import Noise
+
+    torch.manual_seed(0)
+    layer = MNFLinear(512, 512).cuda()
+    with torch.no_grad():
+        layer.W_log_var += 6.0
+        layer.q0_log_var += 8.0
+    x = torch.randn(64, 512, device="cuda")
+    layer.precision = "fp32"
+    ref = layer.forward_mc(x, 32, noise=Noise(None, x.device, 0, seed=5))
+    layer.precision = "tf32"
+    out = layer.forward_mc(x, 32, noise=Noise(None, x.device, 0, seed=5))
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3 * float(ref.pow(2).mean().sqrt()))

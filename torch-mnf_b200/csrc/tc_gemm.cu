@@ -1,0 +1,423 @@
+// tc_gemm.cu -- Blackwell tensor-core path of the MNF contractions:
+//     C[M,N] = A[M,K] * B[N,K]^T  (fp32 in HBM, TF32 on the 5th-gen tensor cores, fp32 accumulate in TMEM)
+// with the MNF epilogues fused (bias, sqrt-variance * noise, ReLU).
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles of A (128 x 32 fp32) and B (256 x 32 fp32) into a
+//            4-stage shared-memory ring, 128-byte swizzle, completion on mbarriers
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N256 x K8),
+//            4 per stage, accumulating into one of two 256-column TMEM accumulators; tcgen05.commit
+//            releases the smem stage / publishes the accumulator
+//   warp 2   TMEM allocator (512 columns)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global; overlaps the next
+//            tile's MMAs through the second accumulator
+// TF32 keeps a 10-bit mantissa: products carry ~2e-4 relative error, inside the 2e-3 tolerance BASELINE.json
+// states for tensor-core GEMM outputs (the exact-fp32 path is simt_gemm_kernel in mnf_common.cuh).
+#include <cuda.h>
+
+#include "mnf_common.cuh"
+
+namespace mnf {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4, UMMA_K = 8, ACC_STAGES = 2;
+constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 256;
+
+struct Epilogue {
+    int mode;           // 0: acc + bias   1: acc + bias + sd[m % sd_rows, n] * eps   2: sqrt(acc + exp(bvar_log[n]))
+    const float *bias;  // [N] or nullptr
+    const float *sd;    // mode 1: [sd_rows, N]
+    int sd_rows;
+    const float *bvar_log;  // mode 2: [N]
+    const float *eps;       // mode 1: [M, N] or nullptr -> Philox
+    uint64_t seed;
+    uint32_t noise_stream;
+    uint64_t row_offset;
+    int relu;
+    float *out;  // [M, N]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                 int K, const Epilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    // barrier slots: full[STAGES], empty[STAGES], acc_full[ACC], acc_empty[ACC], then the TMEM base address
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < ACC_STAGES; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int n_mblk = (M + BM - 1) / BM, n_nblk = (N + BN - 1) / BN, n_kblk = (K + BK - 1) / BK;
+    const long long n_tiles = (long long)n_mblk * n_nblk;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_nblk), n_blk = (int)(tile % n_nblk);
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                mbar_wait(empty(stage), phase ^ 1u);
+                mbar_expect_tx(full(stage), STAGE_BYTES);
+                const uint32_t sa = base + stage * STAGE_BYTES;
+                tma_load_2d(sa, &map_a, full(stage), kb * BK, m_blk * BM);
+                tma_load_2d(sa + A_BYTES, &map_b, full(stage), kb * BK, n_blk * BN);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(acc_empty(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                mbar_wait(full(stage), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + stage * STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+                    umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                }
+                umma_commit(empty(stage));  // frees the smem stage once these MMAs have read it
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(acc_full(acc));  // accumulator complete -> epilogue
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (128 threads, one TMEM lane = one output row each) ----------------
+        const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const Philox rng(ep.seed);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_nblk), n_blk = (int)(tile % n_nblk);
+            mbar_wait(acc_full(acc), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int m = m_blk * BM + quarter * 32 + lane;
+            const uint32_t trow = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(trow + (uint32_t)(c * 32), r);
+                const int n0 = n_blk * BN + c * 32;
+                if (m < M && n0 < N) {
+                    float *orow = ep.out + (size_t)m * N;
+                    const float *sdrow = ep.mode == 1 ? ep.sd + (size_t)(m % ep.sd_rows) * N : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int n = n0 + j + u;
+                            float a = __uint_as_float(r[j + u]);
+                            if (n < N) {
+                                if (ep.mode == 2) {
+                                    a = sqrtf(a + expf(ep.bvar_log[n]));
+                                } else {
+                                    if (ep.bias) a += ep.bias[n];
+                                    if (ep.mode == 1) {
+                                        const long long e = (long long)m * N + n;
+                                        const float z = ep.eps ? ep.eps[e]
+                                                               : philox_normal(rng, (uint64_t)(ep.row_offset * N + e),
+                                                                               ep.noise_stream);
+                                        a = fmaf(sdrow[n], z, a);
+                                    }
+                                    if (ep.relu) a = fmaxf(a, 0.f);
+                                }
+                            }
+                            v[u] = a;
+                        }
+                        const int n = n0 + j;
+                        if (n + 3 < N && (N & 3) == 0) {
+                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (n + u < N) orow[n + u] = v[u];
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty(acc));
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const float *ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    MNF_REQUIRE(fn != nullptr, MNF_E_DEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MNF_REQUIRE(r == CUDA_SUCCESS, MNF_E_ARG, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d)", (int)r,
+                rows, cols);
+    return 0;
+}
+
+bool eligible(const float *A, const float *B, int M, int N, int K) {
+    return M >= 1 && N >= 8 && K >= BK && (K % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0;
+}
+
+int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
+    const DeviceProps *dp = device_props();
+    MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
+    MNF_REQUIRE(dp->cc_major == 10, MNF_E_DEVICE, "tcgen05 path needs an sm_100 device, found sm_%d%d", dp->cc_major,
+                dp->cc_minor);
+    MNF_REQUIRE(eligible(A, B, M, N, K), MNF_E_SHAPE, "shape/alignment not eligible for the tensor-core path");
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, M, K, BM);
+    if (rc) return rc;
+    rc = make_map(&mb, B, N, K, BN);
+    if (rc) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    MNF_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        MNF_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_set[dev & 63] = true;
+    }
+    const long long n_tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const unsigned grid = (unsigned)(n_tiles < dp->sm_count ? n_tiles : dp->sm_count);
+    tf32_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+    return launch_status("tf32_gemm_kernel");
+}
+
+}  // namespace tc
+}  // namespace mnf
+
+namespace mnf {
+namespace tc {
+
+// The tensor core TRUNCATES fp32 operands to TF32 (drops 13 mantissa bits), which biases every product
+// towards zero; operands are therefore rounded to nearest TF32 when they are staged, making the error
+// unbiased (2^-11 per operand) and ~4e-4 of the typical dot-product magnitude in practice.
+__device__ __forceinline__ float rn_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// xz[m,k] = x[m % x_rows, k] * z[m,k]   (A operand of the mean GEMM, mnf_linear.py:48)
+__global__ void xz_kernel(const float4 *__restrict__ x, const float4 *__restrict__ z, float4 *__restrict__ xz,
+                          long long n_rows, int x_rows, int k4) {
+    const long long total = n_rows * k4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / k4;
+        const int c = (int)(e - m * k4);
+        const float4 a = x[(size_t)(m % x_rows) * k4 + c], b = z[e];
+        xz[e] = make_float4(rn_tf32(a.x * b.x), rn_tf32(a.y * b.y), rn_tf32(a.z * b.z), rn_tf32(a.w * b.w));
+    }
+}
+// out = tf32(f(in)): f = identity (0), exp (1: W_var, mnf_linear.py:50) or square (2: x**2, mnf_linear.py:53)
+__global__ void unary_kernel(const float *__restrict__ in, float *__restrict__ out, long long n, int op) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const float v = in[e];
+        out[e] = rn_tf32(op == 2 ? v * v : (op == 1 ? expf(v) : v));
+    }
+}
+
+static unsigned blocks_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+}  // namespace tc
+}  // namespace mnf
+
+using namespace mnf;
+
+extern "C" {
+
+int64_t mnf_linear_tc_workspace(int64_t x_rows, int64_t n_rows, int n_in, int n_out) {
+    return n_rows * n_in + 2 * (int64_t)n_out * n_in + x_rows * n_in + x_rows * (int64_t)n_out;
+}
+
+// MNFLinear.forward (mnf_linear.py:46-56) on the tensor cores:
+//   sd  = sqrt(x^2 exp(W_log_var)^T + exp(b_log_var))      [x_rows, n_out]   (TF32 GEMM, epilogue mode 2)
+//   out = (x*z) W_mean^T + b_mean + sd[m % x_rows] * eps   [n_rows, n_out]   (TF32 GEMM, epilogue mode 1)
+// The variance depends on x only, so under Monte-Carlo replication (x_rows < n_rows) it is evaluated once per
+// distinct input row instead of once per sample -- the flops actually executed are reported as such.
+int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const float *W_mean, const float *W_log_var,
+                          const float *b_mean, const float *b_log_var, const float *eps, uint64_t seed,
+                          uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_rows, int n_in, int n_out,
+                          int relu, float *workspace, void *stream) {
+    MNF_REQUIRE(x && z && W_mean && W_log_var && b_mean && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(n_rows >= 0 && n_rows <= 0x7fffffff - 256 && x_rows >= 1 && x_rows <= n_rows + (n_rows == 0), MNF_E_ARG,
+                "bad row counts");
+    MNF_REQUIRE(n_in % 4 == 0, MNF_E_SHAPE, "tensor-core path needs n_in %% 4 == 0 (got %d)", n_in);
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *xz = workspace, *expW = xz + (size_t)n_rows * n_in, *wm = expW + (size_t)n_out * n_in,
+          *x2 = wm + (size_t)n_out * n_in, *sd = x2 + (size_t)x_rows * n_in;
+    const int k4 = n_in / 4;
+    tc::xz_kernel<<<tc::blocks_for(n_rows * k4), 256, 0, st>>>((const float4 *)x, (const float4 *)z, (float4 *)xz, n_rows,
+                                                              (int)x_rows, k4);
+    tc::unary_kernel<<<tc::blocks_for((long long)n_out * n_in), 256, 0, st>>>(W_log_var, expW, (long long)n_out * n_in, 1);
+    tc::unary_kernel<<<tc::blocks_for((long long)n_out * n_in), 256, 0, st>>>(W_mean, wm, (long long)n_out * n_in, 0);
+    tc::unary_kernel<<<tc::blocks_for(x_rows * n_in), 256, 0, st>>>(x, x2, x_rows * n_in, 2);
+    int rc = launch_status("mnf_linear_forward_tc prologue");
+    if (rc) return rc;
+    tc::Epilogue ev{2, nullptr, nullptr, 1, b_log_var, nullptr, 0, 0, 0, 0, sd};
+    rc = tc::launch(x2, expW, (int)x_rows, n_out, n_in, ev, st);
+    if (rc) return rc;
+    tc::Epilogue em{1, b_mean, sd, (int)x_rows, nullptr, eps, seed, noise_stream, row_offset, relu, out};
+    return tc::launch(xz, wm, (int)n_rows, n_out, n_in, em, st);
+}
+
+// C = A B^T (+ bias), TF32 tensor cores.  Test / building-block entry point.
+int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K, int relu,
+                  void *stream) {
+    MNF_REQUIRE(A && W && out, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(M >= 0 && M <= 0x7fffffff - 256 && N >= 1 && K >= 1, MNF_E_ARG, "bad shape");
+    if (M == 0) return 0;
+    tc::Epilogue ep{0, bias, nullptr, 1, nullptr, nullptr, 0, 0, 0, relu, out};
+    return tc::launch(A, W, (int)M, N, K, ep, (cudaStream_t)stream);
+}
+
+int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K) {
+    return tc::eligible(A, W, (int)M, N, K) ? 1 : 0;
+}
+
+}  // extern "C"

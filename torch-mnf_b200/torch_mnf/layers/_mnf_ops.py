@@ -47,6 +47,11 @@ _lib.register({
     "mnf_conv2d_forward": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int,
                                   _int, _int, _int, _int, _vp]),
     "mnf_kl_div": (_int, [C.POINTER(KlArgs), _vp]),
+    "mnf_linear_tc_workspace": (_i64, [_i64, _i64, _int, _int]),
+    "mnf_linear_forward_tc": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int,
+                                     _int, _int, _vp, _vp]),
+    "mnf_tc_linear": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
+    "mnf_tc_eligible": (_int, [_vp, _vp, _i64, _int, _int]),
 })
 
 
@@ -173,8 +178,24 @@ def rnvp_stack(flows, z, tape, want_inter):
     return xs, ld
 
 
+TC_MIN_WORK = 1 << 24  # n_rows * n_in * n_out below which the fp32 SIMT kernel is used
+
+
+def use_tensor_cores(layer, n_rows, precision):
+    """precision: "fp32" (exact SIMT path), "tf32" (tcgen05), or "auto" (tf32 for large aligned shapes)."""
+    n_out, n_in = layer.W_mean.shape
+    if precision == "fp32":
+        return False
+    ok = n_in % 4 == 0 and n_in >= 32 and n_out >= 8
+    if precision == "tf32":
+        if not ok:
+            raise ValueError(f"tf32 tensor-core path needs n_in % 4 == 0, n_in >= 32, n_out >= 8 (got {n_in}, {n_out})")
+        return True
+    return ok and n_rows * n_in * n_out >= TC_MIN_WORK and n_in >= 128 and n_out >= 64
+
+
 @torch.no_grad()
-def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False):
+def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False, precision="auto"):
     dev = x.device
     R = z.size(0)
     n_in, n_out = layer.W_mean.shape[1], layer.W_mean.shape[0]
@@ -182,6 +203,16 @@ def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False):
     out = torch.empty((R, n_out), device=dev, dtype=torch.float32)
     args = [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
                                            (layer.b_mean, "b_mean"), (layer.b_log_var, "b_log_var"))]
+    if use_tensor_cores(layer, R, precision):
+        xr = x_rows or x.size(0)
+        ws = torch.empty(_lib.lib().mnf_linear_tc_workspace(xr, R, n_in, n_out), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().mnf_linear_forward_tc(x.data_ptr(), xr, z.data_ptr(), *(a.data_ptr() for a in args), _p(eps),
+                                                  noise.seed, sid, noise.row_offset, out.data_ptr(), R, n_in, n_out,
+                                                  int(relu), ws.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, "mnf_linear_forward_tc")
+        _lib.launch_count += 5
+        return out
     with torch.cuda.device(dev):
         rc = _lib.lib().mnf_linear_forward(x.data_ptr(), x_rows or x.size(0), z.data_ptr(), *(a.data_ptr() for a in args),
                                            _p(eps), noise.seed, sid, noise.row_offset, out.data_ptr(), R, n_in, n_out,

@@ -19,6 +19,9 @@ class MNFLinear(nn.Module):
     in the reference's draw order) for parity runs; ``forward_mc(x, n_samples)`` evaluates
     ``forward(x.repeat(n_samples, 1))`` without materialising the repeat."""
 
+    #: "auto" (TF32 tensor cores for large aligned shapes, exact fp32 otherwise), "fp32" or "tf32"
+    precision = "auto"
+
     def __init__(self, n_in, n_out, n_flows_q=2, n_flows_r=2, h_sizes=(50,)):
         super().__init__()
         self.n_in, self.n_out = n_in, n_out
@@ -51,14 +54,14 @@ class MNFLinear(nn.Module):
         x = _lib.require_cuda_f32(x, "input")
         noise = self._noise(noise, x.device, row_offset)
         z, _ = self.sample_z(x.size(0), noise)
-        return ops.linear_forward(self, x, z, noise, relu=relu)
+        return ops.linear_forward(self, x, z, noise, relu=relu, precision=self.precision)
 
     def forward_mc(self, x, n_samples, noise=None, row_offset=0, relu=False):
         """== forward(x.repeat(n_samples, 1)): row r uses x[r % len(x)], own z and eps per row."""
         x = _lib.require_cuda_f32(x, "input")
         noise = self._noise(noise, x.device, row_offset)
         z, _ = self.sample_z(x.size(0) * n_samples, noise)
-        return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu)
+        return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=self.precision)
 
     def kl_div(self, noise=None):
         return ops.kl_div(self, conv=False, tape=noise)
