@@ -35,6 +35,7 @@ N_POINTS = 1 << 24
 K_BINS, BOUND, N_H = 8, 3, 16
 BYTES_PER_POINT = 12  # 8 B point in + 4 B log-prob out (z is not materialised in log-prob mode)
 MLP_FMA_PER_POINT = 3 * 2 * (16 + 256 + 256 + 16 * 23)  # 5376 fused multiply-adds in the conditioners
+NCU_TRAFFIC_BYTES_PER_STEP = 868.0e6  # dram read+write of the 3 segment launches at 2^24 points (ncu --set full, r01)
 METRIC = "flow log-prob points/s"
 WORKLOAD = "cfg2: [ActNormFlow, Glow, NSF_CL(K=8,B=3,n_h=16)] x3, 2-D points, batch 2^24 per GPU"
 
@@ -229,7 +230,7 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.15)
     barrier()
-    launches0 = _lib.launch_count
+    launches0 = _lib.lib().mnf_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.time()
     ev[0].record()
@@ -238,7 +239,7 @@ def run_ours(args):
         ev[i + 1].record()
     barrier()
     t_wall1 = time.time()
-    launches = _lib.launch_count - launches0
+    launches = _lib.lib().mnf_launch_count() - launches0  # kernels launched by libmnf_b200.so in the timed region
     total_ms = ev[0].elapsed_time(ev[-1])
     if world > 1:
         tmax = torch.tensor([total_ms], device=dev)
@@ -335,9 +336,12 @@ def run_ours(args):
                 "how": f"pinned host -> {e_chunks} chunks double-buffered over 3 streams -> NormalizingFlowModel.log_prob -> pinned host"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "kernel": "flow_fast_kernel<16,8,*>",
+                     "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_STEP * n / N_POINTS,
+                     "kernel": "flow_cbank_kernel<16,8> x3 segments (+ cbank_stage_kernel)",
                      "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT, "peak_source": peak_src,
-                     "note": "kernel is fp32-FMA-pipe bound, not HBM bound (DESIGN.md): see fma_pipe"},
+                     "note": "per STEP (3 segment launches): algorithmic 12 B/pt; the segmented stack moves ~52 B/pt "
+                             "(ncu, profiles/r01_flow_cbank_ncu_full.md); kernel is fp32-FMA-pipe bound, not HBM "
+                             "bound (DESIGN.md): see fma_pipe"},
         "fma_pipe": {"mlp_tflops": mlp_tflops, "fp32_peak_tflops_at_sampled_clock": fp32_peak,
                      "frac_mlp_only": mlp_tflops / fp32_peak, "fma_per_point_mlp": MLP_FMA_PER_POINT,
                      "note": "conditioner-MLP FMAs only; spline arithmetic shares the same pipe"},

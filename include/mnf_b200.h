@@ -38,6 +38,8 @@ extern "C" {
 
 int mnf_abi_version(void);
 const char *mnf_last_error(void);
+/* Kernels launched by this library in this process so far (diagnostics; bench.py's gpu_launches). */
+uint64_t mnf_launch_count(void);
 /* Fills SM count, max opt-in shared memory per block, compute capability major/minor of
  * the current device.  Any pointer may be NULL. */
 int mnf_device_info(int *sm_count, int *smem_optin, int *cc_major, int *cc_minor);
@@ -194,7 +196,27 @@ int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const 
                           void *stream);
 /* out = A W^T (+ bias) (+ ReLU) on the tensor cores: A [M,K], W [N,K] (torch Linear layout). */
 int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K,
-                  int relu, void *stream);
+                  int relu, int round_out, void *stream);
+
+/* MAF.inverse -- the density direction -- for a stack of MAF flows (flows/maf.py:53-62 over
+ * layers/made.py:22-23) as a chain of TF32 tensor-core GEMMs; the last GEMM of every flow applies
+ * z = x*exp(s) + t, the parity flip and the log-det row sum in its epilogue.  Weights are packed by the
+ * host once per parameter version: mask folded in (W * mask^T), rounded to TF32, output layer rows
+ * interleaved (s_0, t_0, s_1, t_1, ...).  Tolerance class: tensor-core GEMM (2e-3). */
+#define MNF_MADE_MAX_HIDDEN 4
+typedef struct mnf_made_layer {
+    int32_t n_hidden;                    /* hidden MaskedLinear layers                       */
+    int32_t hidden[MNF_MADE_MAX_HIDDEN]; /* their widths (multiples of 4)                    */
+    int32_t parity;                      /* flip dims after the transform (maf.py:60)        */
+    const float *w[MNF_MADE_MAX_HIDDEN]; /* [hidden[l], in_l] masked, TF32-rounded           */
+    const float *b[MNF_MADE_MAX_HIDDEN]; /* [hidden[l]]                                      */
+    const float *w_out;                  /* [2*dim, hidden[last]] interleaved s/t rows       */
+    const float *b_out;                  /* [2*dim] interleaved                              */
+} mnf_made_layer;
+int64_t mnf_made_workspace(int64_t n_rows, int dim, int max_hidden);
+int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const float *x, float *z,
+                        float *log_det, float *intermediates /* optional [n_flows, n_rows, dim] */,
+                        int64_t n_rows, int dim, float *workspace, void *stream);
 /* 1 if (A, W, M, N, K) can take the tensor-core path (alignment / shape), else 0.  Host-only. */
 int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K);
 

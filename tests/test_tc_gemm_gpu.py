@@ -16,7 +16,7 @@ def tc_linear(A, W, bias=None, relu=False):
 
     out = torch.empty(A.size(0), W.size(0), device=A.device)
     rc = _lib.lib().mnf_tc_linear(A.data_ptr(), W.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(),
-                                  A.size(0), W.size(0), A.size(1), int(relu), _lib.stream_ptr(A.device))
+                                  A.size(0), W.size(0), A.size(1), int(relu), 0, _lib.stream_ptr(A.device))
     _lib.check(rc, "mnf_tc_linear")
     return out
 
@@ -72,3 +72,32 @@ def test_mnf_linear_tf32_mc_replication_wide():
     layer.precision = "tf32"
     out = layer.forward_mc(x, 32, noise=Noise(None, x.device, 0, seed=5))
     torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3 * float(ref.pow(2).mean().sqrt()))
+
+
+def test_maf_stack_tensor_core_density_vs_golden():
+    """BASELINE config 3 shape: MAF x9, D = 64, density direction on the tensor cores (tf32 tolerance class)."""
+    from tests.helpers import golden_spec, load_flow_model
+
+    g = load_golden("maf9_d64")
+    model = load_flow_model(golden_spec(g), golden_sd(g))
+    for f in model.flows:
+        f.precision = "tf32"
+    x = t(g, "inv/x").cuda()
+    zs, ld = model.inverse(x)
+    assert len(zs) == 10
+    ref_z, ref_ld = t(g, "inv/z"), t(g, "inv/ld")
+    torch.testing.assert_close(zs[-1].cpu(), ref_z, rtol=2e-3, atol=2e-3 * float(ref_z.pow(2).mean().sqrt()))
+    torch.testing.assert_close(ld.cpu(), ref_ld, rtol=2e-3, atol=2e-3 * float(ref_ld.pow(2).mean().sqrt()) + 2e-3)
+    torch.testing.assert_close(zs[5].cpu(), t(g, "inv/z_mid"), rtol=2e-3, atol=2e-3 * float(ref_z.pow(2).mean().sqrt()))
+    # single flow through the module API, and the exact-fp32 path for comparison
+    z1, ld1 = model.flows[8].inverse(x)
+    torch.testing.assert_close(z1, zs[1], rtol=1e-6, atol=1e-6)
+    for f in model.flows:
+        f.precision = "fp32"
+    zs32, ld32 = model.inverse(x)
+    torch.testing.assert_close(zs32[-1].cpu(), ref_z, rtol=1e-5, atol=2e-5)
+    model.return_intermediates = False
+    for f in model.flows:
+        f.precision = "tf32"
+    zs2, ld2 = model.inverse(x)
+    assert len(zs2) == 2 and torch.equal(zs2[-1], zs[-1]) and torch.equal(ld2, ld)

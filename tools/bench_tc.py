@@ -20,7 +20,7 @@ def timeit(fn, iters=5):
 
 for M, N, K in [(8192, 4096, 4096), (65536, 4096, 4096)]:
     A = torch.randn(M, K, device="cuda"); W = torch.randn(N, K, device="cuda") / 64; out = torch.empty(M, N, device="cuda")
-    f = lambda: _lib.check(_lib.lib().mnf_tc_linear(A.data_ptr(), W.data_ptr(), None, out.data_ptr(), M, N, K, 0, _lib.stream_ptr(A.device)), "tc")
+    f = lambda: _lib.check(_lib.lib().mnf_tc_linear(A.data_ptr(), W.data_ptr(), None, out.data_ptr(), M, N, K, 0, 0, _lib.stream_ptr(A.device)), "tc")
     ms = timeit(f)
     print(f"tc_linear M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     torch.backends.cuda.matmul.allow_tf32 = True

@@ -10,6 +10,11 @@ char *err_buf() {
     return buf;
 }
 
+unsigned long long &launch_counter() {
+    static unsigned long long n = 0;
+    return n;
+}
+
 int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -45,6 +50,8 @@ extern "C" {
 int mnf_abi_version(void) { return MNF_ABI_VERSION; }
 
 const char *mnf_last_error(void) { return mnf::err_buf(); }
+
+uint64_t mnf_launch_count(void) { return mnf::launch_counter(); }
 
 int mnf_device_info(int *sm_count, int *smem_optin, int *cc_major, int *cc_minor) {
     const mnf::DeviceProps *p = mnf::device_props();

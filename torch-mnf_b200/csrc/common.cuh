@@ -26,7 +26,11 @@ int fail(int code, const char *fmt, ...);
             return ::mnf::fail((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// process-wide count of kernel launches made by this library (mnf_launch_count(); bench.py reports it)
+unsigned long long &launch_counter();
+
 inline int launch_status(const char *what) {
+    ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s launch failed: %s", what, cudaGetErrorString(e));
     return 0;

@@ -20,11 +20,24 @@
 namespace mnf {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4, UMMA_K = 8, ACC_STAGES = 2;
-constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 32, UMMA_K = 8, MAX_BN = 256;
+constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr int THREADS = 256;
+// tile width BN in {32, 64, 128, 256}: narrow outputs (RNVP / MADE hidden layers) take narrow tiles so that
+// neither the B-tile TMA nor the MMA is spent on padding; narrow tiles afford a deeper smem ring
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);  // <= 192 KB of operand ring
+    static constexpr uint32_t B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    // TMEM accumulators in flight: narrow tiles finish their MMAs in a few hundred cycles, so more of them are
+    // kept in flight to cover the epilogue's memory latency
+    static constexpr int ACC_STAGES = BN == 256 ? 2 : (BN == 128 ? 4 : 8);
+    static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // power of two in [64, 512]
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    // cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, K-major both, N>>3 at bit 17, M>>4 at bit 24
+    static constexpr uint32_t kInstrDesc =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 struct Epilogue {
     int mode;           // 0: acc + bias   1: acc + bias + sd[m % sd_rows, n] * eps   2: sqrt(acc + exp(bvar_log[n]))
@@ -37,10 +50,28 @@ struct Epilogue {
     uint32_t noise_stream;
     uint64_t row_offset;
     int relu;
-    float *out;  // [M, N]
+    float *out;  // [M, N]  (mode 3: [M, N/2])
+    // mode 0 extras
+    int round_out;  // store rn_tf32(value): the output feeds another TF32 GEMM
+    // mode 3 (MAF.inverse epilogue, maf.py:53-62): columns are interleaved (s_0, t_0, s_1, t_1, ...);
+    // z = x * exp(s) + t, dims flipped if parity, log_det (+)= sum s.  Needs N <= BN (one column tile).
+    const float *xin;    // [M, N/2] exact fp32 input of the flow
+    float *out_rounded;  // optional second copy of z, TF32-rounded, for the next flow's first GEMM
+    const float *ld_in;  // optional running log-det
+    float *ld_out;
+    int parity;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// The tensor core TRUNCATES fp32 operands to TF32 (drops 13 mantissa bits), which biases every product
+// towards zero; operands are therefore rounded to nearest TF32 when they are staged, making the error
+// unbiased (2^-11 per operand) and ~4e-4 of the typical dot-product magnitude in practice.
+__device__ __forceinline__ float rn_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -74,15 +105,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// cute::UMMA::InstrDescriptor: c=F32, a=b=TF32, K-major both, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate,
+                                          uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDesc), "r"(accumulate)
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -101,9 +130,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                  int K, const Epilogue ep) {
+    constexpr int STAGES = Cfg<BN>::STAGES, ACC_STAGES = Cfg<BN>::ACC_STAGES;
+    constexpr uint32_t STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -178,7 +210,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
                     // advance 32 bytes (8 tf32) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-                    umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0);
+                    umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0, Cfg<BN>::kInstrDesc);
                 }
                 umma_commit(empty(stage));  // frees the smem stage once these MMAs have read it
                 if (++stage == STAGES) {
@@ -204,49 +236,139 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int m = m_blk * BM + quarter * 32 + lane;
             const uint32_t trow = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
+            float s_sum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < BN / 32 && n_blk * BN + c * 32 < N; ++c) {
                 uint32_t r[32];
                 tmem_ld32(trow + (uint32_t)(c * 32), r);
                 const int n0 = n_blk * BN + c * 32;
-                if (m < M && n0 < N) {
-                    float *orow = ep.out + (size_t)m * N;
-                    const float *sdrow = ep.mode == 1 ? ep.sd + (size_t)(m % ep.sd_rows) * N : nullptr;
+                if (ep.mode == 3) {
+                    if (m < M) {
+                        // 32 accumulator columns = 16 (s, t) pairs = 16 consecutive dims: 64 contiguous bytes of
+                        // x / z per thread, moved as float4 (reversed within the row when parity flips the dims)
+                        const int D = N >> 1, i0 = n0 >> 1;
+                        const float *xrow = ep.xin + (size_t)m * D;
+                        float zv[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i0 + 4 * q;
+                            if (i < D) {
+                                const float4 xv = *reinterpret_cast<const float4 *>(xrow + i);
+                                const float4 b0 = *reinterpret_cast<const float4 *>(ep.bias + 2 * i);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(ep.bias + 2 * i + 4);
+                                const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                                const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float sv = __uint_as_float(r[8 * q + 2 * u]) + bs[2 * u];
+                                    const float tv = __uint_as_float(r[8 * q + 2 * u + 1]) + bs[2 * u + 1];
+                                    zv[4 * q + u] = xs[u] * expf(sv) + tv;  // maf.py:58
+                                    s_sum += sv;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i0 + 4 * q;
+                            if (i < D) {
+                                float4 v = make_float4(zv[4 * q], zv[4 * q + 1], zv[4 * q + 2], zv[4 * q + 3]);
+                                size_t o = (size_t)m * D + i;
+                                if (ep.parity) {  // maf.py:60: z.flip(dims=[1])
+                                    v = make_float4(v.w, v.z, v.y, v.x);
+                                    o = (size_t)m * D + (D - 4 - i);
+                                }
+                                *reinterpret_cast<float4 *>(ep.out + o) = v;
+                                if (ep.out_rounded)
+                                    *reinterpret_cast<float4 *>(ep.out_rounded + o) =
+                                        make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+                            }
+                        }
+                    }
+                } else if (m < M && n0 + 32 <= N && (N & 3) == 0) {
+                    // fast path: whole 32-column chunk in range.  All global operands of the chunk are fetched
+                    // with independent float4 loads BEFORE any arithmetic, so the epilogue pays one memory
+                    // latency per chunk instead of one per element (it must stay shorter than a tile's MMAs).
+                    float *orow = ep.out + (size_t)m * N + n0;
+                    float add[32], mul[32], nz[32];
+                    const bool has_bias = ep.mode != 2 && ep.bias != nullptr;
+                    const float *bsrc = ep.mode == 2 ? ep.bvar_log : ep.bias;
+                    if (ep.mode == 2 || has_bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4 *>(bsrc + n0 + j);
+                            add[j] = b.x, add[j + 1] = b.y, add[j + 2] = b.z, add[j + 3] = b.w;
+                        }
+                    }
+                    if (ep.mode == 1) {
+                        const float *sdrow = ep.sd + (size_t)(m % ep.sd_rows) * N + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4 *>(sdrow + j);
+                            mul[j] = b.x, mul[j + 1] = b.y, mul[j + 2] = b.z, mul[j + 3] = b.w;
+                        }
+                        const long long e0 = (long long)m * N + n0;
+                        if (ep.eps) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b = *reinterpret_cast<const float4 *>(ep.eps + e0 + j);
+                                nz[j] = b.x, nz[j + 1] = b.y, nz[j + 2] = b.z, nz[j + 3] = b.w;
+                            }
+                        } else {
+                            // global element index is a multiple of 4 here: one Philox block = 4 normals
+                            const uint64_t g0 = (uint64_t)(ep.row_offset * N + e0);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const uint4 q = rng((g0 + j) >> 2, ep.noise_stream);
+                                const float2 n01 = box_muller(q.x, q.y), n23 = box_muller(q.z, q.w);
+                                nz[j] = n01.x, nz[j + 1] = n01.y, nz[j + 2] = n23.x, nz[j + 3] = n23.y;
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float v[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int n = n0 + j + u;
                             float a = __uint_as_float(r[j + u]);
-                            if (n < N) {
-                                if (ep.mode == 2) {
-                                    a = sqrtf(a + expf(ep.bvar_log[n]));
-                                } else {
-                                    if (ep.bias) a += ep.bias[n];
-                                    if (ep.mode == 1) {
-                                        const long long e = (long long)m * N + n;
-                                        const float z = ep.eps ? ep.eps[e]
-                                                               : philox_normal(rng, (uint64_t)(ep.row_offset * N + e),
-                                                                               ep.noise_stream);
-                                        a = fmaf(sdrow[n], z, a);
-                                    }
-                                    if (ep.relu) a = fmaxf(a, 0.f);
-                                }
+                            if (ep.mode == 2) {
+                                a = sqrtf(a + expf(add[j + u]));
+                            } else {
+                                if (has_bias) a += add[j + u];
+                                if (ep.mode == 1) a = fmaf(mul[j + u], nz[j + u], a);
+                                if (ep.relu) a = fmaxf(a, 0.f);
+                                if (ep.round_out) a = rn_tf32(a);
                             }
                             v[u] = a;
                         }
+                        *reinterpret_cast<float4 *>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                } else if (m < M && n0 < N) {
+                    // ragged edge: element-wise with bounds checks
+                    float *orow = ep.out + (size_t)m * N;
+                    const float *sdrow = ep.mode == 1 ? ep.sd + (size_t)(m % ep.sd_rows) * N : nullptr;
+                    for (int j = 0; j < 32; ++j) {
                         const int n = n0 + j;
-                        if (n + 3 < N && (N & 3) == 0) {
-                            *reinterpret_cast<float4 *>(orow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (n >= N) break;
+                        float a = __uint_as_float(r[j]);
+                        if (ep.mode == 2) {
+                            a = sqrtf(a + expf(ep.bvar_log[n]));
                         } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (n + u < N) orow[n + u] = v[u];
+                            if (ep.bias) a += ep.bias[n];
+                            if (ep.mode == 1) {
+                                const long long e = (long long)m * N + n;
+                                const float z = ep.eps ? ep.eps[e]
+                                                       : philox_normal(rng, (uint64_t)(ep.row_offset * N + e),
+                                                                       ep.noise_stream);
+                                a = fmaf(sdrow[n], z, a);
+                            }
+                            if (ep.relu) a = fmaxf(a, 0.f);
+                            if (ep.round_out) a = rn_tf32(a);
                         }
+                        orow[n] = a;
                     }
                 }
             }
+            if (ep.mode == 3 && m < M) ep.ld_out[m] = (ep.ld_in ? ep.ld_in[m] : 0.f) + s_sum;  // maf.py:61
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty(acc));
             if (++acc == ACC_STAGES) {
@@ -299,12 +421,9 @@ bool eligible(const float *A, const float *B, int M, int N, int K) {
     return M >= 1 && N >= 8 && K >= BK && (K % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0;
 }
 
-int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
-    const DeviceProps *dp = device_props();
-    MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
-    MNF_REQUIRE(dp->cc_major == 10, MNF_E_DEVICE, "tcgen05 path needs an sm_100 device, found sm_%d%d", dp->cc_major,
-                dp->cc_minor);
-    MNF_REQUIRE(eligible(A, B, M, N, K), MNF_E_SHAPE, "shape/alignment not eligible for the tensor-core path");
+template <int BN>
+static int launch_bn(const float *A, const float *B, int M, int N, int K, const Epilogue &ep, const DeviceProps *dp,
+                     cudaStream_t stream) {
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A, M, K, BM);
     if (rc) return rc;
@@ -314,13 +433,26 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
     int dev = 0;
     MNF_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        MNF_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MNF_CUDA(cudaFuncSetAttribute(tf32_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg<BN>::SMEM_BYTES));
         attr_set[dev & 63] = true;
     }
     const long long n_tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const unsigned grid = (unsigned)(n_tiles < dp->sm_count ? n_tiles : dp->sm_count);
-    tf32_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+    tf32_gemm_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
     return launch_status("tf32_gemm_kernel");
+}
+
+int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &ep, cudaStream_t stream) {
+    const DeviceProps *dp = device_props();
+    MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
+    MNF_REQUIRE(dp->cc_major == 10, MNF_E_DEVICE, "tcgen05 path needs an sm_100 device, found sm_%d%d", dp->cc_major,
+                dp->cc_minor);
+    MNF_REQUIRE(eligible(A, B, M, N, K), MNF_E_SHAPE, "shape/alignment not eligible for the tensor-core path");
+    if (N <= 32) return launch_bn<32>(A, B, M, N, K, ep, dp, stream);
+    if (N <= 64) return launch_bn<64>(A, B, M, N, K, ep, dp, stream);
+    if (N <= 128) return launch_bn<128>(A, B, M, N, K, ep, dp, stream);
+    return launch_bn<256>(A, B, M, N, K, ep, dp, stream);
 }
 
 }  // namespace tc
@@ -328,15 +460,6 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 
 namespace mnf {
 namespace tc {
-
-// The tensor core TRUNCATES fp32 operands to TF32 (drops 13 mantissa bits), which biases every product
-// towards zero; operands are therefore rounded to nearest TF32 when they are staged, making the error
-// unbiased (2^-11 per operand) and ~4e-4 of the typical dot-product magnitude in practice.
-__device__ __forceinline__ float rn_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
 
 // xz[m,k] = x[m % x_rows, k] * z[m,k]   (A operand of the mean GEMM, mnf_linear.py:48)
 __global__ void xz_kernel(const float4 *__restrict__ x, const float4 *__restrict__ z, float4 *__restrict__ xz,
@@ -399,21 +522,81 @@ int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const 
     tc::unary_kernel<<<tc::blocks_for(x_rows * n_in), 256, 0, st>>>(x, x2, x_rows * n_in, 2);
     int rc = launch_status("mnf_linear_forward_tc prologue");
     if (rc) return rc;
-    tc::Epilogue ev{2, nullptr, nullptr, 1, b_log_var, nullptr, 0, 0, 0, 0, sd};
+    tc::Epilogue ev{2, nullptr, nullptr, 1, b_log_var, nullptr, 0, 0, 0, 0, sd, 0, nullptr, nullptr, nullptr, nullptr, 0};
     rc = tc::launch(x2, expW, (int)x_rows, n_out, n_in, ev, st);
     if (rc) return rc;
-    tc::Epilogue em{1, b_mean, sd, (int)x_rows, nullptr, eps, seed, noise_stream, row_offset, relu, out};
+    tc::Epilogue em{1, b_mean, sd, (int)x_rows, nullptr, eps, seed, noise_stream, row_offset, relu, out, 0, nullptr, nullptr, nullptr, nullptr, 0};
     return tc::launch(xz, wm, (int)n_rows, n_out, n_in, em, st);
 }
 
 // C = A B^T (+ bias), TF32 tensor cores.  Test / building-block entry point.
 int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K, int relu,
-                  void *stream) {
+                  int round_out, void *stream) {
     MNF_REQUIRE(A && W && out, MNF_E_ARG, "NULL pointer");
     MNF_REQUIRE(M >= 0 && M <= 0x7fffffff - 256 && N >= 1 && K >= 1, MNF_E_ARG, "bad shape");
     if (M == 0) return 0;
-    tc::Epilogue ep{0, bias, nullptr, 1, nullptr, nullptr, 0, 0, 0, relu, out};
+    tc::Epilogue ep{0, bias, nullptr, 1, nullptr, nullptr, 0, 0, 0, relu, out, round_out, nullptr, nullptr, nullptr, nullptr, 0};
     return tc::launch(A, W, (int)M, N, K, ep, (cudaStream_t)stream);
+}
+
+// MAF.inverse (density direction, maf.py:53-62) for a stack of MAF flows on the tensor cores.
+//   layers_host[f]: packed, mask-folded, TF32-rounded weights of flow f (see mnf_made_layer)
+//   x [n_rows, dim] -> z [n_rows, dim], log_det [n_rows] (sum over the flows)
+//   workspace: mnf_made_workspace() floats
+int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const float *x, float *z, float *log_det,
+                        float *intermediates, int64_t n_rows, int dim, float *workspace, void *stream) {
+    MNF_REQUIRE(layers_host && x && z && log_det && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(n_flows >= 1 && dim >= 4 && dim % 4 == 0 && 2 * dim <= tc::MAX_BN, MNF_E_SHAPE,
+                "tensor-core MADE needs dim %% 4 == 0 and dim <= %d (got %d)", tc::MAX_BN / 2, dim);
+    MNF_REQUIRE(n_rows >= 0 && n_rows <= 0x7fffffff - 256, MNF_E_ARG, "bad row count");
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int maxh = 4;
+    for (int f = 0; f < n_flows; ++f)
+        for (int l = 0; l < layers_host[f].n_hidden; ++l) {
+            const int h = layers_host[f].hidden[l];
+            MNF_REQUIRE(h % 4 == 0 && h >= 8, MNF_E_SHAPE, "hidden width %d must be a multiple of 4 and >= 8", h);
+            maxh = h > maxh ? h : maxh;
+        }
+    // workspace: xr (rounded input) | zbuf[2] (ping-pong exact z) | h[2]
+    float *xr = workspace, *za = xr + (size_t)n_rows * dim, *zb = za + (size_t)n_rows * dim,
+          *ha = zb + (size_t)n_rows * dim, *hb = ha + (size_t)n_rows * maxh;
+    tc::unary_kernel<<<tc::blocks_for(n_rows * dim), 256, 0, st>>>(x, xr, n_rows * dim, 0);
+    int rc = launch_status("made round input");
+    if (rc) return rc;
+    const float *cur_exact = x;
+    const float *cur_round = xr;
+    for (int f = 0; f < n_flows; ++f) {
+        const mnf_made_layer &L = layers_host[f];
+        MNF_REQUIRE(L.n_hidden >= 1 && L.n_hidden <= MNF_MADE_MAX_HIDDEN, MNF_E_SHAPE, "flow %d: n_hidden=%d", f, L.n_hidden);
+        const float *a = cur_round;
+        int k = dim;
+        float *hout = ha;
+        for (int l = 0; l < L.n_hidden; ++l) {
+            tc::Epilogue ep{0, L.b[l], nullptr, 1, nullptr, nullptr, 0, 0, 0, 1, hout, 1, nullptr, nullptr, nullptr, nullptr, 0};
+            rc = tc::launch(a, L.w[l], (int)n_rows, L.hidden[l], k, ep, st);
+            if (rc) return rc;
+            a = hout;
+            k = L.hidden[l];
+            hout = (hout == ha) ? hb : ha;
+        }
+        const bool last = f == n_flows - 1;
+        float *zout = intermediates ? intermediates + (size_t)f * n_rows * dim : (last ? z : (cur_exact == za ? zb : za));
+        float *zround = last ? nullptr : xr;  // the rounded copy of the previous input is dead by now
+        tc::Epilogue ep{3, L.b_out, nullptr, 1, nullptr, nullptr, 0, 0, 0, 0, zout, 0, cur_exact, zround,
+                        f == 0 ? nullptr : log_det, log_det, L.parity};
+        rc = tc::launch(a, L.w_out, (int)n_rows, 2 * dim, k, ep, st);
+        if (rc) return rc;
+        cur_exact = zout;
+        cur_round = xr;
+    }
+    if (intermediates)
+        MNF_CUDA(cudaMemcpyAsync(z, cur_exact, sizeof(float) * n_rows * dim, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int64_t mnf_made_workspace(int64_t n_rows, int dim, int max_hidden) {
+    return n_rows * (3 * (int64_t)dim + 2 * (int64_t)max_hidden);
 }
 
 int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K) {

@@ -49,6 +49,7 @@ _f32p = C.c_void_p  # device pointers travel as integers
 _SIGS = {
     "mnf_abi_version": (C.c_int, []),
     "mnf_last_error": (C.c_char_p, []),
+    "mnf_launch_count": (C.c_uint64, []),
     "mnf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
     "mnf_flow_stack_run": (
         C.c_int,

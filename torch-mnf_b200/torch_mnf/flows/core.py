@@ -49,7 +49,32 @@ class NormalizingFlow(nn.Module):
 
         return len(self.flows) > 0 and all(isinstance(f, RNVP) for f in self.flows)
 
+    def _maf_density_stack(self, v: Tensor, inverse: bool):
+        """Stacks made only of MAF (inverse) / IAF (forward) flows in their one-pass direction take the
+        tensor-core MADE chain when eligible (flows/maf.py::_use_tc)."""
+        from .maf import IAF, MAF, _use_tc
+
+        flows = list(self.flows)
+        if not flows or not all(isinstance(f, MAF) for f in flows):
+            return None
+        if any(isinstance(f, IAF) != (not inverse) for f in flows) or not _use_tc(flows, v):
+            return None
+        from ..layers.made import MadeStackPlan, made_density
+
+        order = flows[::-1] if inverse else flows
+        plan = self.__dict__.get("_tc_plan")
+        if plan is None or plan[0] != inverse:
+            plan = (inverse, MadeStackPlan(order))
+            self.__dict__["_tc_plan"] = plan
+        z, ld, inter = made_density(plan[1], v, want_inter=self.return_intermediates)
+        outs = [v] + (list(inter.unbind(0)) if inter is not None else [z])
+        return outs, ld
+
     def _run(self, v: Tensor, inverse: bool, want_lp: bool = False):
+        if not want_lp:
+            got = self._maf_density_stack(v, inverse)
+            if got is not None:
+                return got[0], got[1], None
         for f in self.flows:
             hook = getattr(f, "_before_run", None)
             if hook is not None:

@@ -16,6 +16,8 @@ class MAF(Flow):
     ``parity``; ``forward`` (sampling) decodes the D dimensions sequentially."""
 
     _sequential_on_forward = True
+    #: "auto": TF32 tensor cores for large batches (2e-3 tolerance class), exact fp32 otherwise; "fp32"; "tf32"
+    precision = "auto"
 
     def __init__(self, dim: int, parity: bool, net: nn.Module | None = None,
                  h_sizes: Sequence[int] = (24, 24, 24)) -> None:
@@ -38,19 +40,23 @@ class MAF(Flow):
         off = pk.add(*net_tensors(lin, masks=[m.mask for m in lin]))
         return new_op(_lib.OP_MADE, flags=flags, sizes=sizes, net_off=(off, 0))
 
-    def inverse(self, x):
-        if not self._sequential_on_forward or not _dense_made_ok(self):
-            return super().inverse(x)
-        from ..layers.made import made_density
+    def _density(self, v):
+        """One-pass direction (MAF.inverse / IAF.forward)."""
+        if _use_tc([self], v):
+            from ..layers.made import MadeStackPlan, made_density
 
-        return made_density([self], x)
+            plan = self.__dict__.setdefault("_tc_plan", MadeStackPlan([self]))
+            z, ld, _ = made_density(plan, v)
+            return z, ld
+        return None
+
+    def inverse(self, x):
+        out = self._density(x) if self._sequential_on_forward else None
+        return out if out is not None else super().inverse(x)
 
     def forward(self, z):
-        if self._sequential_on_forward or not _dense_made_ok(self):
-            return super().forward(z)
-        from ..layers.made import made_density
-
-        return made_density([self], z)
+        out = self._density(z) if not self._sequential_on_forward else None
+        return out if out is not None else super().forward(z)
 
 
 class IAF(MAF):
@@ -59,5 +65,15 @@ class IAF(MAF):
     _sequential_on_forward = False
 
 
-def _dense_made_ok(flow) -> bool:
-    return False  # the tiled MADE kernel registers itself here (layers/made.py)
+def _use_tc(flows, v) -> bool:
+    """Tensor-core density path?  All flows must be eligible MAFs with the same precision policy."""
+    from ..layers.made import TC_MIN_ELEMS, made_tc_eligible
+
+    if not flows or not all(isinstance(f, MAF) and made_tc_eligible(f) for f in flows):
+        return False
+    prec = {f.precision for f in flows}
+    if prec == {"fp32"}:
+        return False
+    if prec == {"tf32"}:
+        return True
+    return "fp32" not in prec and v.is_cuda and v.numel() >= TC_MIN_ELEMS

@@ -50,7 +50,7 @@ _lib.register({
     "mnf_linear_tc_workspace": (_i64, [_i64, _i64, _int, _int]),
     "mnf_linear_forward_tc": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int,
                                      _int, _int, _vp, _vp]),
-    "mnf_tc_linear": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
+    "mnf_tc_linear": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
     "mnf_tc_eligible": (_int, [_vp, _vp, _i64, _int, _int]),
 })
 

@@ -65,5 +65,118 @@ class MADE(nn.Sequential):
             layer.set_mask(mask)
 
 
-def made_density(flows, x):
-    raise NotImplementedError
+# ---------------------------------------------------------------------------------------
+# tensor-core density path for stacks of MAF flows (mnf_made_density_tc)
+# ---------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+from .. import _lib  # noqa: E402
+
+MADE_MAX_HIDDEN = 4
+TC_MIN_ELEMS = 1 << 18  # rows * dim below which the exact-fp32 interpreter is used under precision="auto"
+
+
+class MadeLayer(C.Structure):
+    """struct mnf_made_layer."""
+
+    _fields_ = [
+        ("n_hidden", C.c_int32), ("hidden", C.c_int32 * MADE_MAX_HIDDEN), ("parity", C.c_int32),
+        ("w", C.c_void_p * MADE_MAX_HIDDEN), ("b", C.c_void_p * MADE_MAX_HIDDEN),
+        ("w_out", C.c_void_p), ("b_out", C.c_void_p),
+    ]
+
+
+_lib.register({
+    "mnf_made_workspace": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "mnf_made_density_tc": (C.c_int, [C.POINTER(MadeLayer), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+})
+
+
+def _round_tf32(t):
+    """Round to nearest TF32 (10 mantissa bits), ties away from zero like cvt.rna.tf32.f32."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def made_tc_eligible(flow, n_rows=None) -> bool:
+    net = flow.net
+    if not isinstance(net, MADE):
+        return False
+    d = flow.dim
+    lin = [m for m in net if isinstance(m, MaskedLinear)]
+    ok = d % 4 == 0 and 4 <= d <= 128 and 2 <= len(lin) <= MADE_MAX_HIDDEN + 1 and net.n_out == 2 * d
+    return ok and all(m.out_features <= 256 for m in lin[:-1])
+
+
+class MadeStackPlan:
+    """Packed weights of a stack of MAF flows: mask folded, hidden widths zero-padded to multiples of 32
+    (TMA rows of 128 B), output rows interleaved (s_0, t_0, s_1, t_1, ...), everything TF32-rounded."""
+
+    def __init__(self, flows):
+        self.flows = list(flows)
+        self.key = None
+
+    def _tensors(self):
+        out = []
+        for f in self.flows:
+            out += list(f.net.parameters()) + list(f.net.buffers())
+        return out
+
+    def build(self, device):
+        ts = self._tensors()
+        key = (str(device), tuple(t._version for t in ts), ts[0].data_ptr())
+        if key == self.key:
+            return
+        structs, keep, self.max_hidden = [], [], 32
+        with torch.no_grad():
+            for f in self.flows:
+                lin = [m for m in f.net if isinstance(m, MaskedLinear)]
+                d = f.dim
+                st = MadeLayer()
+                st.n_hidden, st.parity = len(lin) - 1, int(bool(f.parity))
+                k_in = d
+                for l, m in enumerate(lin[:-1]):
+                    h = (m.out_features + 31) // 32 * 32
+                    w = torch.zeros(h, k_in, device=device)
+                    w[: m.out_features, : m.in_features] = (m.weight * m.mask.to(m.weight.dtype).T).to(device)
+                    b = torch.zeros(h, device=device)
+                    b[: m.out_features] = m.bias.to(device)
+                    w = _round_tf32(w)
+                    keep += [w, b]
+                    st.hidden[l], st.w[l], st.b[l] = h, w.data_ptr(), b.data_ptr()
+                    self.max_hidden = max(self.max_hidden, h)
+                    k_in = h
+                m = lin[-1]
+                wo = torch.zeros(2 * d, k_in, device=device)
+                full = (m.weight * m.mask.to(m.weight.dtype).T).to(device)  # rows: s_0..s_{d-1}, t_0..t_{d-1} (maf.py:57)
+                wo[0::2, : m.in_features] = full[:d]
+                wo[1::2, : m.in_features] = full[d:]
+                bo = torch.empty(2 * d, device=device)
+                bo[0::2], bo[1::2] = m.bias[:d].to(device), m.bias[d:].to(device)
+                wo = _round_tf32(wo)
+                keep += [wo, bo]
+                st.w_out, st.b_out = wo.data_ptr(), bo.data_ptr()
+                structs.append(st)
+        self.arr = (MadeLayer * len(structs))(*structs)
+        self.keep, self.key = keep, key
+
+
+@torch.no_grad()
+def made_density(plan: MadeStackPlan, x, want_inter=False):
+    """Density direction of a MAF stack on the tensor cores -> (z, log_det, intermediates or None)."""
+    x = _lib.require_cuda_f32(x, "input")
+    dev = x.device
+    B, D = x.shape
+    plan.build(dev)
+    lib = _lib.lib()
+    n = len(plan.flows)
+    z = torch.empty_like(x)
+    ld = torch.empty(B, device=dev, dtype=torch.float32)
+    inter = torch.empty((n, B, D), device=dev, dtype=torch.float32) if want_inter else None
+    ws = torch.empty(lib.mnf_made_workspace(B, D, plan.max_hidden), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.mnf_made_density_tc(plan.arr, n, x.data_ptr(), z.data_ptr(), ld.data_ptr(), _lib.ptr(inter), B, D,
+                                     ws.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_made_density_tc")
+    return z, ld, inter
