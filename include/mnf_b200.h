@@ -194,6 +194,16 @@ int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const 
                           const float *eps, uint64_t seed, uint32_t noise_stream, uint64_t row_offset,
                           float *out, int64_t n_rows, int n_in, int n_out, int relu, float *workspace,
                           void *stream);
+/* mnf_rnvp_forward on the tensor cores (single-Linear conditioners of width <= 64, dim % 16 == 0).
+ * Optionally leaves xz_out = tf32(x[m % x_rows] * z_final), the A operand of mnf_linear_forward_tc's mean
+ * GEMM (pass z = NULL there and put xz_out at the start of its workspace).  workspace:
+ * mnf_rnvp_tc_workspace() floats. */
+int64_t mnf_rnvp_tc_workspace(int n_flows, int64_t n_rows, int dim);
+int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, float *log_det,
+                        const float *const *masks_host, uint64_t seed, uint32_t first_noise_stream,
+                        uint64_t row_offset, int64_t n_rows, int dim, const float *x, int64_t x_rows,
+                        float *xz_out, float *workspace, void *stream);
+
 /* out = A W^T (+ bias) (+ ReLU) on the tensor cores: A [M,K], W [N,K] (torch Linear layout). */
 int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K,
                   int relu, int round_out, void *stream);

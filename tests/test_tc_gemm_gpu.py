@@ -100,4 +100,5 @@ def test_maf_stack_tensor_core_density_vs_golden():
     for f in model.flows:
         f.precision = "tf32"
     zs2, ld2 = model.inverse(x)
-    assert len(zs2) == 2 and torch.equal(zs2[-1], zs[-1]) and torch.equal(ld2, ld)
+    assert len(zs2) == 2 and torch.equal(zs2[-1], zs[-1])
+    torch.testing.assert_close(ld2, ld, rtol=1e-5, atol=1e-5)  # row sums are accumulated with atomics

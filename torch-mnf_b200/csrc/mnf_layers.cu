@@ -27,11 +27,30 @@ __device__ __forceinline__ float noise_bernoulli(const NoiseSrc &s, long long lo
 __global__ void sample_z0_kernel(const float *__restrict__ q0_mean, const float *__restrict__ q0_log_var,
                                  NoiseSrc eps, float *__restrict__ z, long long n_rows, int dim) {
     const long long total = n_rows * dim;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(e % dim);
-        const float std = sqrtf(expf(q0_log_var[d]));  // .exp().sqrt(), mnf_linear.py:59
-        z[e] = q0_mean[d] + std * noise_normal(eps, e, (long long)eps.row_offset * dim + e);
+    const Philox rng(eps.seed);
+    // four consecutive elements per step: one Philox block yields exactly their four normals
+    // (same element -> number mapping as philox_normal)
+    for (long long e0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); e0 < total;
+         e0 += 4LL * gridDim.x * blockDim.x) {
+        float n4[4];
+        if (eps.ptr == nullptr) {
+            const uint4 q = rng((uint64_t)((long long)eps.row_offset * dim + e0) >> 2, eps.stream);
+            const float2 a = box_muller(q.x, q.y), b = box_muller(q.z, q.w);
+            n4[0] = a.x, n4[1] = a.y, n4[2] = b.x, n4[3] = b.y;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long e = e0 + u;
+            if (e >= total) break;
+            const int d = (int)(e % dim);
+            const float std = sqrtf(expf(q0_log_var[d]));  // .exp().sqrt(), mnf_linear.py:59
+            // (row_offset * dim) % 4 == 0 is required for the block alignment; otherwise fall back per element
+            const float nz = eps.ptr ? eps.ptr[e]
+                                     : ((((long long)eps.row_offset * dim) & 3) == 0
+                                            ? n4[u]
+                                            : philox_normal(rng, (uint64_t)((long long)eps.row_offset * dim + e), eps.stream));
+            z[e] = q0_mean[d] + std * nz;
+        }
     }
 }
 
@@ -227,8 +246,9 @@ int mnf_sample_z0(const float *q0_mean, const float *q0_log_var, const float *ep
     MNF_REQUIRE(n_rows >= 0 && dim >= 1, MNF_E_ARG, "bad shape");
     if (n_rows == 0) return 0;
     const long long total = (long long)n_rows * dim;
-    long long blocks = (total + 255) / 256;
+    long long blocks = (total / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
     sample_z0_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         q0_mean, q0_log_var, NoiseSrc{eps, seed, noise_stream, row_offset}, z, n_rows, dim);
     return launch_status("sample_z0_kernel");

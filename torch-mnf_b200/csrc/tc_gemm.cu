@@ -22,7 +22,7 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8, MAX_BN = 256;
 constexpr uint32_t A_BYTES = BM * BK * 4;
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;  // 4 control warps + 2 groups of 4 epilogue warps
 // tile width BN in {32, 64, 128, 256}: narrow outputs (RNVP / MADE hidden layers) take narrow tiles so that
 // neither the B-tile TMA nor the MMA is spent on padding; narrow tiles afford a deeper smem ring
 template <int BN>
@@ -60,7 +60,30 @@ struct Epilogue {
     const float *ld_in;  // optional running log-det
     float *ld_out;
     int parity;
+    // mode 4 (RNVP gate, rnvp.py:32-39): columns interleaved (shift_0, scale_0, shift_1, scale_1, ...), N = 2*dim;
+    // bias interleaved likewise.  z is updated in place, (1-mask)*log(gate) is summed into ld_acc with one
+    // atomicAdd per row and tile.  Optional extra outputs feed the next GEMM without another pass over z:
+    // mz_next = tf32(mask_next * z_new) (next flow's conditioner input), xz_out = tf32(x[m % x_rows] * z_new)
+    // (A operand of the MNFLinear mean GEMM).
+    float *z;
+    float *ld_acc;
+    const float *mask;  // injected [M, dim] or nullptr -> Philox bits (noise_stream)
+    float *mz_next;
+    const float *mask_next;
+    uint32_t next_stream;
+    const float *xmul;
+    int xmul_rows;
+    float *xz_out;
 };
+
+// 16 Bernoulli(0.5) bits for 16 consecutive elements starting at global index e0 (a multiple of 16), identical to
+// philox_bernoulli() element by element
+__device__ __forceinline__ uint32_t philox_bits16(const Philox &g, uint64_t e0, uint32_t stream) {
+    const uint4 q = g(e0 >> 7, stream);
+    const uint32_t bit = (uint32_t)e0 & 127u;
+    const uint32_t w = bit < 32 ? q.x : bit < 64 ? q.y : bit < 96 ? q.z : q.w;
+    return (w >> (bit & 31u)) & 0xFFFFu;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -159,7 +182,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         for (int a = 0; a < ACC_STAGES; ++a) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 128);
+            mbar_init(acc_empty(a), 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -227,6 +250,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else if (warp >= 4) {
         // ---------------- epilogue (128 threads, one TMEM lane = one output row each) ----------------
         const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+        const int group = (warp - 4) >> 2;  // two warps per lane quarter share a tile: even / odd 32-column chunks
         int acc = 0;
         uint32_t acc_phase = 0;
         const Philox rng(ep.seed);
@@ -238,7 +262,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t trow = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quarter * 32) << 16);
             float s_sum = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32 && n_blk * BN + c * 32 < N; ++c) {
+            for (int c = group; c < BN / 32 && n_blk * BN + c * 32 < N; c += 2) {
                 uint32_t r[32];
                 tmem_ld32(trow + (uint32_t)(c * 32), r);
                 const int n0 = n_blk * BN + c * 32;
@@ -281,6 +305,77 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 if (ep.out_rounded)
                                     *reinterpret_cast<float4 *>(ep.out_rounded + o) =
                                         make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+                            }
+                        }
+                    }
+                } else if (ep.mode == 4) {
+                    if (m < M) {
+                        const int D = N >> 1, j0 = n0 >> 1;  // this chunk = 16 consecutive dims of row m
+                        const size_t e0 = (size_t)m * D + j0;
+                        float zin[16], bs[32], mk[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = *reinterpret_cast<const float4 *>(ep.z + e0 + 4 * q);
+                            zin[4 * q] = v.x, zin[4 * q + 1] = v.y, zin[4 * q + 2] = v.z, zin[4 * q + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 v = *reinterpret_cast<const float4 *>(ep.bias + n0 + 4 * q);
+                            bs[4 * q] = v.x, bs[4 * q + 1] = v.y, bs[4 * q + 2] = v.z, bs[4 * q + 3] = v.w;
+                        }
+                        const uint64_t g0 = (uint64_t)ep.row_offset * D + e0;
+                        if (ep.mask) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 v = *reinterpret_cast<const float4 *>(ep.mask + e0 + 4 * q);
+                                mk[4 * q] = v.x, mk[4 * q + 1] = v.y, mk[4 * q + 2] = v.z, mk[4 * q + 3] = v.w;
+                            }
+                        } else {
+                            const uint32_t bits = philox_bits16(rng, g0, ep.noise_stream);
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) mk[u] = (float)((bits >> u) & 1u);
+                        }
+                        float zn[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const float shift = __uint_as_float(r[2 * u]) + bs[2 * u];
+                            const float scale = __uint_as_float(r[2 * u + 1]) + bs[2 * u + 1];
+                            const float gate = __fdividef(1.f, 1.f + __expf(-scale));  // torch.sigmoid, rnvp.py:35
+                            const float z1 = (1.f - mk[u]) * zin[u], z2 = mk[u] * zin[u];
+                            zn[u] = (z1 * gate + (1.f - gate) * shift) + z2;  // rnvp.py:37
+                            s_sum += (1.f - mk[u]) * __logf(gate);           // rnvp.py:36
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4 *>(ep.z + e0 + 4 * q) =
+                                make_float4(zn[4 * q], zn[4 * q + 1], zn[4 * q + 2], zn[4 * q + 3]);
+                        if (ep.mz_next) {
+                            float mn[16];
+                            if (ep.mask_next) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float4 v = *reinterpret_cast<const float4 *>(ep.mask_next + e0 + 4 * q);
+                                    mn[4 * q] = v.x, mn[4 * q + 1] = v.y, mn[4 * q + 2] = v.z, mn[4 * q + 3] = v.w;
+                                }
+                            } else {
+                                const uint32_t bits = philox_bits16(rng, g0, ep.next_stream);
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) mn[u] = (float)((bits >> u) & 1u);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                *reinterpret_cast<float4 *>(ep.mz_next + e0 + 4 * q) =
+                                    make_float4(rn_tf32(mn[4 * q] * zn[4 * q]), rn_tf32(mn[4 * q + 1] * zn[4 * q + 1]),
+                                                rn_tf32(mn[4 * q + 2] * zn[4 * q + 2]), rn_tf32(mn[4 * q + 3] * zn[4 * q + 3]));
+                        }
+                        if (ep.xz_out) {
+                            const float *xr = ep.xmul + (size_t)(m % ep.xmul_rows) * D + j0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 xv = *reinterpret_cast<const float4 *>(xr + 4 * q);
+                                *reinterpret_cast<float4 *>(ep.xz_out + e0 + 4 * q) =
+                                    make_float4(rn_tf32(xv.x * zn[4 * q]), rn_tf32(xv.y * zn[4 * q + 1]),
+                                                rn_tf32(xv.z * zn[4 * q + 2]), rn_tf32(xv.w * zn[4 * q + 3]));
                             }
                         }
                     }
@@ -368,7 +463,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             }
-            if (ep.mode == 3 && m < M) ep.ld_out[m] = (ep.ld_in ? ep.ld_in[m] : 0.f) + s_sum;  // maf.py:61
+            if (ep.mode == 3 && m < M) atomicAdd(&ep.ld_out[m], s_sum);  // maf.py:61 (ld_out pre-initialised by the host)
+            if (ep.mode == 4 && m < M) atomicAdd(&ep.ld_acc[m], s_sum);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty(acc));
             if (++acc == ACC_STAGES) {
@@ -506,7 +602,7 @@ int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const 
                           const float *b_mean, const float *b_log_var, const float *eps, uint64_t seed,
                           uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_rows, int n_in, int n_out,
                           int relu, float *workspace, void *stream) {
-    MNF_REQUIRE(x && z && W_mean && W_log_var && b_mean && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(x && W_mean && W_log_var && b_mean && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
     MNF_REQUIRE(n_rows >= 0 && n_rows <= 0x7fffffff - 256 && x_rows >= 1 && x_rows <= n_rows + (n_rows == 0), MNF_E_ARG,
                 "bad row counts");
     MNF_REQUIRE(n_in % 4 == 0, MNF_E_SHAPE, "tensor-core path needs n_in %% 4 == 0 (got %d)", n_in);
@@ -515,17 +611,21 @@ int mnf_linear_forward_tc(const float *x, int64_t x_rows, const float *z, const 
     float *xz = workspace, *expW = xz + (size_t)n_rows * n_in, *wm = expW + (size_t)n_out * n_in,
           *x2 = wm + (size_t)n_out * n_in, *sd = x2 + (size_t)x_rows * n_in;
     const int k4 = n_in / 4;
-    tc::xz_kernel<<<tc::blocks_for(n_rows * k4), 256, 0, st>>>((const float4 *)x, (const float4 *)z, (float4 *)xz, n_rows,
-                                                              (int)x_rows, k4);
+    if (z)  // z == NULL: the caller (mnf_rnvp_forward_tc) already left tf32(x*z) at the start of the workspace
+        tc::xz_kernel<<<tc::blocks_for(n_rows * k4), 256, 0, st>>>((const float4 *)x, (const float4 *)z, (float4 *)xz,
+                                                                  n_rows, (int)x_rows, k4);
     tc::unary_kernel<<<tc::blocks_for((long long)n_out * n_in), 256, 0, st>>>(W_log_var, expW, (long long)n_out * n_in, 1);
     tc::unary_kernel<<<tc::blocks_for((long long)n_out * n_in), 256, 0, st>>>(W_mean, wm, (long long)n_out * n_in, 0);
     tc::unary_kernel<<<tc::blocks_for(x_rows * n_in), 256, 0, st>>>(x, x2, x_rows * n_in, 2);
     int rc = launch_status("mnf_linear_forward_tc prologue");
     if (rc) return rc;
-    tc::Epilogue ev{2, nullptr, nullptr, 1, b_log_var, nullptr, 0, 0, 0, 0, sd, 0, nullptr, nullptr, nullptr, nullptr, 0};
+    tc::Epilogue ev{};
+    ev.mode = 2, ev.sd_rows = 1, ev.bvar_log = b_log_var, ev.out = sd;
     rc = tc::launch(x2, expW, (int)x_rows, n_out, n_in, ev, st);
     if (rc) return rc;
-    tc::Epilogue em{1, b_mean, sd, (int)x_rows, nullptr, eps, seed, noise_stream, row_offset, relu, out, 0, nullptr, nullptr, nullptr, nullptr, 0};
+    tc::Epilogue em{};
+    em.mode = 1, em.bias = b_mean, em.sd = sd, em.sd_rows = (int)x_rows, em.eps = eps, em.seed = seed;
+    em.noise_stream = noise_stream, em.row_offset = row_offset, em.relu = relu, em.out = out;
     return tc::launch(xz, wm, (int)n_rows, n_out, n_in, em, st);
 }
 
@@ -535,7 +635,8 @@ int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out,
     MNF_REQUIRE(A && W && out, MNF_E_ARG, "NULL pointer");
     MNF_REQUIRE(M >= 0 && M <= 0x7fffffff - 256 && N >= 1 && K >= 1, MNF_E_ARG, "bad shape");
     if (M == 0) return 0;
-    tc::Epilogue ep{0, bias, nullptr, 1, nullptr, nullptr, 0, 0, 0, relu, out, round_out, nullptr, nullptr, nullptr, nullptr, 0};
+    tc::Epilogue ep{};
+    ep.bias = bias, ep.sd_rows = 1, ep.relu = relu, ep.out = out, ep.round_out = round_out;
     return tc::launch(A, W, (int)M, N, K, ep, (cudaStream_t)stream);
 }
 
@@ -562,6 +663,7 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
     float *xr = workspace, *za = xr + (size_t)n_rows * dim, *zb = za + (size_t)n_rows * dim,
           *ha = zb + (size_t)n_rows * dim, *hb = ha + (size_t)n_rows * maxh;
     tc::unary_kernel<<<tc::blocks_for(n_rows * dim), 256, 0, st>>>(x, xr, n_rows * dim, 0);
+    MNF_CUDA(cudaMemsetAsync(log_det, 0, sizeof(float) * n_rows, st));  // epilogues accumulate into it
     int rc = launch_status("made round input");
     if (rc) return rc;
     const float *cur_exact = x;
@@ -573,7 +675,8 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
         int k = dim;
         float *hout = ha;
         for (int l = 0; l < L.n_hidden; ++l) {
-            tc::Epilogue ep{0, L.b[l], nullptr, 1, nullptr, nullptr, 0, 0, 0, 1, hout, 1, nullptr, nullptr, nullptr, nullptr, 0};
+            tc::Epilogue ep{};
+            ep.bias = L.b[l], ep.sd_rows = 1, ep.relu = 1, ep.out = hout, ep.round_out = 1;
             rc = tc::launch(a, L.w[l], (int)n_rows, L.hidden[l], k, ep, st);
             if (rc) return rc;
             a = hout;
@@ -583,8 +686,9 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
         const bool last = f == n_flows - 1;
         float *zout = intermediates ? intermediates + (size_t)f * n_rows * dim : (last ? z : (cur_exact == za ? zb : za));
         float *zround = last ? nullptr : xr;  // the rounded copy of the previous input is dead by now
-        tc::Epilogue ep{3, L.b_out, nullptr, 1, nullptr, nullptr, 0, 0, 0, 0, zout, 0, cur_exact, zround,
-                        f == 0 ? nullptr : log_det, log_det, L.parity};
+        tc::Epilogue ep{};
+        ep.mode = 3, ep.bias = L.b_out, ep.sd_rows = 1, ep.out = zout, ep.xin = cur_exact, ep.out_rounded = zround;
+        ep.ld_in = f == 0 ? nullptr : log_det, ep.ld_out = log_det, ep.parity = L.parity;
         rc = tc::launch(a, L.w_out, (int)n_rows, 2 * dim, k, ep, st);
         if (rc) return rc;
         cur_exact = zout;
@@ -597,6 +701,124 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
 
 int64_t mnf_made_workspace(int64_t n_rows, int dim, int max_hidden) {
     return n_rows * (3 * (int64_t)dim + 2 * (int64_t)max_hidden);
+}
+
+namespace mnf {
+namespace tc {
+
+constexpr int RNVP_HP = 64;  // conditioner width padded to one 64-wide tile / two K blocks
+
+// per flow: Wn_p [64, dim] (rows >= h zero), bn_p [64], Wts [2*dim, 64] interleaved (t_n, s_n) rows with K padded,
+// bts [2*dim]; everything TF32-rounded
+__global__ void rnvp_pack_kernel(const float *__restrict__ Wn, const float *__restrict__ bn,
+                                 const float *__restrict__ Wt, const float *__restrict__ bt,
+                                 const float *__restrict__ Ws, const float *__restrict__ bsc, int h, int dim,
+                                 float *__restrict__ Wn_p, float *__restrict__ bn_p, float *__restrict__ Wts,
+                                 float *__restrict__ bts) {
+    const long long n1 = (long long)RNVP_HP * dim, n2 = 2LL * dim * RNVP_HP;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n1 + n2; e += (long long)gridDim.x * blockDim.x) {
+        if (e < n1) {
+            const int j = (int)(e / dim), k = (int)(e % dim);
+            Wn_p[e] = j < h ? rn_tf32(Wn[(size_t)j * dim + k]) : 0.f;
+            if (k == 0) bn_p[j] = j < h ? bn[j] : 0.f;
+        } else {
+            const long long f = e - n1;
+            const int row = (int)(f / RNVP_HP), k = (int)(f % RNVP_HP), n = row >> 1;
+            const float *src = (row & 1) ? Ws : Wt;
+            Wts[f] = k < h ? rn_tf32(src[(size_t)n * h + k]) : 0.f;
+            if (k == 0) bts[row] = (row & 1) ? bsc[n] : bt[n];
+        }
+    }
+}
+
+// mz = tf32(mask * z) for the first flow of the stack
+__global__ void mask_mul_kernel(const float *__restrict__ z, const float *__restrict__ mask, float *__restrict__ mz,
+                                long long n_rows, int dim, uint64_t seed, uint32_t stream, uint64_t row_offset) {
+    const Philox rng(seed);
+    const long long total16 = n_rows * dim / 16;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total16; c += (long long)gridDim.x * blockDim.x) {
+        const long long e0 = c * 16;
+        const uint32_t bits = mask ? 0u : philox_bits16(rng, (uint64_t)row_offset * dim + e0, stream);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(z + e0 + 4 * q);
+            float m[4];
+            if (mask) {
+                const float4 mv = *reinterpret_cast<const float4 *>(mask + e0 + 4 * q);
+                m[0] = mv.x, m[1] = mv.y, m[2] = mv.z, m[3] = mv.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m[u] = (float)((bits >> (4 * q + u)) & 1u);
+            }
+            *reinterpret_cast<float4 *>(mz + e0 + 4 * q) =
+                make_float4(rn_tf32(m[0] * v.x), rn_tf32(m[1] * v.y), rn_tf32(m[2] * v.z), rn_tf32(m[3] * v.w));
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace mnf
+
+int64_t mnf_rnvp_tc_workspace(int n_flows, int64_t n_rows, int dim) {
+    const int64_t per_flow = (int64_t)tc::RNVP_HP * dim + tc::RNVP_HP + 2LL * dim * tc::RNVP_HP + 2LL * dim;
+    return n_rows * dim + n_rows * tc::RNVP_HP + n_flows * per_flow + 64;
+}
+
+// NormalizingFlow([RNVP...]).forward (core.py:17-25 over rnvp.py:25-39) on the tensor cores, in place on z.
+// Per flow: y = tf32(mask*z) Wn^T + bn (narrow-tile GEMM), then [shift | scale] = y [Wt; Ws]^T with the gated
+// update, the log-det row sum and the staging of the next GEMM's operand fused into the epilogue.
+// Needs single-Linear conditioners (h_sizes of length 1, width <= 64) and dim % 16 == 0.
+int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, float *log_det,
+                        const float *const *masks_host, uint64_t seed, uint32_t first_noise_stream, uint64_t row_offset,
+                        int64_t n_rows, int dim, const float *x, int64_t x_rows, float *xz_out, float *workspace,
+                        void *stream) {
+    MNF_REQUIRE(flows_host && z && log_det && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(n_flows >= 1 && n_rows >= 0 && n_rows <= 0x7fffffff - 256, MNF_E_ARG, "bad shape");
+    MNF_REQUIRE(dim % 16 == 0 && dim >= 32, MNF_E_SHAPE, "tensor-core RNVP needs dim %% 16 == 0 and dim >= 32 (got %d)", dim);
+    MNF_REQUIRE(!xz_out || (x && x_rows >= 1), MNF_E_ARG, "xz_out needs x");
+    for (int f = 0; f < n_flows; ++f)
+        MNF_REQUIRE(flows_host[f].n_net == 1 && flows_host[f].net_sizes[0] <= tc::RNVP_HP, MNF_E_SHAPE,
+                    "tensor-core RNVP needs a single-Linear conditioner of width <= %d", tc::RNVP_HP);
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *mz = workspace, *y = mz + (size_t)n_rows * dim, *wbase = y + (size_t)n_rows * tc::RNVP_HP;
+    wbase += (16 - ((uintptr_t)wbase / 4) % 16) % 16;  // keep every packed matrix 64-byte aligned
+    const size_t per_flow = (size_t)tc::RNVP_HP * dim + tc::RNVP_HP + 2ull * dim * tc::RNVP_HP + 2ull * dim;
+    MNF_CUDA(cudaMemsetAsync(log_det, 0, sizeof(float) * n_rows, st));
+    for (int f = 0; f < n_flows; ++f) {
+        const mnf_rnvp_flow &fl = flows_host[f];
+        float *Wn_p = wbase + f * per_flow, *bn_p = Wn_p + (size_t)tc::RNVP_HP * dim, *Wts = bn_p + tc::RNVP_HP,
+              *bts = Wts + 2ull * dim * tc::RNVP_HP;
+        tc::rnvp_pack_kernel<<<tc::blocks_for((long long)tc::RNVP_HP * dim * 3), 256, 0, st>>>(
+            fl.net_w[0], fl.net_b[0], fl.t_w, fl.t_b, fl.s_w, fl.s_b, fl.net_sizes[0], dim, Wn_p, bn_p, Wts, bts);
+    }
+    tc::mask_mul_kernel<<<tc::blocks_for(n_rows * dim / 16), 256, 0, st>>>(z, masks_host ? masks_host[0] : nullptr, mz,
+                                                                         n_rows, dim, seed, first_noise_stream, row_offset);
+    int rc = launch_status("rnvp tc prologue");
+    if (rc) return rc;
+    for (int f = 0; f < n_flows; ++f) {
+        float *Wn_p = wbase + f * per_flow, *bn_p = Wn_p + (size_t)tc::RNVP_HP * dim, *Wts = bn_p + tc::RNVP_HP,
+              *bts = Wts + 2ull * dim * tc::RNVP_HP;
+        tc::Epilogue e1{};
+        e1.bias = bn_p, e1.sd_rows = 1, e1.out = y, e1.round_out = 1;
+        rc = tc::launch(mz, Wn_p, (int)n_rows, tc::RNVP_HP, dim, e1, st);
+        if (rc) return rc;
+        const bool last = f == n_flows - 1;
+        tc::Epilogue e2{};
+        e2.mode = 4, e2.bias = bts, e2.sd_rows = 1, e2.z = z, e2.ld_acc = log_det, e2.seed = seed;
+        e2.row_offset = row_offset, e2.mask = masks_host ? masks_host[f] : nullptr;
+        e2.noise_stream = first_noise_stream + (uint32_t)f;
+        if (!last) {
+            e2.mz_next = mz;
+            e2.mask_next = masks_host ? masks_host[f + 1] : nullptr;
+            e2.next_stream = first_noise_stream + (uint32_t)f + 1;
+        } else if (xz_out) {
+            e2.xmul = x, e2.xmul_rows = (int)x_rows, e2.xz_out = xz_out;
+        }
+        rc = tc::launch(y, Wts, (int)n_rows, 2 * dim, tc::RNVP_HP, e2, st);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K) {

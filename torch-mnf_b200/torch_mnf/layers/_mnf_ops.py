@@ -50,6 +50,9 @@ _lib.register({
     "mnf_linear_tc_workspace": (_i64, [_i64, _i64, _int, _int]),
     "mnf_linear_forward_tc": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int,
                                      _int, _int, _vp, _vp]),
+    "mnf_rnvp_tc_workspace": (_i64, [_int, _i64, _int]),
+    "mnf_rnvp_forward_tc": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64, _i64,
+                                   _int, _vp, _i64, _vp, _vp, _vp]),
     "mnf_tc_linear": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
     "mnf_tc_eligible": (_int, [_vp, _vp, _i64, _int, _int]),
 })
@@ -168,6 +171,36 @@ def rnvp_stack_inplace(flows, z, noise: Noise, want_inter=False):
     return ld, inter
 
 
+def rnvp_tc_ok(flows, dim) -> bool:
+    return (len(flows) >= 1 and dim % 16 == 0 and dim >= 32
+            and all(len(f.net.linears()) == 1 and f.net.linears()[0].out_features <= 64 for f in flows))
+
+
+@torch.no_grad()
+def rnvp_stack_tc(flows, z, noise: Noise, x=None, x_rows=None, xz_out=None):
+    """Tensor-core variant of rnvp_stack_inplace; optionally leaves tf32(x*z_final) in xz_out."""
+    dev = z.device
+    R, dim = z.shape
+    n = len(flows)
+    keep = []
+    arr = (RnvpFlow * n)(*[_rnvp_struct(f, dev, keep)[0] for f in flows])
+    masks, first_sid = [], None
+    for _ in range(n):
+        m, sid = noise.bernoulli((R, dim))
+        masks.append(m)
+        first_sid = sid if first_sid is None else first_sid
+    mask_arr = (C.c_void_p * n)(*[m.data_ptr() for m in masks]) if masks[0] is not None else None
+    ld = torch.empty(R, device=dev, dtype=torch.float32)
+    lib = _lib.lib()
+    ws = torch.empty(lib.mnf_rnvp_tc_workspace(n, R, dim), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.mnf_rnvp_forward_tc(arr, n, z.data_ptr(), ld.data_ptr(), mask_arr, noise.seed, first_sid or 0,
+                                     noise.row_offset, R, dim, _p(x), x_rows or (x.size(0) if x is not None else 1),
+                                     _p(xz_out), ws.data_ptr(), _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_rnvp_forward_tc")
+    return ld
+
+
 def rnvp_stack(flows, z, tape, want_inter):
     """NormalizingFlow([RNVP...]).forward: returns (list incl. the input, log_det[B])."""
     z = _lib.require_cuda_f32(z, "input")
@@ -195,19 +228,21 @@ def use_tensor_cores(layer, n_rows, precision):
 
 
 @torch.no_grad()
-def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False, precision="auto"):
+def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False, precision="auto", staged_ws=None, n_rows=None):
+    """staged_ws: tensor-core workspace whose first n_rows*n_in floats already hold tf32(x*z) (z is then None)."""
     dev = x.device
-    R = z.size(0)
+    R = z.size(0) if z is not None else n_rows
     n_in, n_out = layer.W_mean.shape[1], layer.W_mean.shape[0]
     eps, sid = noise.normal((R, n_out))
     out = torch.empty((R, n_out), device=dev, dtype=torch.float32)
     args = [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
                                            (layer.b_mean, "b_mean"), (layer.b_log_var, "b_log_var"))]
-    if use_tensor_cores(layer, R, precision):
+    if staged_ws is not None or use_tensor_cores(layer, R, precision):
         xr = x_rows or x.size(0)
-        ws = torch.empty(_lib.lib().mnf_linear_tc_workspace(xr, R, n_in, n_out), device=dev, dtype=torch.float32)
+        ws = staged_ws if staged_ws is not None else torch.empty(
+            _lib.lib().mnf_linear_tc_workspace(xr, R, n_in, n_out), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            rc = _lib.lib().mnf_linear_forward_tc(x.data_ptr(), xr, z.data_ptr(), *(a.data_ptr() for a in args), _p(eps),
+            rc = _lib.lib().mnf_linear_forward_tc(x.data_ptr(), xr, _p(z), *(a.data_ptr() for a in args), _p(eps),
                                                   noise.seed, sid, noise.row_offset, out.data_ptr(), R, n_in, n_out,
                                                   int(relu), ws.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "mnf_linear_forward_tc")
