@@ -64,7 +64,11 @@ constexpr int kNumVariants = 4;
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int variant, float *workspace, cudaStream_t stream, bool plan_only) {
-    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows ? 3 : 2);
+    bool has_spline = false;
+    for (int k = 0; k < n_ops; ++k) has_spline |= ops[k].type == MNF_OP_NSF_CL;
+    // measured (r01): the constant-bank variant wins on spline stacks (4.10 vs 5.52 ms per 2^24 points) and loses
+    // slightly on pure AffineHalfFlow stacks (16.1 vs 15.0 ms), where a segment still holds two conditioners
+    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
     FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
     if (mode == 3 && inter && (n_rows % 2)) return 1;

@@ -524,6 +524,10 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
 // -> FFMA2, with no shared-memory or register-file traffic for weights.  Between segments the points
 // and the running log-det make one round trip through HBM (20 B/point, noise next to the FMA time).
 // =====================================================================================
+// launcher-internal op flags: an NSF_CL flow is cut into its two conditioner/spline halves, one per segment,
+// so a segment kernel holds ONE unrolled conditioner (~30 KB of code) instead of two
+constexpr uint32_t kFlagHalfA = 0x100u, kFlagHalfB = 0x200u;
+
 template <int H, int K>
 struct CbankLayout {
     static constexpr int kSpline = fast_net_slots(H, 3 * K - 1, 2);  // floats per staged spline conditioner
@@ -535,21 +539,27 @@ static_assert(CbankLayout<24, 8>::kSegStride <= kConstFloats, "segment nets must
 __device__ float g_flow_stage[MNF_MAX_OPS * 2 * 1900];  // staged nets of a whole program, execution order
 static_assert(CbankLayout<24, 8>::kSegStride <= 2 * 1900 && CbankLayout<16, 8>::kSegStride <= 2 * 1900, "stage size");
 
-// one CTA per (segment, net): re-lay-out the net from the parameter blob into the stage
+// one CTA per (segment, slot): re-lay-out the segment's net(s) from the parameter blob into the stage.
+// NSF_CL halves own one net (slot 0); an AffineHalfFlow segment owns s_net (slot 0) and t_net (slot 1).
 template <int H>
 __global__ void cbank_stage_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
-                                   int seg_stride, int second_off_spline, int second_off_affine, int inverse) {
+                                   int seg_stride, int second_off_affine, int inverse) {
     // prog is in EXECUTION order; segment index = number of net-bearing ops before this one
-    int target = blockIdx.x >> 1, which_exec = blockIdx.x & 1, seg = 0;
+    int target = blockIdx.x >> 1, slot = blockIdx.x & 1, seg = 0;
     for (int k = 0; k < prog.n_ops; ++k) {
         const mnf_flow_op &op = prog.ops[k];
         if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
         if (seg++ != target) continue;
-        int which = which_exec;  // AffineHalf: s then t.  NSF_CL: f1,f2 forward; f2,f1 inverse
-        if (op.type == MNF_OP_NSF_CL && inverse) which = 1 - which_exec;
-        if (op.type == MNF_OP_AFFINE_HALF && !(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) return;
-        const int second = op.type == MNF_OP_NSF_CL ? second_off_spline : second_off_affine;
-        stage_net<H, 3>(params + op.net_off[which], g_flow_stage + target * seg_stride + (which_exec ? second : 0),
+        int which = slot;
+        if (op.type == MNF_OP_NSF_CL) {
+            if (slot) return;
+            // forward: half A = f1, half B = f2 (spline_flow.py:249-266); inverse: half A = f2, half B = f1 (:268-285)
+            const bool half_b = op.flags & kFlagHalfB;
+            which = (half_b != (inverse != 0)) ? 1 : 0;
+        } else if (!(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) {
+            return;
+        }
+        stage_net<H, 3>(params + op.net_off[which], g_flow_stage + target * seg_stride + (slot ? second_off_affine : 0),
                         op.sizes[op.n_lin]);
         return;
     }
@@ -620,6 +630,7 @@ flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restr
         v1 = make_float2(q.y, q.y);
         if (ld_in) ld.x = ld.y = ld_in[2 * pair];
     }
+    int slot = 0;  // per-flow output slot within this segment
 #pragma unroll 1
     for (int kk = 0; kk < prog.n_ops; ++kk) {
         const mnf_flow_op &op = prog.ops[kk];
@@ -667,29 +678,25 @@ flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restr
             }
             if (parity) v0 = tr; else v1 = tr;
         } else if (op.type == MNF_OP_NSF_CL) {
-            // the stage holds the two conditioners in execution order: forward f1 (lower -> upper) then f2
-            // (upper -> lower), spline_flow.py:249-266; inverse f2 then f1, spline_flow.py:268-285
-            // step A conditions on v0 going forward (f1) and on v1 going backward (f2); step B the reverse
-            {
-                const float2 cond = inverse ? v1 : v0;
-                float2 tr = inverse ? v0 : v1;
-                cb_spline_half<H, K, 0>(op, cond, tr, inverse != 0, ld);
-                if (inverse) v0 = tr; else v1 = tr;
-            }
-            {
-                const float2 cond = inverse ? v0 : v1;
-                float2 tr = inverse ? v1 : v0;
-                cb_spline_half<H, K, L::kSpline>(op, cond, tr, inverse != 0, ld);
-                if (inverse) v1 = tr; else v0 = tr;
-            }
+            // one half of the coupling layer per segment (its conditioner sits at constant-bank offset 0).
+            // Half A conditions on v0 going forward (f1: lower -> upper) and on v1 going backward (f2);
+            // half B the other way round.
+            const bool cond_v0 = ((op.flags & kFlagHalfB) != 0) == (inverse != 0);
+            const float2 cond = cond_v0 ? v0 : v1;
+            float2 tr = cond_v0 ? v1 : v0;
+            cb_spline_half<H, K, 0>(op, cond, tr, inverse != 0, ld);
+            if (cond_v0) v1 = tr; else v0 = tr;
         }
+        // per-flow outputs are defined after the flow's LAST half
+        if ((op.flags & kFlagHalfA) != 0) continue;
         if (inter && live) {
-            float *dst = inter + ((size_t)kk * n_rows + 2 * pair) * 2;
+            float *dst = inter + ((size_t)slot * n_rows + 2 * pair) * 2;
             if (has_b)
                 st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
             else
                 st_stream2(reinterpret_cast<float2 *>(dst), make_float2(v0.x, v1.x));
         }
+        ++slot;
     }
     if (!live) return;
     const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
@@ -719,19 +726,31 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
                  cudaStream_t stream) {
     using L = CbankLayout<H, K>;
     const int inverse = dir_flags & 1;
-    FlowProgram exec;  // execution order
-    exec.n_ops = prog.n_ops;
-    for (int k = 0; k < prog.n_ops; ++k) exec.ops[k] = prog.ops[inverse ? prog.n_ops - 1 - k : k];
-    // segments: cut before every net-bearing op except the first
-    int seg_begin[MNF_MAX_OPS + 1], n_seg = 0, nets_seen = 0;
+    // execution order, NSF_CL flows cut into halves; every net-bearing entry starts a new segment
+    struct Exec {
+        int n = 0;
+        mnf_flow_op ops[2 * MNF_MAX_OPS];
+        int flow_index[2 * MNF_MAX_OPS];  // execution index of the flow an entry belongs to (for intermediates)
+    } ex;
+    for (int k = 0; k < prog.n_ops; ++k) {
+        const mnf_flow_op &op = prog.ops[inverse ? prog.n_ops - 1 - k : k];
+        if (op.type == MNF_OP_NSF_CL) {
+            ex.ops[ex.n] = op, ex.ops[ex.n].flags |= kFlagHalfA, ex.flow_index[ex.n++] = k;
+            ex.ops[ex.n] = op, ex.ops[ex.n].flags |= kFlagHalfB, ex.flow_index[ex.n++] = k;
+        } else {
+            ex.ops[ex.n] = op, ex.flow_index[ex.n++] = k;
+        }
+    }
+    int seg_begin[2 * MNF_MAX_OPS + 1], n_seg = 0, nets_seen = 0;
     seg_begin[n_seg++] = 0;
-    for (int k = 0; k < exec.n_ops; ++k) {
-        const bool net = exec.ops[k].type == MNF_OP_AFFINE_HALF || exec.ops[k].type == MNF_OP_NSF_CL;
+    for (int k = 0; k < ex.n; ++k) {
+        const bool net = ex.ops[k].type == MNF_OP_AFFINE_HALF || ex.ops[k].type == MNF_OP_NSF_CL;
         if (net && nets_seen++ > 0) seg_begin[n_seg++] = k;
     }
-    seg_begin[n_seg] = exec.n_ops;
+    seg_begin[n_seg] = ex.n;
     MNF_REQUIRE(n_seg == 1 || workspace != nullptr, MNF_E_ARG,
                 "multi-segment constant-bank run needs a workspace of 3*n_rows floats");
+    MNF_REQUIRE(nets_seen <= MNF_MAX_OPS, MNF_E_SHAPE, "too many conditioner nets for the stage (%d)", nets_seen);
 
     static ConstBankGuard guard;
     int dev = 0;
@@ -741,8 +760,12 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
     else MNF_CUDA(cudaStreamWaitEvent(stream, guard.done[dev], 0));  // other streams: wait, no host sync
 
     if (nets_seen > 0) {
-        cbank_stage_kernel<H><<<2 * nets_seen, 128, 0, stream>>>(exec, params, L::kSegStride, L::kSpline, L::kAffine,
-                                                                  inverse);
+        // the stage kernel walks net-bearing entries only; hand it those (<= MNF_MAX_OPS of them)
+        FlowProgram nets;
+        nets.n_ops = 0;
+        for (int k = 0; k < ex.n; ++k)
+            if (ex.ops[k].type == MNF_OP_AFFINE_HALF || ex.ops[k].type == MNF_OP_NSF_CL) nets.ops[nets.n_ops++] = ex.ops[k];
+        cbank_stage_kernel<H><<<2 * nets_seen, 128, 0, stream>>>(nets, params, L::kSegStride, L::kAffine, inverse);
         int rc = launch_status("cbank_stage_kernel");
         if (rc) return rc;
     }
@@ -757,7 +780,7 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
         sp.n_ops = seg_begin[sgm + 1] - seg_begin[sgm];
         bool has_net = false;
         for (int k = 0; k < sp.n_ops; ++k) {
-            sp.ops[k] = exec.ops[seg_begin[sgm] + k];
+            sp.ops[k] = ex.ops[seg_begin[sgm] + k];
             has_net |= sp.ops[k].type == MNF_OP_AFFINE_HALF || sp.ops[k].type == MNF_OP_NSF_CL;
         }
         if (has_net) {
@@ -766,9 +789,11 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
             ++net_idx;
         }
         const bool first = sgm == 0, last = sgm == n_seg - 1;
-        flow_cbank_kernel<H, K><<<blocks, 128, 0, stream>>>(
-            sp, params, first ? x : z_tmp, first ? nullptr : ld_tmp, last ? y : z_tmp, last ? log_det : ld_tmp,
-            last ? base_lp : nullptr, inter ? inter + (size_t)seg_begin[sgm] * n_rows * 2 : nullptr, n_rows, dir_flags);
+        // per-flow outputs: entry k of the segment writes slot flow_index (half A entries are skipped in-kernel)
+        float *inter_seg = inter ? inter + (size_t)ex.flow_index[seg_begin[sgm]] * n_rows * 2 : nullptr;
+        flow_cbank_kernel<H, K><<<blocks, 128, 0, stream>>>(sp, params, first ? x : z_tmp, first ? nullptr : ld_tmp,
+                                                            last ? y : z_tmp, last ? log_det : ld_tmp,
+                                                            last ? base_lp : nullptr, inter_seg, n_rows, dir_flags);
         rc = launch_status("flow_cbank_kernel");
         if (rc) break;
     }
