@@ -65,7 +65,9 @@ __device__ __forceinline__ float philox_bernoulli(const Philox &g, uint64_t e, u
 // SIMT GEMM skeleton.  NACC accumulator sets share one pass over K (NACC = 2: the MNF
 // mean / variance pair shares the x tile).  Problem functor interface:
 //   int M, N, K;
-//   void load_a(int m, int k, float (&a)[NACC])      -- value(s) of A' at (m, k), in range
+//   RowCtx row_ctx(int m)                             -- per-row addressing state, computed ONCE per thread and
+//                                                        tile row (keeps div/mod out of the K loop)
+//   void load_a(const RowCtx&, int m, int k, float (&a)[NACC]) -- value(s) of A' at (m, k), in range
 //   void load_b(int n, int k, float (&b)[NACC])      -- value(s) of B' at (n, k), in range
 //   void epilogue4(int m_base, int n, const float (&acc)[NACC][4], float (&rowsum)[4])
 //        -- one output column n, four consecutive rows m_base..m_base+3 (bounds on m are the
@@ -90,6 +92,13 @@ __global__ void __launch_bounds__(GTHREADS) simt_gemm_kernel(const Prob p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[s][i][j] = 0.f;
 
+    // a thread always loads the same 4 tile rows (idx / GBK is independent of k0): row contexts are hoisted
+    typename Prob::RowCtx rctx[(GBM * GBK) / GTHREADS];
+#pragma unroll
+    for (int e = 0; e < (GBM * GBK) / GTHREADS; ++e) {
+        const int mm = (tid + e * GTHREADS) / GBK;
+        rctx[e] = p.row_ctx(m0 + mm < p.M ? m0 + mm : 0);
+    }
     for (int k0 = 0; k0 < p.K; k0 += GBK) {
         // each thread loads 4 elements of the A tile and 4 of the B tile; k fastest for coalescing
 #pragma unroll
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(GTHREADS) simt_gemm_kernel(const Prob p) {
             float a[NACC], b[NACC];
 #pragma unroll
             for (int s = 0; s < NACC; ++s) a[s] = b[s] = 0.f;
-            if (m0 + mm < p.M && k0 + kk < p.K) p.load_a(m0 + mm, k0 + kk, a);
+            if (m0 + mm < p.M && k0 + kk < p.K) p.load_a(rctx[e], m0 + mm, k0 + kk, a);
             if (n0 + mm < p.N && k0 + kk < p.K) p.load_b(n0 + mm, k0 + kk, b);
 #pragma unroll
             for (int s = 0; s < NACC; ++s) {
@@ -146,9 +155,63 @@ __global__ void __launch_bounds__(GTHREADS) simt_gemm_kernel(const Prob p) {
     }
 }
 
+// M <= 4 rows (kl_div runs its RNVP stacks with ONE row): a 64-row tile would leave one CTA walking all of K.
+// Instead one CTA per output column reduces over K with all its threads (coalesced reads of the weight row).
+template <class Prob, int NACC>
+__global__ void __launch_bounds__(128) simt_gemv_kernel(const Prob p) {
+    __shared__ float red[NACC][4][4];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    float acc[NACC][4];
+#pragma unroll
+    for (int s = 0; s < NACC; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[s][i] = 0.f;
+    typename Prob::RowCtx rctx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rctx[i] = p.row_ctx(i < p.M ? i : 0);
+    for (int k = tid; k < p.K; k += 128) {
+        float b[NACC];
+        p.load_b(n, k, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < p.M) {
+                float a[NACC];
+                p.load_a(rctx[i], i, k, a);
+#pragma unroll
+                for (int s = 0; s < NACC; ++s) acc[s][i] = fmaf(a[s], b[s], acc[s][i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NACC; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = warp_sum(acc[s][i]);
+            if ((tid & 31) == 0) red[s][i][tid >> 5] = v;
+        }
+    __syncthreads();
+    if (tid == 0) {
+        float r[NACC][4], rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < NACC; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[s][i] = (red[s][i][0] + red[s][i][1]) + (red[s][i][2] + red[s][i][3]);
+        p.epilogue4(0, n, r, rowsum);
+        if constexpr (Prob::kRowReduce) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < p.M) p.row_out(i, rowsum[i]);
+        }
+    }
+}
+
 template <class Prob, int NACC>
 int launch_simt_gemm(const Prob &p, cudaStream_t stream, const char *what) {
     if (p.M <= 0 || p.N <= 0) return 0;
+    if (p.M <= 4 && p.K >= 256) {
+        simt_gemv_kernel<Prob, NACC><<<(unsigned)p.N, 128, 0, stream>>>(p);
+        return launch_status(what);
+    }
     dim3 grid((unsigned)((p.M + GBM - 1) / GBM), (unsigned)((p.N + GBN - 1) / GBN));
     if (grid.y > 65535) return fail(MNF_E_SHAPE, "%s: too many column tiles (%u)", what, grid.y);
     simt_gemm_kernel<Prob, NACC><<<grid, GTHREADS, 0, stream>>>(p);

@@ -45,21 +45,44 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
     const size_t base = (size_t)row * a.cols;
     const Philox rng(a.seed);
     float kl = 0.f, dot_mean = 0.f, dot_noise = 0.f;
-    for (int c = threadIdx.x; c < a.cols; c += blockDim.x) {
-        const size_t f = base + c;
-        const float lv = a.W_log_var[f];
+    auto element = [&](size_t f, int c, float wmean, float lv, float e) {
         const float var = expf(lv);
         const float zz = a.conv ? a.z[f / a.z_block] : a.z[c];
-        const float wm = a.W_mean[f] * zz;
+        const float wm = wmean * zz;
         kl += -logf(var) + var + wm * wm - 1.f;  // mnf_linear.py:73 / mnf_conv.py:99 (-W_var.log())
         const float rc = a.r0_c[c];
         dot_mean = fmaf(rc, wm, dot_mean);
         const float sd = sqrtf(var);
-        if (a.conv) {
-            dot_noise = fmaf(rc, sd, dot_noise);  // W_std row . r0_c; scaled by eps_w[row] below
-        } else {
-            const float e = a.eps ? a.eps[f] : philox_normal(rng, f, a.noise_stream);
-            dot_noise = fmaf(rc, sd * e, dot_noise);
+        dot_noise = fmaf(rc, a.conv ? sd : sd * e, dot_noise);  // conv: W_std row . r0_c, scaled by eps_w[row] below
+    };
+    if ((a.cols & 3) == 0) {
+        // float4 path: one pass over W_mean / W_log_var (and eps_w) at full sector width; one Philox block gives
+        // the four normals of four consecutive elements (same mapping as philox_normal)
+        for (int c = 4 * threadIdx.x; c < a.cols; c += 4 * blockDim.x) {
+            const size_t f = base + c;
+            const float4 wm4 = *reinterpret_cast<const float4 *>(a.W_mean + f);
+            const float4 lv4 = *reinterpret_cast<const float4 *>(a.W_log_var + f);
+            float e4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!a.conv) {
+                if (a.eps) {
+                    const float4 q = *reinterpret_cast<const float4 *>(a.eps + f);
+                    e4[0] = q.x, e4[1] = q.y, e4[2] = q.z, e4[3] = q.w;
+                } else {
+                    const uint4 q = rng((uint64_t)f >> 2, a.noise_stream);
+                    const float2 n01 = box_muller(q.x, q.y), n23 = box_muller(q.z, q.w);
+                    e4[0] = n01.x, e4[1] = n01.y, e4[2] = n23.x, e4[3] = n23.y;
+                }
+            }
+            element(f, c, wm4.x, lv4.x, e4[0]);
+            element(f + 1, c + 1, wm4.y, lv4.y, e4[1]);
+            element(f + 2, c + 2, wm4.z, lv4.z, e4[2]);
+            element(f + 3, c + 3, wm4.w, lv4.w, e4[3]);
+        }
+    } else {
+        for (int c = threadIdx.x; c < a.cols; c += blockDim.x) {
+            const size_t f = base + c;
+            const float e = a.conv ? 0.f : (a.eps ? a.eps[f] : philox_normal(rng, f, a.noise_stream));
+            element(f, c, a.W_mean[f], a.W_log_var[f], e);
         }
     }
     kl = block_sum(kl, red);

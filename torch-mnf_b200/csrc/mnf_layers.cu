@@ -62,7 +62,9 @@ struct LinearProb {
     float *C;
     int leaky;
     static constexpr bool kRowReduce = false;
-    __device__ void load_a(int m, int k, float (&a)[1]) const { a[0] = A[(size_t)m * K + k]; }
+    using RowCtx = size_t;
+    __device__ RowCtx row_ctx(int m) const { return (size_t)m * K; }
+    __device__ void load_a(const RowCtx &r, int, int k, float (&a)[1]) const { a[0] = A[r + k]; }
     __device__ void load_b(int n, int k, float (&v)[1]) const { v[0] = W[(size_t)n * K + k]; }
     __device__ void epilogue4(int m0, int n, const float (&acc)[1][4], float (&)[4]) const {
 #pragma unroll
@@ -84,8 +86,10 @@ struct RnvpHiddenProb {
     NoiseSrc mask;
     int leaky;
     static constexpr bool kRowReduce = false;
-    __device__ void load_a(int m, int k, float (&a)[1]) const {
-        const long long e = (long long)m * K + k;
+    using RowCtx = long long;
+    __device__ RowCtx row_ctx(int m) const { return (long long)m * K; }
+    __device__ void load_a(const RowCtx &r, int, int k, float (&a)[1]) const {
+        const long long e = r + k;
         a[0] = noise_bernoulli(mask, e, (long long)mask.row_offset * K + e) * z[e];
     }
     __device__ void load_b(int n, int k, float (&v)[1]) const { v[0] = Wn[(size_t)n * K + k]; }
@@ -109,7 +113,9 @@ struct RnvpOutProb {
     float *logdet;  // [M], accumulated with atomics over column tiles (zeroed by the caller)
     NoiseSrc mask;
     static constexpr bool kRowReduce = true;
-    __device__ void load_a(int m, int k, float (&a)[2]) const { a[0] = a[1] = y[(size_t)m * K + k]; }
+    using RowCtx = size_t;
+    __device__ RowCtx row_ctx(int m) const { return (size_t)m * K; }
+    __device__ void load_a(const RowCtx &r, int, int k, float (&a)[2]) const { a[0] = a[1] = y[r + k]; }
     __device__ void load_b(int n, int k, float (&v)[2]) const {
         v[0] = Wt[(size_t)n * K + k];
         v[1] = Ws[(size_t)n * K + k];
@@ -143,9 +149,13 @@ struct MnfLinearProb {
     NoiseSrc eps;
     int relu;
     static constexpr bool kRowReduce = false;
-    __device__ void load_a(int m, int k, float (&a)[2]) const {
-        const float xv = x[(size_t)(m % x_rows) * K + k];
-        a[0] = xv * z[(size_t)m * K + k];
+    struct RowCtx {
+        size_t xo, zo;
+    };
+    __device__ RowCtx row_ctx(int m) const { return RowCtx{(size_t)(m % x_rows) * K, (size_t)m * K}; }
+    __device__ void load_a(const RowCtx &r, int, int k, float (&a)[2]) const {
+        const float xv = x[r.xo + k];
+        a[0] = xv * z[r.zo + k];
         a[1] = xv * xv;
     }
     __device__ void load_b(int n, int k, float (&v)[2]) const {
@@ -196,11 +206,17 @@ struct MnfConvProb {
             r = m / (OW * OH);
         }
     }
-    __device__ void load_a(int m, int k, float (&a)[2]) const {
+    // offset of filter tap k inside an image, (ci*H + ky)*W + kx, tabulated on the host (K <= kMaxTaps)
+    static constexpr int kMaxTaps = 640;
+    int koff[kMaxTaps];
+    using RowCtx = size_t;  // offset of the output pixel's receptive-field origin in x
+    __device__ RowCtx row_ctx(int m) const {
         int r, oy, ox;
         decode(m, r, oy, ox);
-        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
-        const float xv = x[(((size_t)(r % x_imgs) * C + ci) * H + oy + ky) * W + ox + kx];
+        return ((size_t)(r % x_imgs) * C * H + oy) * W + ox;
+    }
+    __device__ void load_a(const RowCtx &r, int, int k, float (&a)[2]) const {
+        const float xv = x[r + koff[k]];
         a[0] = xv;
         a[1] = xv * xv;
     }
@@ -320,8 +336,14 @@ int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const flo
                 "fused 2x2 max-pool needs even output size, got %dx%d", OH, OW);
     const long long M = (long long)n_imgs * OH * OW;
     MNF_REQUIRE(M <= 0x7fffffff - 64, MNF_E_SHAPE, "too many output pixels for one call (%lld): chunk the batch", M);
+    MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "c_in*k*k = %d exceeds %d filter taps",
+                c_in * ksize * ksize, MnfConvProb::kMaxTaps);
     MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)x_imgs, c_in, height, width, ksize, OH, OW,
-                  W_mean, W_log_var, b_log_var, z, out, NoiseSrc{eps, seed, noise_stream, row_offset}, relu_pool};
+                  W_mean, W_log_var, b_log_var, z, out, NoiseSrc{eps, seed, noise_stream, row_offset}, relu_pool, {}};
+    for (int k = 0; k < p.K; ++k) {
+        const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
+        p.koff[k] = (ci * height + ky) * width + kx;
+    }
     return launch_simt_gemm<MnfConvProb, 2>(p, (cudaStream_t)stream, "mnf_conv2d_forward");
 }
 

@@ -65,6 +65,9 @@ class Noise:
     per-draw stream ids."""
 
     def __init__(self, tape, device, row_offset: int = 0, seed: int | None = None):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.tape, self.device, self.row_offset = tape, device, int(row_offset)
         self.streams = 0
         if tape is None and seed is None:
