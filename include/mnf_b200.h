@@ -240,6 +240,28 @@ int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const flo
                        uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_imgs, int c_in,
                        int height, int width, int c_out, int ksize, int relu_pool, void *stream);
 
+/* Pieces of the MNF-LeNet Monte-Carlo pipeline (models/mnf_lenet.py:13-26 driven as in mnf_mnist.ipynb:316-318).
+ * mnf_conv2d_moments: the sample-independent mean and standard deviation of an MNFConv2d (z is shared by the
+ *   call, mnf_conv.py:72), [n_imgs, c_out, OH, OW] each.
+ * mnf_conv_noise_relu_pool: out[r] = maxpool2(relu(mean[r % n_unique] + sd[r % n_unique] * eps[r])).
+ * mnf_conv2d_forward_tc: MNFConv2d.forward + ReLU + MaxPool2d(2) as im2col + two TF32 tensor-core GEMMs
+ *   (workspace: mnf_conv_tc_workspace() floats; tolerance class 2e-3). */
+int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                       const float *b_log_var, float *mean_out, float *sd_out, int64_t n_imgs, int c_in,
+                       int height, int width, int c_out, int ksize, void *stream);
+int mnf_conv_noise_relu_pool(const float *mean, const float *sd, int64_t n_unique, const float *eps,
+                             uint64_t seed, uint32_t noise_stream, uint64_t row_offset, float *out,
+                             int64_t n_rows, int channels, int out_h, int out_w, void *stream);
+int64_t mnf_conv_tc_workspace(int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize);
+int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                          const float *b_log_var, const float *eps, uint64_t seed, uint32_t noise_stream,
+                          uint64_t row_offset, float *out, int64_t n_imgs, int c_in, int height, int width,
+                          int c_out, int ksize, float *workspace, void *stream);
+int mnf_conv_tc_stage(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                      const float *b_log_var, float *a_mean, float *a_var, float *Bm, float *Bv, float *bvar_p,
+                      int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize, int Np, int Kp,
+                      void *stream);
+
 /* Weight-space part of MNFLinear.kl_div (mnf_linear.py:66-90, conv = 0) and MNFConv2d.kl_div
  * (mnf_conv.py:90-133, conv = 1).  z / ld_q come from sample_z (flow_q), zT / ld_r from
  * flow_r.forward(z); both are produced by mnf_rnvp_forward with one row.  out[0] is the KL

@@ -102,3 +102,29 @@ def test_maf_stack_tensor_core_density_vs_golden():
     zs2, ld2 = model.inverse(x)
     assert len(zs2) == 2 and torch.equal(zs2[-1], zs[-1])
     torch.testing.assert_close(ld2, ld, rtol=1e-5, atol=1e-5)  # row sums are accumulated with atomics
+
+
+def test_mnf_lenet_mc_pipeline_tensor_cores():
+    """MNF-LeNet Monte-Carlo pipeline (conv1 moments once per image, conv2 / fc1 on tensor cores) vs the oracle on
+    identical injected noise: tf32 tolerance class on the log-probabilities, exact MC-mean argmax."""
+    from oracle import mnf_cpu
+    from tests.test_mnf_gpu import _lenet, lenet_draws, seeded_tape
+
+    g, net = _lenet()
+    sd = golden_sd(g)
+    gen = torch.Generator().manual_seed(7)
+    labels = torch.randint(0, 10, (32,), generator=gen)
+    x = (t(g, "templates")[labels] + 0.25 * torch.randn(32, 1, 28, 28, generator=gen)).clamp(0, 1)
+    S, R = 16, 512
+    assert R >= net.TC_MIN_ROWS
+    ref = mnf_cpu.lenet_forward(sd, x.repeat(S, 1, 1, 1), seeded_tape(lenet_draws(R), 3))
+    y = net(x.cuda(), noise=seeded_tape(lenet_draws(R), 3), n_samples=S).cpu()
+    # log-probs of confidently rejected classes are very negative; compare on the probability scale as well
+    torch.testing.assert_close(y.exp(), ref.exp(), rtol=2e-2, atol=2e-3)
+    big = ref > -10
+    torch.testing.assert_close(y[big], ref[big], rtol=2e-3, atol=2e-2)
+    p_ref, p = ref.exp().view(S, 32, 10).mean(0), y.exp().view(S, 32, 10).mean(0)
+    assert torch.equal(p.argmax(1), p_ref.argmax(1))
+    net.precision = "fp32"
+    y32 = net(x.cuda(), noise=seeded_tape(lenet_draws(R), 3), n_samples=S).cpu()
+    torch.testing.assert_close(y32, ref, rtol=1e-4, atol=2e-4)

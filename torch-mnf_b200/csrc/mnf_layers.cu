@@ -191,6 +191,7 @@ struct MnfConvProb {
     float *out;                   // [R, N, OH, OW] or pooled [R, N, OH/2, OW/2]
     NoiseSrc eps;                 // indexed like the un-pooled output [R, N, OH, OW]
     int pool;
+    float *sd_out;                // moments mode: out <- mean, sd_out <- sqrt(var), no noise
     static constexpr bool kRowReduce = false;
     __device__ __forceinline__ void decode(int m, int &r, int &oy, int &ox) const {
         if (pool) {
@@ -235,6 +236,11 @@ struct MnfConvProb {
             decode(m, r, oy, ox);
             const long long e = (((long long)r * N + n) * OH + oy) * OW + ox;
             const long long ge = ((((long long)r + (long long)eps.row_offset) * N + n) * OH + oy) * OW + ox;
+            if (sd_out) {
+                out[e] = acc[0][i];
+                sd_out[e] = sqrtf(acc[1][i] + bvar);
+                continue;
+            }
             const float v = acc[0][i] + sqrtf(acc[1][i] + bvar) * noise_normal(eps, e, ge);  // b_mean == 0
             if (pool)
                 best = fmaxf(best, v);
@@ -250,11 +256,172 @@ struct MnfConvProb {
     __device__ void row_out(int, float) const {}
 };
 
+// out[r, c, py, px] = max over the 2x2 window of relu(mean[b] + sd[b] * eps[r]),  b = r % n_unique:
+// the noise / ReLU / MaxPool2d(2) tail of an MNFConv2d whose mean and variance do not depend on the sample
+// (z is shared by the whole call, mnf_conv.py:72, so under MC replication they are per-IMAGE quantities).
+__global__ void conv_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd, int n_unique,
+                                       NoiseSrc eps, float *__restrict__ out, long long n_rows, int C, int OH, int OW) {
+    // one thread = two horizontally adjacent pooled pixels = a 2 x 4 patch of the un-pooled map, so that each
+    // Philox block (4 consecutive elements) is generated once and fully used.  Needs OW % 4 == 0 (host checks).
+    const int PH = OH >> 1, PW = OW >> 1, PW2 = PW >> 1;
+    const long long total = n_rows * C * PH * PW2;
+    const Philox rng(eps.seed);
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
+         o += (long long)gridDim.x * blockDim.x) {
+        const int px2 = (int)(o % PW2), py = (int)((o / PW2) % PH), c = (int)((o / ((long long)PW2 * PH)) % C);
+        const long long r = o / ((long long)PW2 * PH * C);
+        const size_t ub = (((size_t)(r % n_unique) * C + c) * OH + 2 * py) * OW + 4 * px2;
+        const long long le = ((r * C + c) * OH + 2 * py) * OW + 4 * px2;  // index in the un-pooled [R, C, OH, OW]
+        const long long ge = le + (long long)eps.row_offset * C * OH * OW;
+        float best0 = 0.f, best1 = 0.f;  // ReLU floor
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const float4 m4 = *reinterpret_cast<const float4 *>(mean + ub + dy * OW);
+            const float4 s4 = *reinterpret_cast<const float4 *>(sd + ub + dy * OW);
+            float4 n4;
+            if (eps.ptr) {
+                n4 = *reinterpret_cast<const float4 *>(eps.ptr + le + dy * OW);
+            } else {
+                const uint4 q = rng((uint64_t)(ge + (long long)dy * OW) >> 2, eps.stream);
+                const float2 a = box_muller(q.x, q.y), b = box_muller(q.z, q.w);
+                n4 = make_float4(a.x, a.y, b.x, b.y);
+            }
+            best0 = fmaxf(best0, fmaxf(fmaf(s4.x, n4.x, m4.x), fmaf(s4.y, n4.y, m4.y)));
+            best1 = fmaxf(best1, fmaxf(fmaf(s4.z, n4.z, m4.z), fmaf(s4.w, n4.w, m4.w)));
+        }
+        *reinterpret_cast<float2 *>(out + ((r * C + c) * PH + py) * PW + 2 * px2) = make_float2(best0, best1);
+    }
+}
+
+// im2col for the tensor-core conv: row m is pool-major (4 consecutive rows = one 2x2 window of one image),
+// column k = (ci, ky, kx) padded with zeros to Kp; writes tf32(x) and tf32(x^2)
+__global__ void __launch_bounds__(256)
+conv_im2col_kernel(const float *__restrict__ x, float *__restrict__ a_mean, float *__restrict__ a_var,
+                   long long n_imgs, int C, int H, int W, int ks, int OH, int OW, int Kp) {
+    // one CTA per image: the image (C*H*W floats) and the tap-offset table live in shared memory, the CTA
+    // then streams out its OH*OW rows of Kp columns as float4 (the kernel is write-bound: 2 * 4 * Kp bytes/row)
+    extern __shared__ float sm[];
+    float *xs = sm;
+    int *koff = reinterpret_cast<int *>(sm + C * H * W);
+    const int K = C * ks * ks, PW = OW >> 1, rows = OH * OW, k4n = Kp >> 2;
+    auto rn = [](float f) {
+        uint32_t b;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(f));
+        return __uint_as_float(b);
+    };
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
+        koff[k] = k < K ? (ci * H + ky) * W + kx : -1;
+    }
+    for (long long img = blockIdx.x; img < n_imgs; img += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C * H * W; i += blockDim.x) xs[i] = x[(size_t)img * C * H * W + i];
+        __syncthreads();
+        for (int t = threadIdx.x; t < rows * k4n; t += blockDim.x) {
+            const int k4 = t % k4n, ml = t / k4n;  // ml: pool-major row inside the image
+            const int q = ml & 3, w = ml >> 2;
+            const int px = w % PW, py = w / PW;
+            const int base = (2 * py + (q >> 1)) * W + 2 * px + (q & 1);
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int off = koff[4 * k4 + u];
+                v[u] = off >= 0 ? xs[base + off] : 0.f;
+            }
+            const size_t o = ((size_t)img * rows + ml) * Kp + 4 * k4;
+            *reinterpret_cast<float4 *>(a_mean + o) = make_float4(rn(v[0]), rn(v[1]), rn(v[2]), rn(v[3]));
+            *reinterpret_cast<float4 *>(a_var + o) =
+                make_float4(rn(v[0] * v[0]), rn(v[1] * v[1]), rn(v[2] * v[2]), rn(v[3] * v[3]));
+        }
+    }
+}
+
+// weights of the tensor-core conv: Bm[n][k] = tf32(W_mean[n][k] * z[n]), Bv[n][k] = tf32(exp(W_log_var[n][k])),
+// rows padded to Np and columns to Kp with zeros; bvar_p[n] = b_log_var[n] (0 in the padding)
+__global__ void conv_pack_weights_kernel(const float *__restrict__ Wm, const float *__restrict__ Wlv,
+                                         const float *__restrict__ blv, const float *__restrict__ z, int N, int K,
+                                         int Np, int Kp, float *__restrict__ Bm, float *__restrict__ Bv,
+                                         float *__restrict__ bvar_p) {
+    auto rn = [](float f) {
+        uint32_t b;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(f));
+        return __uint_as_float(b);
+    };
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Np * Kp; e += gridDim.x * blockDim.x) {
+        const int n = e / Kp, k = e % Kp;
+        const bool in = n < N && k < K;
+        Bm[e] = in ? rn(Wm[(size_t)n * K + k] * z[n]) : 0.f;
+        Bv[e] = in ? rn(expf(Wlv[(size_t)n * K + k])) : 0.f;
+        if (k == 0) bvar_p[n] = n < N ? blv[n] : 0.f;
+    }
+}
+
 }  // namespace mnf
 
 using namespace mnf;
 
 extern "C" {
+
+// mean = conv2d(x, W_mean * z), sd = sqrt(conv2d(x^2, exp(W_log_var)) + exp(b_log_var)) without noise
+// ([n_imgs, c_out, OH, OW] each): the sample-independent part of MNFConv2d.forward (mnf_conv.py:69-75).
+int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                       const float *b_log_var, float *mean_out, float *sd_out, int64_t n_imgs, int c_in, int height,
+                       int width, int c_out, int ksize, void *stream) {
+    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && mean_out && sd_out, MNF_E_ARG, "NULL pointer");
+    const int OH = height - ksize + 1, OW = width - ksize + 1;
+    MNF_REQUIRE(n_imgs >= 0 && OH >= 1 && OW >= 1, MNF_E_SHAPE, "bad shape");
+    const long long M = (long long)n_imgs * OH * OW;
+    MNF_REQUIRE(M <= 0x7fffffff - 64, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
+    MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "too many filter taps");
+    MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)(n_imgs > 0 ? n_imgs : 1), c_in, height, width, ksize,
+                  OH, OW, W_mean, W_log_var, b_log_var, z, mean_out, NoiseSrc{nullptr, 0, 0, 0}, 0, sd_out, {}};
+    for (int k = 0; k < p.K; ++k) {
+        const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
+        p.koff[k] = (ci * height + ky) * width + kx;
+    }
+    return launch_simt_gemm<MnfConvProb, 2>(p, (cudaStream_t)stream, "mnf_conv2d_moments");
+}
+
+// out[r] = maxpool2(relu(mean[r % n_unique] + sd[r % n_unique] * eps[r])) -- the per-sample tail of an MNFConv2d
+// under Monte-Carlo replication.  eps: [n_rows, c, OH, OW] or NULL (Philox, same element numbering).
+int mnf_conv_noise_relu_pool(const float *mean, const float *sd, int64_t n_unique, const float *eps, uint64_t seed,
+                             uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_rows, int channels,
+                             int out_h, int out_w, void *stream) {
+    MNF_REQUIRE(mean && sd && out, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(n_rows >= 0 && n_unique >= 1 && out_h % 2 == 0 && out_w % 4 == 0, MNF_E_SHAPE,
+                "conv output %dx%d: height must be even and width a multiple of 4", out_h, out_w);
+    MNF_REQUIRE(((uintptr_t)mean % 16) == 0 && ((uintptr_t)sd % 16) == 0 && (!eps || ((uintptr_t)eps % 16) == 0) &&
+                    ((uintptr_t)out % 8) == 0 && ((row_offset * channels * out_h * out_w) % 4) == 0,
+                MNF_E_ALIGN, "pointers must be 16-byte aligned");
+    if (n_rows == 0) return 0;
+    const long long total = (long long)n_rows * channels * (out_h / 2) * (out_w / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    conv_noise_pool_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        mean, sd, (int)n_unique, NoiseSrc{eps, seed, noise_stream, row_offset}, out, n_rows, channels, out_h, out_w);
+    return launch_status("conv_noise_pool_kernel");
+}
+
+// staging for mnf_conv2d_forward_tc (tc_gemm.cu): im2col of x and x^2 (pool-major rows) and packed weights
+int mnf_conv_tc_stage(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                      const float *b_log_var, float *a_mean, float *a_var, float *Bm, float *Bv, float *bvar_p,
+                      int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize, int Np, int Kp,
+                      void *stream) {
+    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && a_mean && a_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
+    const int OH = height - ksize + 1, OW = width - ksize + 1, K = c_in * ksize * ksize;
+    MNF_REQUIRE(OH >= 2 && OW >= 2 && OH % 2 == 0 && OW % 2 == 0 && Kp % 4 == 0 && Kp >= K && Np >= c_out, MNF_E_SHAPE,
+                "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    conv_pack_weights_kernel<<<64, 256, 0, st>>>(W_mean, W_log_var, b_log_var, z, c_out, K, Np, Kp, Bm, Bv, bvar_p);
+    const size_t smem = sizeof(float) * ((size_t)c_in * height * width + Kp);
+    MNF_REQUIRE(smem <= 200 * 1024, MNF_E_SHAPE, "image of %d x %d x %d floats does not fit shared memory", c_in, height, width);
+    if (smem > 48 * 1024)
+        MNF_CUDA(cudaFuncSetAttribute(conv_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long blocks = n_imgs < 148 * 8 ? n_imgs : 148 * 8;
+    if (blocks < 1) blocks = 1;
+    conv_im2col_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, a_mean, a_var, n_imgs, c_in, height, width, ksize, OH, OW, Kp);
+    return launch_status("conv tc staging");
+}
 
 int mnf_sample_z0(const float *q0_mean, const float *q0_log_var, const float *eps, uint64_t seed,
                   uint32_t noise_stream, uint64_t row_offset, float *z, int64_t n_rows, int dim, void *stream) {
@@ -339,7 +506,8 @@ int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const flo
     MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "c_in*k*k = %d exceeds %d filter taps",
                 c_in * ksize * ksize, MnfConvProb::kMaxTaps);
     MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)x_imgs, c_in, height, width, ksize, OH, OW,
-                  W_mean, W_log_var, b_log_var, z, out, NoiseSrc{eps, seed, noise_stream, row_offset}, relu_pool, {}};
+                  W_mean, W_log_var, b_log_var, z, out, NoiseSrc{eps, seed, noise_stream, row_offset}, relu_pool,
+                  nullptr, {}};
     for (int k = 0; k < p.K; ++k) {
         const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
         p.koff[k] = (ci * height + ky) * width + kx;

@@ -74,6 +74,10 @@ struct Epilogue {
     const float *xmul;
     int xmul_rows;
     float *xz_out;
+    // mode 5 (MNFConv2d tail on an im2col GEMM whose rows are pool-major): v = acc + sd[m, n] * eps, ReLU, max over
+    // the 4 consecutive rows of a 2x2 window (4 adjacent TMEM lanes -> two shuffles), out[r, n, py, px].
+    // sd: [M, N] (row stride N); eps indexed like the un-pooled [R, conv_c, conv_oh, conv_ow] tensor.
+    int conv_c, conv_oh, conv_ow;
 };
 
 // 16 Bernoulli(0.5) bits for 16 consecutive elements starting at global index e0 (a multiple of 16), identical to
@@ -307,6 +311,36 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                         make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
                             }
                         }
+                    }
+                } else if (ep.mode == 5) {
+                    // rows of a warp are 32 consecutive pool-major rows = 8 windows; all lanes take part in the shuffles
+                    const int OH = ep.conv_oh, OW = ep.conv_ow, PW = OW >> 1, PH = OH >> 1, Cc = ep.conv_c;
+                    const int mm = m < M ? m : M - 1;
+                    const int q = mm & 3, w = mm >> 2;
+                    const int px = w % PW, py = (w / PW) % PH;
+                    const long long rr = w / (PW * PH);
+                    const int oy = 2 * py + (q >> 1), ox = 2 * px + (q & 1);
+                    const float *sdrow = ep.sd + (size_t)mm * N + n0;
+                    float sdv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4 *>(sdrow + j);
+                        sdv[j] = b.x, sdv[j + 1] = b.y, sdv[j + 2] = b.z, sdv[j + 3] = b.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + j;
+                        float v = 0.f;
+                        if (n < Cc) {
+                            const long long le = ((rr * Cc + n) * OH + oy) * OW + ox;
+                            const float nz = ep.eps ? ep.eps[le]
+                                                    : philox_normal(rng, (uint64_t)(le + (long long)ep.row_offset * Cc * OH * OW),
+                                                                    ep.noise_stream);
+                            v = fmaxf(fmaf(sdv[j], nz, __uint_as_float(r[j])), 0.f);
+                        }
+                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+                        if (q == 0 && m < M && n < Cc) ep.out[((rr * Cc + n) * PH + py) * PW + px] = v;
                     }
                 } else if (ep.mode == 4) {
                     if (m < M) {
@@ -819,6 +853,49 @@ int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, 
         if (rc) return rc;
     }
     return 0;
+}
+
+int mnf_conv_tc_stage(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                      const float *b_log_var, float *a_mean, float *a_var, float *Bm, float *Bv, float *bvar_p,
+                      int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize, int Np, int Kp,
+                      void *stream);
+
+int64_t mnf_conv_tc_workspace(int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize) {
+    const int OH = height - ksize + 1, OW = width - ksize + 1;
+    const int64_t Kp = (c_in * ksize * ksize + 31) / 32 * 32, Np = (c_out + 31) / 32 * 32;
+    const int64_t M = n_imgs * OH * OW;
+    return 2 * M * Kp + M * Np + 2 * Np * Kp + Np + 64;
+}
+
+// MNFConv2d.forward + ReLU + MaxPool2d(2) (mnf_conv.py:67-78, mnf_lenet.py:16-21) on the tensor cores:
+// im2col (pool-major rows, TF32-rounded x and x^2) -> variance GEMM (sd = sqrt(. + exp(b_log_var))) -> mean GEMM whose
+// epilogue adds sd * eps, applies ReLU and the 2x2 max-pool.  out: [n_imgs, c_out, OH/2, OW/2].
+int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, const float *W_log_var,
+                          const float *b_log_var, const float *eps, uint64_t seed, uint32_t noise_stream,
+                          uint64_t row_offset, float *out, int64_t n_imgs, int c_in, int height, int width, int c_out,
+                          int ksize, float *workspace, void *stream) {
+    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
+    const int OH = height - ksize + 1, OW = width - ksize + 1;
+    MNF_REQUIRE(OH >= 2 && OW >= 2 && OH % 2 == 0 && OW % 2 == 0, MNF_E_SHAPE, "output %dx%d must be even for the pool", OH, OW);
+    MNF_REQUIRE(c_out <= tc::MAX_BN, MNF_E_SHAPE, "c_out=%d exceeds one column tile", c_out);
+    const int Kp = (c_in * ksize * ksize + 31) / 32 * 32, Np = (c_out + 31) / 32 * 32;
+    const long long M = (long long)n_imgs * OH * OW;
+    MNF_REQUIRE(n_imgs >= 0 && M <= 0x7fffffff - 256, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
+    if (n_imgs == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *a_mean = workspace, *a_var = a_mean + (size_t)M * Kp, *sd = a_var + (size_t)M * Kp, *Bm = sd + (size_t)M * Np,
+          *Bv = Bm + (size_t)Np * Kp, *bvar_p = Bv + (size_t)Np * Kp;
+    int rc = mnf_conv_tc_stage(x, z, W_mean, W_log_var, b_log_var, a_mean, a_var, Bm, Bv, bvar_p, n_imgs, c_in, height,
+                               width, c_out, ksize, Np, Kp, stream);
+    if (rc) return rc;
+    tc::Epilogue ev{};
+    ev.mode = 2, ev.sd_rows = 1, ev.bvar_log = bvar_p, ev.out = sd;
+    rc = tc::launch(a_var, Bv, (int)M, Np, Kp, ev, st);
+    if (rc) return rc;
+    tc::Epilogue em{};
+    em.mode = 5, em.sd = sd, em.sd_rows = 1, em.eps = eps, em.seed = seed, em.noise_stream = noise_stream;
+    em.row_offset = row_offset, em.out = out, em.conv_c = c_out, em.conv_oh = OH, em.conv_ow = OW;
+    return tc::launch(a_mean, Bm, (int)M, Np, Kp, em, st);
 }
 
 int mnf_tc_eligible(const float *A, const float *W, int64_t M, int N, int K) {

@@ -53,6 +53,12 @@ _lib.register({
     "mnf_rnvp_tc_workspace": (_i64, [_int, _i64, _int]),
     "mnf_rnvp_forward_tc": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64, _i64,
                                    _int, _vp, _i64, _vp, _vp, _vp]),
+    "mnf_conv2d_moments": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp]),
+    "mnf_conv_noise_relu_pool": (_int, [_vp, _vp, _i64, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _vp]),
+    "mnf_conv_tc_workspace": (_i64, [_i64, _int, _int, _int, _int, _int]),
+    "mnf_conv2d_forward_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _int,
+                                     _int, _vp, _vp]),
+    "mnf_conv_tc_stage": (_int, [_vp] * 10 + [_i64, _int, _int, _int, _int, _int, _int, _int, _vp]),
     "mnf_tc_linear": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
     "mnf_tc_eligible": (_int, [_vp, _vp, _i64, _int, _int]),
 })
@@ -227,7 +233,7 @@ def use_tensor_cores(layer, n_rows, precision):
         if not ok:
             raise ValueError(f"tf32 tensor-core path needs n_in % 4 == 0, n_in >= 32, n_out >= 8 (got {n_in}, {n_out})")
         return True
-    return ok and n_rows * n_in * n_out >= TC_MIN_WORK and n_in >= 128 and n_out >= 64
+    return ok and n_rows * n_in * n_out >= TC_MIN_WORK and n_in >= 128 and n_out >= 32
 
 
 @torch.no_grad()
@@ -278,6 +284,56 @@ def conv_forward(layer, x, z, noise: Noise, n_imgs=None, relu_pool=False):
                                            int(relu_pool), _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv2d_forward")
     _lib.launch_count += 1
+    return out
+
+
+def _conv_args(layer, dev):
+    return [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
+                                           (layer.b_log_var, "b_log_var"))]
+
+
+@torch.no_grad()
+def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows):
+    """maxpool2(relu(MNFConv2d(x.repeat(...)))) for n_rows = len(x) * S rows: mean and variance are evaluated once
+    per distinct image (z is shared by the call), only the noise / ReLU / pool tail runs per sample."""
+    dev = x.device
+    B, c_in, H, W = x.shape
+    c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
+    OH, OW = H - ks + 1, W - ks + 1
+    mean = torch.empty((B, c_out, OH, OW), device=dev, dtype=torch.float32)
+    sd = torch.empty_like(mean)
+    args = _conv_args(layer, dev)
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = lib.mnf_conv2d_moments(x.data_ptr(), z.data_ptr(), *(a.data_ptr() for a in args), mean.data_ptr(),
+                                    sd.data_ptr(), B, c_in, H, W, c_out, ks, _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_conv2d_moments")
+    eps, sid = noise.normal((n_rows, c_out, OH, OW))
+    out = torch.empty((n_rows, c_out, OH // 2, OW // 2), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = lib.mnf_conv_noise_relu_pool(mean.data_ptr(), sd.data_ptr(), B, _p(eps), noise.seed, sid, noise.row_offset,
+                                          out.data_ptr(), n_rows, c_out, OH, OW, _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_conv_noise_relu_pool")
+    return out
+
+
+@torch.no_grad()
+def conv_forward_tc(layer, x, z, noise: Noise):
+    """maxpool2(relu(MNFConv2d(x))) through im2col + TF32 tensor-core GEMMs."""
+    dev = x.device
+    R, c_in, H, W = x.shape
+    c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
+    OH, OW = H - ks + 1, W - ks + 1
+    eps, sid = noise.normal((R, c_out, OH, OW))
+    out = torch.empty((R, c_out, OH // 2, OW // 2), device=dev, dtype=torch.float32)
+    lib = _lib.lib()
+    ws = torch.empty(lib.mnf_conv_tc_workspace(R, c_in, H, W, c_out, ks), device=dev, dtype=torch.float32)
+    args = _conv_args(layer, dev)
+    with torch.cuda.device(dev):
+        rc = lib.mnf_conv2d_forward_tc(x.data_ptr(), z.data_ptr(), *(a.data_ptr() for a in args), _p(eps), noise.seed, sid,
+                                       noise.row_offset, out.data_ptr(), R, c_in, H, W, c_out, ks, ws.data_ptr(),
+                                       _lib.stream_ptr(dev))
+    _lib.check(rc, "mnf_conv2d_forward_tc")
     return out
 
 

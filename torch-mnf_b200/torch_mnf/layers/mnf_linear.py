@@ -50,10 +50,11 @@ class MNFLinear(nn.Module):
         ld, _ = ops.rnvp_stack_inplace(list(self.flow_q.flows), z, noise)
         return z, ld.squeeze()
 
-    def _forward_rows(self, x, n_rows, noise, relu):
+    def _forward_rows(self, x, n_rows, noise, relu, precision=None):
         """forward over n_rows output rows, row r reading x[r % len(x)]."""
+        precision = precision or self.precision
         flows_q = list(self.flow_q.flows)
-        if ops.use_tensor_cores(self, n_rows, self.precision) and ops.rnvp_tc_ok(flows_q, self.n_in):
+        if ops.use_tensor_cores(self, n_rows, precision) and ops.rnvp_tc_ok(flows_q, self.n_in):
             # all-tensor-core pipeline: the last RNVP epilogue leaves tf32(x*z) where the mean GEMM expects it
             ws = torch.empty(_lib.lib().mnf_linear_tc_workspace(x.size(0), n_rows, self.n_in, self.n_out),
                              device=x.device, dtype=torch.float32)
@@ -61,11 +62,11 @@ class MNFLinear(nn.Module):
             ops.rnvp_stack_tc(flows_q, z, noise, x=x, x_rows=x.size(0), xz_out=ws)
             return ops.linear_forward(self, x, None, noise, x_rows=x.size(0), relu=relu, staged_ws=ws, n_rows=n_rows)
         z, _ = self.sample_z(n_rows, noise)
-        return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=self.precision)
+        return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=precision)
 
-    def forward(self, x, noise=None, row_offset=0, relu=False):
+    def forward(self, x, noise=None, row_offset=0, relu=False, precision=None):
         x = _lib.require_cuda_f32(x, "input")
-        return self._forward_rows(x, x.size(0), self._noise(noise, x.device, row_offset), relu)
+        return self._forward_rows(x, x.size(0), self._noise(noise, x.device, row_offset), relu, precision)
 
     def forward_mc(self, x, n_samples, noise=None, row_offset=0, relu=False):
         """== forward(x.repeat(n_samples, 1)): row r uses x[r % len(x)], own z and eps per row."""

@@ -30,15 +30,27 @@ class MNFLeNet(nn.Sequential):
             MNFLinear(50, 10, **kwargs), nn.LogSoftmax(dim=-1),
         )
 
+    #: "auto": batches of >= TC_MIN_ROWS rows take the Monte-Carlo pipeline (conv1 moments once per image, conv2 and
+    #: fc1 on TF32 tensor cores; tolerance class 2e-3); "fp32": exact-fp32 kernels throughout
+    precision = "auto"
+    TC_MIN_ROWS = 512
+
     def forward(self, x, noise=None, n_samples: int = 1, row_offset: int = 0, seed=None):
         x = _lib.require_cuda_f32(x, "input")
         R = x.size(0) * n_samples
         nz = ops.Noise(noise, x.device, row_offset, seed=seed)
-        h = self[0].forward(x, nz, relu_pool=True, n_imgs=R)
-        h = self[3].forward(h, nz, relu_pool=True)
+        if self.precision != "fp32" and R >= self.TC_MIN_ROWS:
+            z1, _ = self[0].sample_z(nz)
+            h = ops.conv_mc_relu_pool(self[0], x, z1, nz, R)
+            z2, _ = self[3].sample_z(nz)
+            h = ops.conv_forward_tc(self[3], h, z2, nz)
+        else:
+            h = self[0].forward(x, nz, relu_pool=True, n_imgs=R)
+            h = self[3].forward(h, nz, relu_pool=True)
         h = h.view(R, -1)
-        h = self[7].forward(h, nz, relu=True)
-        h = self[9].forward(h, nz)
+        prec = "fp32" if self.precision == "fp32" else None
+        h = self[7].forward(h, nz, relu=True, precision=prec)
+        h = self[9].forward(h, nz, precision=prec)
         return torch.log_softmax(h, dim=-1)
 
     def kl_div(self, noise=None):
