@@ -202,7 +202,10 @@ int64_t mnf_rnvp_tc_workspace(int n_flows, int64_t n_rows, int dim);
 int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, float *log_det,
                         const float *const *masks_host, uint64_t seed, uint32_t first_noise_stream,
                         uint64_t row_offset, int64_t n_rows, int dim, const float *x, int64_t x_rows,
-                        float *xz_out, float *workspace, void *stream);
+                        float *xz_out, float *workspace,
+                        /* optional: draw z0 = q0_mean + sqrt(exp(q0_log_var)) * eps_z here (z is then output only) */
+                        const float *q0_mean, const float *q0_log_var, const float *eps_z, uint32_t eps_stream,
+                        void *stream);
 
 /* out = A W^T (+ bias) (+ ReLU) on the tensor cores: A [M,K], W [N,K] (torch Linear layout). */
 int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K,

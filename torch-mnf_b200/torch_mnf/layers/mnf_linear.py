@@ -58,8 +58,13 @@ class MNFLinear(nn.Module):
             # all-tensor-core pipeline: the last RNVP epilogue leaves tf32(x*z) where the mean GEMM expects it
             ws = torch.empty(_lib.lib().mnf_linear_tc_workspace(x.size(0), n_rows, self.n_in, self.n_out),
                              device=x.device, dtype=torch.float32)
-            z = ops.sample_z0(self.q0_mean, self.q0_log_var, n_rows, noise)
-            ops.rnvp_stack_tc(flows_q, z, noise, x=x, x_rows=x.size(0), xz_out=ws)
+            ok4 = self.n_in % 4 == 0 and (noise.row_offset * self.n_in) % 16 == 0
+            if ok4:  # z0 drawn inside the RNVP call (one pass less over z)
+                ops.rnvp_stack_tc(flows_q, None, noise, x=x, x_rows=x.size(0), xz_out=ws,
+                                  q0=(self.q0_mean, self.q0_log_var), n_rows=n_rows)
+            else:
+                z = ops.sample_z0(self.q0_mean, self.q0_log_var, n_rows, noise)
+                ops.rnvp_stack_tc(flows_q, z, noise, x=x, x_rows=x.size(0), xz_out=ws)
             return ops.linear_forward(self, x, None, noise, x_rows=x.size(0), relu=relu, staged_ws=ws, n_rows=n_rows)
         z, _ = self.sample_z(n_rows, noise)
         return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=precision)
