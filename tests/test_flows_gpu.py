@@ -214,3 +214,22 @@ def test_full_size_properties_cfg2():
     # checksum against the oracle on a strided sample
     idx = torch.arange(0, 1 << 24, 4099, device="cuda")
     close_vs_oracle((zs[-1][idx], ld[idx]), sd, specs, x[idx].cpu(), True, "sampled")
+
+
+def test_conditioner_free_stack_streaming_kernel():
+    """[ActNorm, Glow] x 3 in 2-D is a single affine map: the composed streaming kernel (HBM-bound path) must agree
+    with the oracle and with the op-by-op kernel."""
+    specs = [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}, {"type": "Glow", "dim": 2}] * 3
+    sd = random_flow_sd(specs, seed=5, scale=0.4)
+    model = load_flow_model(specs, sd, return_intermediates=False)
+    g = torch.Generator().manual_seed(2)
+    x = 2.0 * torch.randn(40000, 2, generator=g)
+    for inverse in (True, False):
+        ref, ref_ld = flows_cpu.stack(sd, specs, x, inverse=inverse)
+        y, ld, _, _ = model._program().run(x.cuda(), inverse)             # composed streaming path
+        y2, ld2, _, _ = model._program().run(x.cuda(), inverse, kernel=2)  # op-by-op register-resident kernel
+        for a, b in ((y, ld), (y2, ld2)):
+            torch.testing.assert_close(a.cpu(), ref[-1], rtol=1e-5, atol=2e-5)
+            torch.testing.assert_close(b.cpu(), ref_ld, rtol=1e-5, atol=1e-5)
+    lp = model.log_prob(x.cuda())
+    torch.testing.assert_close(lp.cpu(), flows_cpu.log_prob(sd, specs, x), rtol=1e-5, atol=5e-5)

@@ -44,7 +44,7 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
             slots += per_net;
         }
     }
-    if (H == 0) return p;  // nothing for this kernel to accelerate -> generic handles it
+    if (H == 0) H = 8, K = 5;  // conditioner-free stack (ActNorm / Glow only): pure streaming, any instantiation does
     if (K == 0) K = 8;
     const bool have = (H == 16 && K == 8) || (H == 24 && K == 8) || (H == 8 && K == 5);
     if (!have) return p;
@@ -60,6 +60,90 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
 constexpr long long kCbankMinRows = 1 << 16;
 constexpr int kNumVariants = 4;
 
+// ---------------------------------------------------------------------------------------------------
+// Conditioner-free stacks (AffineConstantFlow / ActNormFlow / Glow only, dim 2): the whole stack is ONE
+// affine map v -> v A + b with a constant log-det.  A one-thread kernel composes it (fp64) from the packed
+// parameters, then a streaming kernel applies it: 8 points per thread in flight, 128-bit accesses, nothing
+// but HBM traffic (8 B in, 8 B out, 4 B log-det per point) -- the one flow kernel that is truly HBM-bound.
+// ---------------------------------------------------------------------------------------------------
+__global__ void affine_compose_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
+                                      int inverse, float *__restrict__ comp) {
+    double A[4] = {1, 0, 0, 1}, b[2] = {0, 0}, ld = 0;
+    for (int kk = 0; kk < prog.n_ops; ++kk) {
+        const mnf_flow_op &op = prog.ops[inverse ? prog.n_ops - 1 - kk : kk];
+        double W[4], t[2] = {0, 0};
+        if (op.type == MNF_OP_AFFINE_CONST) {
+            const double s0 = params[op.aux_off], s1 = params[op.aux_off + 1];
+            const double t0 = params[op.aux_off + 2], t1 = params[op.aux_off + 3];
+            if (inverse) {  // (v - t) * exp(-s), affine_constant_flow.py:24
+                W[0] = exp(-s0), W[3] = exp(-s1), W[1] = W[2] = 0;
+                t[0] = -t0 * W[0], t[1] = -t1 * W[3];
+                ld -= s0 + s1;
+            } else {  // v * exp(s) + t, affine_constant_flow.py:19
+                W[0] = exp(s0), W[3] = exp(s1), W[1] = W[2] = 0;
+                t[0] = t0, t[1] = t1;
+                ld += s0 + s1;
+            }
+        } else {  // Glow: v @ W (glow.py:28) or v @ W^-1 (glow.py:36)
+            const float *Wp = params + op.aux_off + (inverse ? 4 : 0);
+            for (int i = 0; i < 4; ++i) W[i] = Wp[i];
+            ld += inverse ? -(double)params[op.aux_off + 8] : (double)params[op.aux_off + 8];
+        }
+        const double n00 = A[0] * W[0] + A[1] * W[2], n01 = A[0] * W[1] + A[1] * W[3];
+        const double n10 = A[2] * W[0] + A[3] * W[2], n11 = A[2] * W[1] + A[3] * W[3];
+        const double nb0 = b[0] * W[0] + b[1] * W[2] + t[0], nb1 = b[0] * W[1] + b[1] * W[3] + t[1];
+        A[0] = n00, A[1] = n01, A[2] = n10, A[3] = n11, b[0] = nb0, b[1] = nb1;
+    }
+    for (int i = 0; i < 4; ++i) comp[i] = (float)A[i];
+    comp[4] = (float)b[0], comp[5] = (float)b[1], comp[6] = (float)ld;
+}
+
+__global__ void __launch_bounds__(256)
+affine_stream_kernel(const float *__restrict__ comp, const float4 *__restrict__ x, float4 *__restrict__ y,
+                     float2 *__restrict__ log_det, float2 *__restrict__ base_lp, long long n_pairs, int sum_lp) {
+    const float a00 = comp[0], a01 = comp[1], a10 = comp[2], a11 = comp[3], b0 = comp[4], b1 = comp[5], ld = comp[6];
+    const float c = -1.8378770664093453f;
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < n_pairs; p0 += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (p0 + u * stride < n_pairs) v[u] = ld_stream4(x + p0 + u * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long p = p0 + u * stride;
+            if (p >= n_pairs) break;
+            const float4 q = v[u];
+            const float4 o = make_float4(fmaf(q.y, a10, fmaf(q.x, a00, b0)), fmaf(q.y, a11, fmaf(q.x, a01, b1)),
+                                         fmaf(q.w, a10, fmaf(q.z, a00, b0)), fmaf(q.w, a11, fmaf(q.z, a01, b1)));
+            if (y) st_stream4(y + p, o);
+            if (log_det) st_stream2(log_det + p, make_float2(ld, ld));
+            if (base_lp) {
+                float2 lp = make_float2(fmaf(-0.5f, fmaf(o.x, o.x, o.y * o.y), c), fmaf(-0.5f, fmaf(o.z, o.z, o.w * o.w), c));
+                if (sum_lp) lp = make_float2(lp.x + ld, lp.y + ld);
+                st_stream2(base_lp + p, lp);
+            }
+        }
+    }
+}
+
+static int launch_affine_stream(const FlowProgram &prog, const float *params, const float *x, float *y, float *log_det,
+                                float *base_lp, int64_t n_rows, int dir_flags, float *workspace, const DeviceProps *dp,
+                                cudaStream_t stream) {
+    affine_compose_kernel<<<1, 1, 0, stream>>>(prog, params, dir_flags & 1, workspace);
+    int rc = launch_status("affine_compose_kernel");
+    if (rc) return rc;
+    const long long n_pairs = n_rows / 2;
+    long long blocks = (n_pairs + 256 * 4 - 1) / (256 * 4);
+    const long long cap = (long long)dp->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    affine_stream_kernel<<<(unsigned)blocks, 256, 0, stream>>>(workspace, (const float4 *)x, (float4 *)y, (float2 *)log_det,
+                                                             (float2 *)base_lp, n_pairs, (dir_flags & 2) != 0);
+    return launch_status("affine_stream_kernel");
+}
+
 // returns 1 if the program is not eligible (caller falls back to the generic kernel)
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
@@ -69,6 +153,9 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     // measured (r01): the constant-bank variant wins on spline stacks (4.10 vs 5.52 ms per 2^24 points) and loses
     // slightly on pure AffineHalfFlow stacks (16.1 vs 15.0 ms), where a segment still holds two conditioners
     int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
+    bool has_net = false;
+    for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
+    if (!has_net && mode == 3) mode = 2;
     FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
     if (mode == 3 && inter && (n_rows % 2)) return 1;
@@ -87,6 +174,8 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     prog.n_ops = n_ops;
     for (int k = 0; k < n_ops; ++k) prog.ops[k] = ops[k];
     (void)n_params;
+    if (!has_net && variant < 0 && !inter && workspace && n_rows % 2 == 0 && n_rows >= 2)
+        return launch_affine_stream(prog, params, x, y, log_det, base_lp, n_rows, inverse, workspace, dp, stream);
     if (p.H == 16 && p.K == 8)
         return launch_fast_16_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
                                 workspace, dp, stream);
