@@ -187,3 +187,20 @@ def test_philox_mode_statistics_and_sharding():
     mr, sr = ref.mean(0), ref.std(0)
     assert ((m - mr).abs() < 6 * sr / R**0.5 + 1e-4).all(), (m, mr)
     assert ((s / sr - 1).abs() < 0.05).all(), (s, sr)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_mnf_lenet_mc_sharding_invariance(precision):
+    """Splitting the MC samples over two 'ranks' (row_offset, same seed) reproduces the single-device run: conv z is
+    shared by all ranks, per-row noise is keyed by the global row."""
+    g, net = _lenet()
+    net.precision = precision
+    x = t(g, "x")[:4].cuda().repeat(8, 1, 1, 1)  # 32 images
+    S = 32  # 1024 rows: above the tensor-core threshold in "auto"
+    full = net(x, n_samples=S, seed=77)
+    half = S // 2
+    lo = net(x, n_samples=half, seed=77, row_offset=0)
+    hi = net(x, n_samples=half, seed=77, row_offset=half * x.size(0))
+    both = torch.cat([lo, hi])
+    torch.testing.assert_close(both, full, rtol=1e-5, atol=1e-5)
+    assert not torch.equal(net(x, n_samples=S, seed=78), full)

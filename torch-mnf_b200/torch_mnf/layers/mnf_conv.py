@@ -38,8 +38,14 @@ class MNFConv2d(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
         noise = noise if isinstance(noise, ops.Noise) else ops.Noise(noise, dev)
-        z = ops.sample_z0(self.q0_mean, self.q0_log_var, -1, noise)
-        ld, _ = ops.rnvp_stack_inplace(list(self.flow_q.flows), z, noise)
+        # z is ONE draw shared by the whole call (mnf_conv.py:80-88): it must not depend on which shard of the
+        # rows this rank owns, so it is drawn at row offset 0 whatever the caller's offset is
+        keep, noise.row_offset = noise.row_offset, 0
+        try:
+            z = ops.sample_z0(self.q0_mean, self.q0_log_var, -1, noise)
+            ld, _ = ops.rnvp_stack_inplace(list(self.flow_q.flows), z, noise)
+        finally:
+            noise.row_offset = keep
         return z, ld.squeeze()
 
     def forward(self, x, noise=None, row_offset=0, relu_pool=False, n_imgs=None):
