@@ -202,12 +202,37 @@ def run_ours(args):
     cn = n // chunks
     x_host = make_points(n, seed=100 + rank).pin_memory()
     x = x_host.to(dev, non_blocking=True)
-    # gather buffer [chunk][rank][cn]; the kernel writes this rank's slice directly
-    gathered = torch.empty((chunks, world, cn), device=dev, dtype=torch.float32)
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    # Result gather.  Preferred: NVLink peer memory -- the kernel stores each log-prob into every rank's gather
+    # buffer while it computes (torch_mnf.distributed.PeerGather: NVLS multicast or per-peer stores), so the step
+    # has no data-moving collective, only barriers.  Fallback (--gather nccl, or no symmetric memory): chunked
+    # NCCL all-gather on a side stream; the kernel writes this rank's slice of the gather buffer directly.
+    peer = None
+    if world > 1 and args.gather == "peer":
+        try:
+            from torch_mnf.distributed import PeerGather
+
+            peer = PeerGather(n, dev)
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+            peer = None
+    if peer is not None:
+        chunks = 1
+        cn = n
+        gathered = peer.buffer.view(1, world, n)
+        gather_out = peer.gather_out(use_multicast=not args.no_multicast)
+    else:
+        gathered = torch.empty((chunks, world, cn), device=dev, dtype=torch.float32)
+        gather_out = None
+    comm = torch.cuda.Stream(device=dev) if (world > 1 and peer is None) else None
 
     def step():
         cur = torch.cuda.current_stream(dev)
+        if peer is not None:
+            peer.barrier()  # peers are done reading the previous step's results
+            model.log_prob(x, out=gathered[0, rank], gather=gather_out)
+            peer.barrier()  # every rank's stores have landed everywhere
+            return
         for c in range(chunks):
             model.log_prob(x[c * cn:(c + 1) * cn], out=gathered[c, rank])
             if world > 1:
@@ -246,6 +271,15 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         total_ms = float(tmax)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    gather_ok = True
+    if world > 1:
+        # every rank must now hold every rank's log-probs: compare a checksum per slice with an all-gather of the
+        # owners' checksums
+        mine = gathered.view(-1, world, cn)[:, rank].double().sum().reshape(1)
+        sums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        seen = torch.stack([gathered.view(-1, world, cn)[:, r].double().sum() for r in range(world)])
+        gather_ok = bool(torch.allclose(seen, torch.cat(sums), rtol=1e-9, atol=1e-6))
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
 
@@ -328,13 +362,16 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "points_per_gpu": n, "l2": "inputs (134 MB/GPU) larger than the 126 MB L2",
-                   "collective": f"all_gather of log-probs in {chunks} chunks overlapped with compute" if world > 1
-                   else "none (N=1)", "parallelism": f"points sharded over {world} GPU(s), weights replicated"},
+                   "collective": ("none (N=1)" if world == 1 else
+                                  ("fused in the kernel: log-probs stored to every rank over NVLink peer memory ("
+                                   + ("NVLS multicast multimem.st" if gather_out.multicast_ptr else "per-peer st.global")
+                                   + "), 2 barriers per step") if peer is not None else
+                                  f"NCCL all_gather of log-probs in {chunks} chunks overlapped with compute"), "parallelism": f"points sharded over {world} GPU(s), weights replicated"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * n,
                 "ms_per_step": e_ms, "matches_resident_path": bool(chk),
                 "how": f"pinned host -> {e_chunks} chunks double-buffered over 3 streams -> NormalizingFlowModel.log_prob -> pinned host"},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "gather_verified": gather_ok,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_STEP * n / N_POINTS,
                      "kernel": "flow_cbank_kernel<16,8> x6 segments (+ cbank_stage_kernel)",
@@ -476,6 +513,9 @@ def main():
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU (default 2^24)")
     ap.add_argument("--chunks", type=int, default=4, help="all-gather chunks per step when N>1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1 result gather: fused peer-memory stores (default) or NCCL all-gather")
+    ap.add_argument("--no-multicast", action="store_true", help="peer gather: per-peer stores even if NVLS multicast exists")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
                     help="cfg2 (default, the headline flow log-prob line) or cfg4 (MNF-LeNet MC prediction)")
     ap.add_argument("--mc-samples", type=int, default=64, help="cfg4: MC samples per image per GPU per step")

@@ -104,10 +104,26 @@ typedef struct mnf_flow_op {
  *                  MNF_RUN_LOGPROB makes base_log_prob receive log_det + base log-density, i.e.
  *                  log p(x) of tests/test_flows.py:22-24 in one pass.
  * Replaces NormalizingFlow.forward/inverse (flows/core.py:17-35). */
+/* Optional fused result gather over NVLink / NVSwitch peer memory: besides base_log_prob the kernel stores every
+ * log-probability straight into the gather buffers of the other ranks (peer-mapped device pointers, e.g. from
+ * torch.distributed._symmetric_memory) at element row_offset + i -- or, when multicast_ptr is set, with ONE
+ * multimem.st per element that the switch replicates to every rank.  The data transfer overlaps the kernel's
+ * arithmetic; the only collective left after the launch is a barrier.  Supported by the constant-bank dim-2
+ * kernel in MNF_RUN_LOGPROB mode. */
+#define MNF_MAX_PEERS 8
+typedef struct mnf_gather_out {
+    int32_t n_peers;                 /* entries of peer_ptrs in use (0 with multicast)       */
+    int32_t reserved;
+    int64_t row_offset;              /* first element of this rank's slice in every gather buffer */
+    float *peer_ptrs[MNF_MAX_PEERS]; /* base of the [world * n_rows] buffer on each OTHER rank */
+    float *multicast_ptr;            /* NVLS multicast address of the same buffer, or NULL    */
+} mnf_gather_out;
+
 int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *params,
                        int64_t n_params, const float *x, float *y, float *log_det,
                        float *base_log_prob, float *intermediates, int64_t n_rows, int dim,
-                       int flags, float *workspace, void *stream);
+                       int flags, float *workspace, const mnf_gather_out *gather /* may be NULL */,
+                       void *stream);
 
 /* Floats of scratch `workspace` must provide for a run of this shape (0 = none needed; NULL is then
  * accepted).  The constant-bank variant of the dim-2 kernel parks points and log-dets there between

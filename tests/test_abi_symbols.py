@@ -40,6 +40,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.FlowOp) == 4 * (5 + 7 + 2 + 2)  # mnf_flow_op: 16 32-bit words
     assert ctypes.sizeof(RnvpFlow) == 4 * 5 + 4 + 8 * (4 + 4 + 4)  # n_net, sizes[4], pad, 12 pointers
     assert ctypes.sizeof(KlArgs) == 16 + 8 * 14 + 8 + 8 + 8 * 2
+    assert ctypes.sizeof(_lib.GatherOut) == 4 + 4 + 8 + 8 * 8 + 8  # mnf_gather_out
 
 
 def test_argument_errors_do_not_need_a_gpu():

@@ -147,12 +147,15 @@ static int launch_affine_stream(const FlowProgram &prog, const float *params, co
 // returns 1 if the program is not eligible (caller falls back to the generic kernel)
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
-                     int variant, float *workspace, cudaStream_t stream, bool plan_only) {
+                     int variant, float *workspace, const mnf_gather_out *gather, cudaStream_t stream,
+                     bool plan_only) {
     bool has_spline = false;
     for (int k = 0; k < n_ops; ++k) has_spline |= ops[k].type == MNF_OP_NSF_CL;
     // measured (r01): the constant-bank variant wins on spline stacks (4.10 vs 5.52 ms per 2^24 points) and loses
     // slightly on pure AffineHalfFlow stacks (16.1 vs 15.0 ms), where a segment still holds two conditioners
     int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
+    const bool want_gather = gather && (gather->n_peers > 0 || gather->multicast_ptr);
+    if (want_gather && (mode != 3 || !(inverse & 2) || (n_rows & 1))) return 1;  // caller reports the restriction
     bool has_net = false;
     for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
     if (!has_net && mode == 3) mode = 2;
@@ -178,13 +181,13 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
         return launch_affine_stream(prog, params, x, y, log_det, base_lp, n_rows, inverse, workspace, dp, stream);
     if (p.H == 16 && p.K == 8)
         return launch_fast_16_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                workspace, dp, stream);
+                                workspace, gather, dp, stream);
     if (p.H == 24 && p.K == 8)
         return launch_fast_24_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                workspace, dp, stream);
+                                workspace, gather, dp, stream);
     if (p.H == 8 && p.K == 5)
         return launch_fast_8_5(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                               workspace, dp, stream);
+                               workspace, gather, dp, stream);
     return 1;
 }
 

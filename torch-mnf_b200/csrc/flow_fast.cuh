@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(128, 4)
 flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
                   const float *__restrict__ x, const float *__restrict__ ld_in, float *__restrict__ y,
                   float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
-                  long long n_rows, int dir_flags) {
+                  long long n_rows, int dir_flags, const __grid_constant__ mnf_gather_out gather) {
     using L = CbankLayout<H, K>;
     const int inverse = dir_flags & 1;
     const bool sum_lp = dir_flags & 2;
@@ -707,6 +707,15 @@ flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restr
         if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
         if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
         if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
+        // fused gather: the result also goes straight to the other ranks over NVLink (n_rows is even here)
+        if (gather.multicast_ptr) {
+            asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(gather.multicast_ptr + gather.row_offset + 2 * pair),
+                         "f"(lp.x), "f"(lp.y)
+                         : "memory");
+        } else {
+            for (int p = 0; p < gather.n_peers; ++p)
+                st_stream2(reinterpret_cast<float2 *>(gather.peer_ptrs[p] + gather.row_offset) + pair, lp);
+        }
     } else {
         if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
         if (log_det) log_det[2 * pair] = ld.x;
@@ -723,8 +732,10 @@ struct ConstBankGuard {  // the bank and the stage are shared by every launch of
 template <int H, int K>
 int launch_cbank(const FlowProgram &prog, const float *params, const float *x, float *y, float *log_det,
                  float *base_lp, float *inter, int64_t n_rows, int dir_flags, float *workspace,
-                 cudaStream_t stream) {
+                 const mnf_gather_out *gather, cudaStream_t stream) {
     using L = CbankLayout<H, K>;
+    mnf_gather_out no_gather{};
+    if (gather) MNF_REQUIRE(gather->n_peers >= 0 && gather->n_peers <= MNF_MAX_PEERS, MNF_E_ARG, "bad n_peers");
     const int inverse = dir_flags & 1;
     // execution order, NSF_CL flows cut into halves; every net-bearing entry starts a new segment
     struct Exec {
@@ -793,7 +804,8 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
         float *inter_seg = inter ? inter + (size_t)ex.flow_index[seg_begin[sgm]] * n_rows * 2 : nullptr;
         flow_cbank_kernel<H, K><<<blocks, 128, 0, stream>>>(sp, params, first ? x : z_tmp, first ? nullptr : ld_tmp,
                                                             last ? y : z_tmp, last ? log_det : ld_tmp,
-                                                            last ? base_lp : nullptr, inter_seg, n_rows, dir_flags);
+                                                            last ? base_lp : nullptr, inter_seg, n_rows, dir_flags,
+                                                            (last && gather) ? *gather : no_gather);
         rc = launch_status("flow_cbank_kernel");
         if (rc) break;
     }
@@ -804,7 +816,7 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
 #define MNF_FLOW_FAST_ARGS                                                                                    \
     int variant, const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,      \
         const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int inverse,  \
-        float *workspace, const DeviceProps *dp, cudaStream_t stream
+        float *workspace, const mnf_gather_out *gather, const DeviceProps *dp, cudaStream_t stream
 
 #define MNF_FLOW_FAST_DEFINE(HH, KK)                                                                            \
     int launch_fast_##HH##_##KK(MNF_FLOW_FAST_ARGS) {                                                           \
@@ -816,7 +828,7 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
                                           inverse, dp, stream);                                                 \
         if (variant == 3)                                                                                       \
             return launch_cbank<HH, KK>(prog, params, x, y, log_det, base_lp, inter, n_rows, inverse, workspace, \
-                                        stream);                                                                \
+                                        gather, stream);                                                        \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \
                                       inverse, dp, stream);                                                     \
     }

@@ -10,7 +10,7 @@ int launch_flow_generic(const mnf_flow_op *ops, int n_ops, const float *params, 
                         int inverse, cudaStream_t stream);
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
-                     int mode, float *workspace, cudaStream_t stream, bool plan_only);
+                     int mode, float *workspace, const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
 
 // ---- Glow: W = P (tril(L,-1)+I) (triu(U,1)+diag S), W^-1 = Um^-1 Lm^-1 P^T (glow.py:20-24,35) ----
 // one thread per column; fp64 internally, rounded once to fp32.
@@ -92,14 +92,15 @@ int mnf_flow_stack_plan(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t
     int rc = validate_program(ops_host, n_ops, dim, n_params);
     if (rc) return rc;
     return launch_flow_fast(ops_host, n_ops, nullptr, n_params, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
-                            dim, 0, -1, nullptr, nullptr, true) == 0
+                            dim, 0, -1, nullptr, nullptr, nullptr, true) == 0
                ? 1
                : 0;
 }
 
 int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params,
                        const float *x, float *y, float *log_det, float *base_log_prob, float *intermediates,
-                       int64_t n_rows, int dim, int flags, float *workspace, void *stream) {
+                       int64_t n_rows, int dim, int flags, float *workspace, const mnf_gather_out *gather,
+                       void *stream) {
     int rc = validate_program(ops_host, n_ops, dim, n_params);
     if (rc) return rc;
     MNF_REQUIRE(n_rows >= 0, MNF_E_ARG, "n_rows=%lld is negative", (long long)n_rows);
@@ -114,9 +115,11 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
     cudaStream_t st = (cudaStream_t)stream;
     if (!(flags & MNF_RUN_GENERIC)) {
         rc = launch_flow_fast(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
-                              n_rows, dim, inverse, variant, workspace, st, false);
+                              n_rows, dim, inverse, variant, workspace, gather, st, false);
         if (rc != 1) return rc;
     }
+    MNF_REQUIRE(!gather || (gather->n_peers == 0 && !gather->multicast_ptr), MNF_E_SHAPE,
+                "peer-memory gather output needs the constant-bank dim-2 kernel (spline stack, >= 65536 rows)");
     return launch_flow_generic(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
                                n_rows, dim, inverse, st);
 }

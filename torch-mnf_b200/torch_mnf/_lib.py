@@ -43,6 +43,13 @@ class FlowOp(C.Structure):
     ]
 
 
+class GatherOut(C.Structure):
+    """struct mnf_gather_out."""
+
+    _fields_ = [("n_peers", C.c_int32), ("reserved", C.c_int32), ("row_offset", C.c_int64),
+                ("peer_ptrs", C.c_void_p * 8), ("multicast_ptr", C.c_void_p)]
+
+
 _lib = None
 
 _f32p = C.c_void_p  # device pointers travel as integers
@@ -54,7 +61,7 @@ _SIGS = {
     "mnf_flow_stack_run": (
         C.c_int,
         [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p,
-         C.c_int64, C.c_int, C.c_int, _f32p, C.c_void_p],
+         C.c_int64, C.c_int, C.c_int, _f32p, C.POINTER(GatherOut), C.c_void_p],
     ),
     "mnf_flow_stack_workspace": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "mnf_flow_stack_plan": (C.c_int, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),

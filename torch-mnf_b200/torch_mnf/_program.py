@@ -150,10 +150,11 @@ class FlowProgram:
 
     @torch.no_grad()
     def run(self, x, inverse: bool, want_inter: bool = False, want_base_lp: bool = False, out=None,
-            log_det=None, kernel=None, log_prob_only=False, log_prob_out=None):
+            log_det=None, kernel=None, log_prob_only=False, log_prob_out=None, gather=None):
         """kernel: None = library default, "generic" = interpreter, 0/1/2 = dim-2 kernel variant.
         log_prob_only: return (None, None, None, log_det + standard-normal log-density) without
-        storing the transformed points (single-chunk programs only)."""
+        storing the transformed points (single-chunk programs only).
+        gather: optional _lib.GatherOut -- also store the log-probs into peer ranks' buffers (fused gather)."""
         x = _lib.require_cuda_f32(x, "input")
         if x.dim() != 2:
             raise ValueError(f"flows take [batch, dim] inputs, got shape {tuple(x.shape)}")
@@ -173,7 +174,7 @@ class FlowProgram:
             with torch.cuda.device(dev):
                 rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
                                             None, None, lp.data_ptr(), None, B, D, flags, _lib.ptr(ws),
-                                            _lib.stream_ptr(dev))
+                                            C.byref(gather) if gather is not None else None, _lib.stream_ptr(dev))
             _lib.check(rc, "mnf_flow_stack_run")
             _lib.launch_count += 1
             return None, None, None, lp
@@ -205,7 +206,7 @@ class FlowProgram:
                 rc = lib.mnf_flow_stack_run(
                     ops_ptr, cnt, self._blob.data_ptr(), self._blob.numel(), src.data_ptr(), y.data_ptr(),
                     ld_chunk.data_ptr(), _lib.ptr(lp) if last else None,
-                    inter[done:].data_ptr() if inter is not None else None, B, D, flags, _lib.ptr(ws), stream,
+                    inter[done:].data_ptr() if inter is not None else None, B, D, flags, _lib.ptr(ws), None, stream,
                 )
                 _lib.check(rc, "mnf_flow_stack_run")
                 _lib.launch_count += 1

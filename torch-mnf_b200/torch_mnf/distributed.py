@@ -53,3 +53,44 @@ def reduce_mc_probs(log_probs: torch.Tensor, n_images: int, group=None) -> torch
         dist.all_reduce(sums, group=group)
         dist.all_reduce(count, group=group)
     return sums / count
+
+
+class PeerGather:
+    """Gather buffer in NVLink peer memory (torch symmetric memory) for per-row results of a sharded batch.
+
+    ``buffer`` is a ``[world * n_rows]`` fp32 tensor that exists at the same offset on every rank.  The flow kernel
+    stores its log-probs into the local slice AND -- through ``gather_out()`` -- into every peer's copy while it
+    computes (NVLS multicast when the fabric supports it, else one store per peer), so no collective moves data
+    afterwards; ``barrier()`` orders the step against the peers' reads."""
+
+    def __init__(self, n_rows: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        group = group or dist.group.WORLD
+        self.world, self.rank, self.n_rows = dist.get_world_size(group), dist.get_rank(group), n_rows
+        if self.world - 1 > 8:
+            raise ValueError("PeerGather supports up to 9 ranks per node")
+        self.buffer = symm.empty(self.world * n_rows, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.buffer, group)
+        self._lib = _lib
+        self.multicast = bool(getattr(self.handle, "has_multicast_support", False)) and int(self.handle.multicast_ptr) != 0
+
+    def local_slice(self) -> torch.Tensor:
+        return self.buffer[self.rank * self.n_rows:(self.rank + 1) * self.n_rows]
+
+    def gather_out(self, use_multicast: bool = True):
+        g = self._lib.GatherOut()
+        g.row_offset = self.rank * self.n_rows
+        if use_multicast and self.multicast:
+            g.n_peers, g.multicast_ptr = 0, int(self.handle.multicast_ptr)
+        else:
+            peers = [int(p) for r, p in enumerate(self.handle.buffer_ptrs) if r != self.rank]
+            g.n_peers = len(peers)
+            for i, p in enumerate(peers):
+                g.peer_ptrs[i] = p
+        return g
+
+    def barrier(self):
+        self.handle.barrier()

@@ -147,17 +147,18 @@ class NormalizingFlowModel(NormalizingFlow):
         loc = getattr(self.base, "loc", None)
         return self.base.log_prob(z if loc is None or loc.device == z.device else z.to(loc.device)).to(z.device)
 
-    def log_prob(self, x: Tensor, out: Tensor | None = None) -> Tensor:
+    def log_prob(self, x: Tensor, out: Tensor | None = None, gather=None) -> Tensor:
         """log p(x) = log_det(inverse) + base_log_prob in ONE pass (the reference's callers
         run the inverse twice, tests/test_flows.py:22-24).  For a standard-normal base nothing but
         the [B] result is written to HBM; ``out`` lets the caller place it (e.g. in its slice of an
-        all-gather buffer)."""
+        all-gather buffer); ``gather`` (a ``_lib.GatherOut``) makes the kernel store the result into the other
+        ranks' buffers as well (peer memory / NVLS multicast), see ``torch_mnf.distributed.PeerGather``."""
         if self._base_is_std(x.size(-1)) and 0 < len(self.flows) <= _lib.MAX_OPS:
             for f in self.flows:
                 hook = getattr(f, "_before_run", None)
                 if hook is not None:
                     hook(x, True)
-            return self._program().run(x, inverse=True, log_prob_only=True, log_prob_out=out)[3]
+            return self._program().run(x, inverse=True, log_prob_only=True, log_prob_out=out, gather=gather)[3]
         zs, ld = self.inverse(x)
         return ld + self.base_log_prob(x)
 
