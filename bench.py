@@ -520,6 +520,7 @@ def main():
                     help="cfg2 (default, the headline flow log-prob line) or cfg4 (MNF-LeNet MC prediction)")
     ap.add_argument("--mc-samples", type=int, default=64, help="cfg4: MC samples per image per GPU per step")
     args = ap.parse_args()
+    torch.set_grad_enabled(False)  # the workload is density evaluation / prediction, not training
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg4":

@@ -125,6 +125,24 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
                        int flags, float *workspace, const mnf_gather_out *gather /* may be NULL */,
                        void *stream);
 
+/* Reverse-mode pass of mnf_flow_stack_run (the reference trains through torch autograd:
+ * tests/test_flows.py:14-31 calls loss.backward() on -(log_det + base_log_prob)).
+ *   x              [n_rows, dim]         the input the forward run saw
+ *   intermediates  [n_ops, n_rows, dim]  what the forward run stored (output of every flow, execution order)
+ *   grad_intermediates  same shape or NULL: d loss / d (each flow's output), the last slice being the stack's result
+ *   grad_y         [n_rows, dim] or NULL: extra d loss / d result (added to the last slice above)
+ *   grad_log_det   [n_rows] or NULL
+ *   grad_x         [n_rows, dim] or NULL (out): d loss / d x
+ *   grad_params    [n_params] (in/out): parameter gradients are ADDED at the offsets the parameters have in
+ *                  `params` (zero it first); for a Glow op it receives d/dW, d/dW^-1 and d/dlogdet of the assembled
+ *                  block and the host chains them to L, S, U.
+ * flags: MNF_RUN_INVERSE or 0 -- the direction of the forward run.  Every flow type and direction except
+ * NSF_AR.forward.  Exact-fp32 arithmetic, one thread per point. */
+int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params,
+                            float *grad_params, const float *x, const float *intermediates,
+                            const float *grad_y, const float *grad_log_det, const float *grad_intermediates,
+                            float *grad_x, int64_t n_rows, int dim, int flags, void *stream);
+
 /* Floats of scratch `workspace` must provide for a run of this shape (0 = none needed; NULL is then
  * accepted).  The constant-bank variant of the dim-2 kernel parks points and log-dets there between
  * stack segments. */

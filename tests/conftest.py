@@ -28,3 +28,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode_by_default(request):
+    """Parity tests exercise the inference kernels; modules whose name contains 'autograd' keep grad enabled
+    (with grad enabled and trainable parameters the flows take the differentiable path, like the reference)."""
+    import torch
+
+    keep = "autograd" in request.module.__name__ or "train" in request.module.__name__
+    with torch.set_grad_enabled(keep):
+        yield

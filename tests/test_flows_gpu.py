@@ -148,6 +148,36 @@ def test_actnorm_data_dependent_init():
     close(ld, t(g, "ld"), "ld")
 
 
+def test_actnorm_init_inside_a_stack():
+    """Each ActNorm initialises from ITS input -- the output of the flows that run before it in the inverse
+    direction (affine_constant_flow.py:42-50 called from core.py:30-33) -- not from the stack's input."""
+    from oracle import flows_cpu
+
+    specs = [{"type": "ActNormFlow", "dim": 4, "scale": True, "shift": True}, {"type": "Glow", "dim": 4},
+             {"type": "ActNormFlow", "dim": 4, "scale": True, "shift": True},
+             {"type": "AffineHalfFlow", "dim": 4, "parity": False, "scale": True, "shift": True, "h_sizes": [8, 8]}]
+    sd = random_flow_sd(specs, seed=5, scale=0.6)
+    model = load_flow_model(specs, sd)
+    for f in model.flows:
+        if hasattr(f, "data_dep_init_done"):
+            f.data_dep_init_done = False
+    x = 2.0 * torch.randn(512, 4, generator=torch.Generator().manual_seed(3)) + 1.0
+    zs, ld = model.inverse(x.cuda())
+
+    v, ld_ref = x, torch.zeros(x.size(0))
+    for i in reversed(range(len(specs))):
+        p = flows_cpu.sub(sd, f"flows.{i}.")
+        if specs[i]["type"] == "ActNormFlow":
+            p["s"], p["t"] = flows_cpu.actnorm_init(p, specs[i], v)
+            close(getattr(model.flows[i], "s"), p["s"], f"flows.{i}.s")
+            close(getattr(model.flows[i], "t"), p["t"], f"flows.{i}.t")
+        v, l = flows_cpu.apply_flow(p, specs[i], v, True)
+        ld_ref = ld_ref + l
+    close(zs[-1], v, "z")
+    close(ld, ld_ref, "ld")
+    assert all(f.data_dep_init_done for f in model.flows if hasattr(f, "data_dep_init_done"))
+
+
 ORACLE_CASES = {
     "cfg2_shape": [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}, {"type": "Glow", "dim": 2},
                    {"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}] * 3,

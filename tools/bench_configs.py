@@ -4,6 +4,8 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
+
+torch.set_grad_enabled(False)  # inference kernels; training goes through mnf_flow_stack_backward
 from oracle import flows_cpu, mnf_cpu
 from oracle.noise import FreshNoise
 from tests.helpers import golden_sd, golden_spec, load_flow_model, load_golden, random_flow_sd, t

@@ -3,6 +3,8 @@ import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
+
+torch.set_grad_enabled(False)  # inference kernels; training goes through mnf_flow_stack_backward
 from tests.helpers import load_flow_model, random_flow_sd
 from tests.test_flows_gpu import ORACLE_CASES
 

@@ -2,6 +2,8 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
+
+torch.set_grad_enabled(False)  # inference kernels; training goes through mnf_flow_stack_backward
 from torch_mnf.layers import MNFLinear
 from torch_mnf.layers._mnf_ops import Noise
 torch.manual_seed(0)

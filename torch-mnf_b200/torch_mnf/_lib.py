@@ -63,6 +63,11 @@ _SIGS = {
         [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p,
          C.c_int64, C.c_int, C.c_int, _f32p, C.POINTER(GatherOut), C.c_void_p],
     ),
+    "mnf_flow_stack_backward": (
+        C.c_int,
+        [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+         C.c_int64, C.c_int, C.c_int, C.c_void_p],
+    ),
     "mnf_flow_stack_workspace": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "mnf_flow_stack_plan": (C.c_int, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
     "mnf_glow_assemble": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p]),

@@ -17,8 +17,9 @@ from . import _lib
 
 
 class ParamPacker:
-    def __init__(self, device):
+    def __init__(self, device, differentiable: bool = False):
         self.device = device
+        self.differentiable = differentiable  # keep the autograd graph from the nn.Parameters to the blob
         self.parts: list[torch.Tensor] = []
         self.n = 0
         self.post = []  # callables(blob) run after the blob exists (e.g. Glow assembly)
@@ -34,18 +35,29 @@ class ParamPacker:
         self._pad()
         off = self.n
         for t in tensors:
-            t = t.detach()
+            if not self.differentiable:
+                t = t.detach()
             if t.device != self.device:
                 raise RuntimeError(f"parameter on {t.device}, input on {self.device}")
             self.parts.append(t.reshape(-1).to(torch.float32))
             self.n += t.numel()
         return off
 
-    def reserve(self, n: int, fill=None) -> int:
+    def reserve(self, n: int, fill=None, torch_fill=None) -> int:
+        """n floats written after the blob exists by ``fill(blob, off)`` (a kernel); in differentiable mode
+        ``torch_fill()`` must return the same n values as a differentiable tensor instead."""
         self._pad()
         off = self.n
-        self.parts.append(torch.zeros(n, device=self.device))
         self.n += n
+        if self.differentiable:
+            if torch_fill is None:
+                raise NotImplementedError("this flow has no differentiable parameter assembly")
+            t = torch_fill().reshape(-1).to(torch.float32)
+            if t.numel() != n:
+                raise RuntimeError(f"torch_fill returned {t.numel()} values, expected {n}")
+            self.parts.append(t)
+            return off
+        self.parts.append(torch.zeros(n, device=self.device))
         if fill is not None:
             self.post.append(lambda blob, off=off: fill(blob, off))
         return off
@@ -109,6 +121,51 @@ def _state_key(flows, device, tensors):
     )
 
 
+class _FlowStackFn(torch.autograd.Function):
+    """Differentiable launch of a flow program: forward = mnf_flow_stack_run keeping every flow's output,
+    backward = mnf_flow_stack_backward.  The parameter blob is an autograd function of the nn.Parameters
+    (torch.cat of views, MADE masks and the Glow assembly applied by torch), so d loss / d blob is chained
+    to them by torch."""
+
+    @staticmethod
+    def forward(ctx, prog, inverse, x, blob):
+        B, D = x.shape
+        lib = _lib.lib()
+        n = prog._n_ops
+        ld = torch.empty(B, device=x.device, dtype=torch.float32)
+        inter = torch.empty((n, B, D), device=x.device, dtype=torch.float32)
+        ws = FlowProgram._workspace(lib, n, B, D, x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mnf_flow_stack_run(prog._ops, n, blob.data_ptr(), blob.numel(), x.data_ptr(), None,
+                                        ld.data_ptr(), None, inter.data_ptr(), B, D,
+                                        _lib.RUN_INVERSE if inverse else 0, _lib.ptr(ws), None, _lib.stream_ptr(x.device))
+        _lib.check(rc, "mnf_flow_stack_run")
+        _lib.launch_count += 1
+        ctx.prog, ctx.inverse = prog, inverse
+        ctx.save_for_backward(x, inter, blob)
+        return ld, inter
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_ld, g_inter):
+        x, inter, blob = ctx.saved_tensors
+        prog = ctx.prog
+        B, D = x.shape
+        lib = _lib.lib()
+        g_blob = torch.zeros_like(blob)
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+        g_ld = g_ld.contiguous() if g_ld is not None else None
+        g_inter = g_inter.contiguous() if g_inter is not None else None
+        with torch.cuda.device(x.device):
+            rc = lib.mnf_flow_stack_backward(prog._ops, prog._n_ops, blob.data_ptr(), blob.numel(), g_blob.data_ptr(),
+                                             x.data_ptr(), inter.data_ptr(), None, _lib.ptr(g_ld), _lib.ptr(g_inter),
+                                             _lib.ptr(g_x), B, D, _lib.RUN_INVERSE if ctx.inverse else 0,
+                                             _lib.stream_ptr(x.device))
+        _lib.check(rc, "mnf_flow_stack_backward")
+        _lib.launch_count += 1
+        return None, None, g_x, g_blob
+
+
 class FlowProgram:
     """Cached (descriptors, blob) for a sequence of flow modules."""
 
@@ -147,6 +204,26 @@ class FlowProgram:
         self._build(device)
         n = min(self._n_ops, _lib.MAX_OPS)
         return _lib.lib().mnf_flow_stack_plan(self._ops, n, dim, self._blob.numel())
+
+    def needs_grad(self, x) -> bool:
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._tensors))
+
+    def run_autograd(self, x, inverse: bool):
+        """(log_det [B], outputs of every flow [n_ops, B, D]) with the autograd graph attached
+        (mnf_flow_stack_backward).  One chunk only: at most MNF_MAX_OPS flows."""
+        x = _lib.require_cuda_f32(x, "input")
+        if x.dim() != 2:
+            raise ValueError(f"flows take [batch, dim] inputs, got shape {tuple(x.shape)}")
+        self._build(x.device)
+        if not 0 < self._n_ops <= _lib.MAX_OPS:
+            raise NotImplementedError(f"autograd through {self._n_ops} flows: between 1 and {_lib.MAX_OPS} supported")
+        pk = ParamPacker(self._blob.device, differentiable=True)
+        for f in self.flows:
+            f._emit(pk)
+        blob = pk.finish()
+        if blob.numel() != self._blob.numel():
+            raise RuntimeError("differentiable parameter blob does not match the cached layout")
+        return _FlowStackFn.apply(self, inverse, x, blob)
 
     @torch.no_grad()
     def run(self, x, inverse: bool, want_inter: bool = False, want_base_lp: bool = False, out=None,

@@ -27,10 +27,19 @@ class Flow(nn.Module):
     def _shape_log_det(self, ld):
         return ld
 
+    def _run_single(self, v, inverse: bool):
+        prog = self._single()
+        hook = getattr(self, "_before_run", None)
+        if prog.needs_grad(v):  # training: keep the autograd graph (mnf_flow_stack_backward)
+            if hook is not None:
+                hook(v, inverse)
+            ld, inter = prog.run_autograd(v, inverse)
+            return inter[-1], self._shape_log_det(ld)
+        out, ld, _, _ = prog.run(v, inverse=inverse)
+        return out, self._shape_log_det(ld)
+
     def forward(self, z):
-        x, ld, _, _ = self._single().run(z, inverse=False)
-        return x, self._shape_log_det(ld)
+        return self._run_single(z, inverse=False)
 
     def inverse(self, x):
-        z, ld, _, _ = self._single().run(x, inverse=True)
-        return z, self._shape_log_det(ld)
+        return self._run_single(x, inverse=True)

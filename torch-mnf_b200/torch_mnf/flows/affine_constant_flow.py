@@ -38,8 +38,11 @@ class ActNormFlow(AffineConstantFlow):
         super().__init__(*args, **kwargs)
         self.data_dep_init_done = False
 
+    def _init_pending(self, inverse: bool) -> bool:
+        return inverse and not self.data_dep_init_done
+
     def _before_run(self, x, inverse):
-        if not inverse or self.data_dep_init_done:
+        if not self._init_pending(inverse):
             return
         x = _lib.require_cuda_f32(x, "input")
         do_s = bool((self.s != 0).any())  # an all-zero parameter is left alone (:45,47)

@@ -2,6 +2,7 @@
 
 from __future__ import annotations
 
+import math
 from collections.abc import Sequence
 
 import torch
@@ -70,16 +71,38 @@ class NormalizingFlow(nn.Module):
         outs = [v] + (list(inter.unbind(0)) if inter is not None else [z])
         return outs, ld
 
+    def _data_dependent_init(self, v: Tensor, inverse: bool) -> None:
+        """ActNorm initialises itself from the first batch IT sees, i.e. the output of the flows that run before
+        it in this direction (affine_constant_flow.py:42-50 inside core.py:30-33's loop).  Flows with a pending
+        init get that input from a one-off run of the preceding sub-stack."""
+        order = list(self.flows)[::-1] if inverse else list(self.flows)
+        for i, f in enumerate(order):
+            pending = getattr(f, "_init_pending", None)
+            if pending is None or not pending(inverse):
+                continue
+            inp = v.detach()
+            if i > 0:
+                head = order[:i][::-1] if inverse else order[:i]
+                with torch.no_grad():
+                    inp = FlowProgram(head).run(inp, inverse)[0]
+            f._before_run(inp, inverse)
+
     def _run(self, v: Tensor, inverse: bool, want_lp: bool = False):
         if not want_lp:
             got = self._maf_density_stack(v, inverse)
             if got is not None:
                 return got[0], got[1], None
-        for f in self.flows:
-            hook = getattr(f, "_before_run", None)
-            if hook is not None:
-                hook(v, inverse)
-        y, ld, inter, lp = self._program().run(
+        self._data_dependent_init(v, inverse)
+        prog = self._program()
+        if len(self.flows) and prog.needs_grad(v):  # training: mnf_flow_stack_run + mnf_flow_stack_backward
+            ld, inter = prog.run_autograd(v, inverse)
+            outs = [v] + (list(inter.unbind(0)) if self.return_intermediates else [inter[-1]])
+            lp = None
+            if want_lp:  # standard-normal base density of the result, differentiable through torch
+                z = inter[-1]
+                lp = -0.5 * z.square().sum(1) - 0.5 * z.size(1) * math.log(2 * math.pi)
+            return outs, ld, lp
+        y, ld, inter, lp = prog.run(
             v, inverse, want_inter=self.return_intermediates, want_base_lp=want_lp
         )
         outs = [v] + (list(inter.unbind(0)) if inter is not None else [y])
@@ -153,12 +176,14 @@ class NormalizingFlowModel(NormalizingFlow):
         the [B] result is written to HBM; ``out`` lets the caller place it (e.g. in its slice of an
         all-gather buffer); ``gather`` (a ``_lib.GatherOut``) makes the kernel store the result into the other
         ranks' buffers as well (peer memory / NVLS multicast), see ``torch_mnf.distributed.PeerGather``."""
-        if self._base_is_std(x.size(-1)) and 0 < len(self.flows) <= _lib.MAX_OPS:
-            for f in self.flows:
-                hook = getattr(f, "_before_run", None)
-                if hook is not None:
-                    hook(x, True)
+        if self._base_is_std(x.size(-1)) and 0 < len(self.flows) <= _lib.MAX_OPS and not (
+            torch.is_grad_enabled() and self._program().needs_grad(x)
+        ):
+            self._data_dependent_init(x, True)
             return self._program().run(x, inverse=True, log_prob_only=True, log_prob_out=out, gather=gather)[3]
+        if self._base_is_std(x.size(-1)) and len(self.flows):  # training: one differentiable pass
+            _, ld, lp = self._run(x, inverse=True, want_lp=True)
+            return ld + lp
         zs, ld = self.inverse(x)
         return ld + self.base_log_prob(x)
 

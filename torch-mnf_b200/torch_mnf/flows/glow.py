@@ -40,7 +40,13 @@ class Glow(Flow):
                 )
             _lib.check(rc, "mnf_glow_assemble")
 
-        return new_op(_lib.OP_GLOW, aux_off=pk.reserve(2 * D * D + 1, fill))
+        return new_op(_lib.OP_GLOW, aux_off=pk.reserve(2 * D * D + 1, fill, self._assemble_torch))
+
+    def _assemble_torch(self):
+        """[W | W^-1 | log_det] as a differentiable function of L, S, U (training path only; glow.py:20-24,34-35)."""
+        eye = torch.eye(self.dim, device=self.L.device, dtype=self.L.dtype)
+        W = self.P @ (torch.tril(self.L, diagonal=-1) + eye) @ (torch.triu(self.U, diagonal=1) + torch.diag(self.S))
+        return torch.cat([W.reshape(-1), torch.inverse(W).reshape(-1), self.S.abs().log().sum().reshape(1)])
 
     def _shape_log_det(self, ld):
         return ld[0]  # the reference returns a 0-d tensor

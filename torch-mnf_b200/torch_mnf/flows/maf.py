@@ -4,6 +4,7 @@ from __future__ import annotations
 
 from collections.abc import Sequence
 
+import torch
 from torch import nn
 
 from .. import _lib
@@ -71,6 +72,8 @@ def _use_tc(flows, v) -> bool:
 
     if not flows or not all(isinstance(f, MAF) and made_tc_eligible(f) for f in flows):
         return False
+    if torch.is_grad_enabled() and (v.requires_grad or any(p.requires_grad for f in flows for p in f.parameters())):
+        return False  # training goes through the differentiable program (mnf_flow_stack_backward)
     prec = {f.precision for f in flows}
     if prec == {"fp32"}:
         return False
