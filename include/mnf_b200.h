@@ -155,7 +155,8 @@ int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 #define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2,3} */
 
 /* Which kernel mnf_flow_stack_run would pick: 0 = generic interpreter, 1 = specialised
- * D=2 register-resident kernel.  Host-only, no launch. */
+ * D=2 register-resident kernel, 2 = the constant-bank MADE kernel (all-MAF/IAF stacks of the BASELINE
+ * config-3 shape, dim 64 / hidden 24-24-24, in their one-pass direction).  Host-only, no launch. */
 int mnf_flow_stack_plan(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
 
 /* Glow._assemble_W + torch.inverse (glow.py:20-24, 34-35):  W = P (tril(L,-1)+I)(triu(U,1)+diag S),

@@ -148,6 +148,41 @@ def test_actnorm_data_dependent_init():
     close(ld, t(g, "ld"), "ld")
 
 
+def test_made_constant_bank_kernel():
+    """MAF x9 dim 64 (BASELINE config 3) takes the constant-bank MADE kernel: ragged batch, intermediates,
+    log-prob-only mode, against the generic interpreter and the CPU oracle."""
+    g = load_golden("maf9_d64")
+    specs, sd = golden_spec(g), golden_sd(g)
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    assert prog.plan("cuda", 64) == 2
+    x = torch.randn(2 * 256 + 37, 64, generator=torch.Generator().manual_seed(5))
+    xg = x.cuda()
+    y_f, ld_f, inter_f, lp_f = prog.run(xg, True, want_inter=True, want_base_lp=True)
+    y_g, ld_g, inter_g, lp_g = prog.run(xg, True, want_inter=True, want_base_lp=True, kernel="generic")
+    for a, b, what in ((y_f, y_g, "z"), (ld_f, ld_g, "ld"), (inter_f, inter_g, "inter"), (lp_f, lp_g, "base_lp")):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-5, msg=lambda m: f"{what}: {m}")
+    y_n, ld_n, _, _ = prog.run(xg, True)  # no intermediates: in-place chain on y
+    torch.testing.assert_close(y_n, y_g, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(ld_n, ld_g, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(model.log_prob(xg), ld_g + lp_g, rtol=1e-5, atol=5e-5)
+    close_vs_oracle((y_f, ld_f), sd, specs, x, True, "made_fast")
+
+
+def test_model_sample_draws_on_device():
+    """NormalizingFlowModel.sample (core.py:51-55): base draw + forward; same distribution as pushing torch's own
+    standard-normal draws through forward()."""
+    g = load_golden("nsfcl3_stack")
+    model = load_flow_model(golden_spec(g), golden_sd(g))
+    torch.manual_seed(0)
+    x = model.sample((4096,))
+    assert x.shape == (4096, 2) and x.is_cuda and torch.isfinite(x).all()
+    torch.manual_seed(0)
+    z = torch.randn(4096, 2, device="cuda")
+    torch.testing.assert_close(x, model.forward(z)[0][-1])
+    assert model.sample(3, 5).shape == (3, 5, 2)
+
+
 def test_actnorm_init_inside_a_stack():
     """Each ActNorm initialises from ITS input -- the output of the flows that run before it in the inverse
     direction (affine_constant_flow.py:42-50 called from core.py:30-33) -- not from the stack's input."""

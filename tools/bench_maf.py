@@ -20,9 +20,25 @@ def timeit(fn, iters=5):
     return min(a.elapsed_time(b) for a, b in ev)
 
 
-for prec, n in (("tf32", 1 << 20), ("fp32", 1 << 16)):
+for prec, n in (("tf32", 1 << 20), ("fp32", 1 << 20)):
     for f in model.flows:
         f.precision = prec
     x = torch.randn(n, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
     ms = timeit(lambda: model.inverse(x))
     print(f"MAF x9 D=64 density {prec}: rows={n} {ms:.3f} ms  {n/ms/1e3:.2f} Mrows/s  ({516*n/ms/1e6:.0f} GB/s algorithmic)", flush=True)
+
+# Sequential directions: sampling through MAF (D MADE passes per flow) and NSF_AR.forward
+for f in model.flows:
+    f.precision = "fp32"
+for n in (1 << 12, 1 << 16):
+    z = torch.randn(n, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    ms = timeit(lambda: model.forward(z), iters=3)
+    print(f"MAF x9 D=64 sampling (64 sequential passes per flow): rows={n} {ms:.3f} ms  {n/ms:.1f} krows/s", flush=True)
+
+g2 = load_golden("nsfar2_d3")
+ar = load_flow_model(golden_spec(g2), golden_sd(g2), return_intermediates=False)
+n = 1 << 20
+z = torch.randn(n, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+for name, fn in (("forward (sequential)", lambda: ar.forward(z)), ("inverse", lambda: ar.inverse(z))):
+    ms = timeit(fn)
+    print(f"ActNorm+Glow+NSF_AR x2 D=3 {name}: rows={n} {ms:.3f} ms  {n/ms/1e3:.2f} Mrows/s", flush=True)

@@ -11,6 +11,9 @@ int launch_flow_generic(const mnf_flow_op *ops, int n_ops, const float *params, 
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int mode, float *workspace, const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
+int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                     float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
+                     cudaStream_t stream, bool plan_only);
 
 // ---- Glow: W = P (tril(L,-1)+I) (triu(U,1)+diag S), W^-1 = Um^-1 Lm^-1 P^T (glow.py:20-24,35) ----
 // one thread per column; fp64 internally, rounded once to fp32.
@@ -91,6 +94,11 @@ extern "C" {
 int mnf_flow_stack_plan(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params) {
     int rc = validate_program(ops_host, n_ops, dim, n_params);
     if (rc) return rc;
+    float dummy = 0.f;  // a non-NULL output so that the plan does not depend on a scratch buffer
+    for (int inverse = 0; inverse < 2; ++inverse)
+        if (launch_made_fast(ops_host, n_ops, nullptr, nullptr, &dummy, nullptr, nullptr, nullptr, 0, dim, inverse,
+                             nullptr, nullptr, true) == 0)
+            return 2;
     return launch_flow_fast(ops_host, n_ops, nullptr, n_params, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
                             dim, 0, -1, nullptr, nullptr, nullptr, true) == 0
                ? 1
@@ -113,6 +121,11 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
     MNF_REQUIRE(y || log_det || base_log_prob, MNF_E_ARG, "no output requested");
     MNF_REQUIRE(params || n_params == 0, MNF_E_ARG, "params is NULL");
     cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & MNF_RUN_GENERIC) && !gather) {
+        rc = launch_made_fast(ops_host, n_ops, params, x, y, log_det, base_log_prob, intermediates, n_rows, dim,
+                              inverse, workspace, st, false);
+        if (rc != 1) return rc;
+    }
     if (!(flags & MNF_RUN_GENERIC)) {
         rc = launch_flow_fast(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
                               n_rows, dim, inverse, variant, workspace, gather, st, false);
@@ -126,6 +139,7 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
 
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim) {
     (void)n_ops;
+    if (dim == 64) return n_rows * 64;  // MADE density stack in log-prob mode parks z here between flows
     return 3 * (n_rows + (n_rows & 1)) * (dim == 2 ? 1 : 0);
 }
 

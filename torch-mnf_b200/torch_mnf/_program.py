@@ -134,7 +134,7 @@ class _FlowStackFn(torch.autograd.Function):
         n = prog._n_ops
         ld = torch.empty(B, device=x.device, dtype=torch.float32)
         inter = torch.empty((n, B, D), device=x.device, dtype=torch.float32)
-        ws = FlowProgram._workspace(lib, n, B, D, x.device)
+        ws = FlowProgram._workspace(lib, n, B, D, x.device, have_y=True)
         with torch.cuda.device(x.device):
             rc = lib.mnf_flow_stack_run(prog._ops, n, blob.data_ptr(), blob.numel(), x.data_ptr(), None,
                                         ld.data_ptr(), None, inter.data_ptr(), B, D,
@@ -195,7 +195,9 @@ class FlowProgram:
         self._key = key
 
     @staticmethod
-    def _workspace(lib, n_ops, n_rows, dim, dev):
+    def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False):
+        if have_y and dim != 2:
+            return None  # only log-prob-only runs (no y buffer) of the MADE kernel park points in the workspace
         need = lib.mnf_flow_stack_workspace(n_ops, n_rows, dim)
         return torch.empty(need, device=dev, dtype=torch.float32) if need > 0 else None
 
@@ -263,7 +265,7 @@ class FlowProgram:
             y.copy_(x)
             ld.zero_()
         stream = _lib.stream_ptr(dev)
-        ws = self._workspace(lib, min(n, _lib.MAX_OPS), B, D, dev)
+        ws = self._workspace(lib, min(n, _lib.MAX_OPS), B, D, dev, have_y=True)
         flags = _lib.RUN_INVERSE if inverse else 0
         if kernel == "generic":
             flags |= _lib.RUN_GENERIC

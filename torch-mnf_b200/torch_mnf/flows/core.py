@@ -188,10 +188,16 @@ class NormalizingFlowModel(NormalizingFlow):
         return ld + self.base_log_prob(x)
 
     def sample(self, *num_samples: int) -> Tensor:
-        """core.py:51-55.  Base samples are drawn by torch and moved to the flows' device."""
-        z = self.base.sample(*num_samples)
+        """core.py:51-55.  A standard-normal base is drawn directly on the flows' device (no host round trip);
+        any other base is sampled by torch.distributions and moved over."""
         p = next(self.parameters(), None)
-        if p is not None and z.device != p.device:
-            z = z.to(p.device)
-        xs, _ = self.forward(z.float())
-        return xs[-1]
+        n = tuple(num_samples[0]) if len(num_samples) == 1 and not isinstance(num_samples[0], int) else num_samples
+        dim = int(self.base.event_shape[0]) if len(self.base.event_shape) == 1 else None
+        if p is not None and p.is_cuda and dim is not None and self._base_is_std(dim):
+            z = torch.randn(*n, dim, device=p.device, dtype=torch.float32)
+        else:
+            z = self.base.sample(*num_samples)
+            if p is not None and z.device != p.device:
+                z = z.to(p.device)
+        xs, _ = self.forward(z.float().reshape(-1, z.size(-1)))
+        return xs[-1].reshape(z.shape)

@@ -79,4 +79,6 @@ def _use_tc(flows, v) -> bool:
         return False
     if prec == {"tf32"}:
         return True
+    if all(f.dim == 64 and list(getattr(f.net, "hidden_sizes", [])) == [24, 24, 24] for f in flows):
+        return False  # the exact-fp32 constant-bank MADE kernel (made_fast.cu) beats the TF32 GEMM chain here
     return "fp32" not in prec and v.is_cuda and v.numel() >= TC_MIN_ELEMS
