@@ -1,5 +1,6 @@
 // made_fast.cu -- exact-fp32 density pass of a stack of MAF / IAF flows (maf.py:53-62) for the BASELINE config-3
-// shape (dim 64, MADE 64-24-24-24-128): one launch per flow, persistent blocks, two rows per thread, packed
+// shape (dim 64, MADE 64-24-24-24-128): one launch per flow, one persistent 12-warp block per SM, two rows per
+// lane, every warp owning a private 64-row tile (no block barriers in the steady state), packed
 // FFMA2 with the masked weights broadcast from shared memory (LDS.128: four weights feed four FFMA2).  A first
 // version kept the weights in the constant bank as uniform operands like the dim-2 flow kernel; its 115 KB of
 // straight-line code ran at 2.8 stalled cycles per issue waiting for instructions (profiles/r01_made_fast_*).  The K=64 / N=24 contractions are far too small for a tensor-core tile to pay:
@@ -93,35 +94,40 @@ __device__ __forceinline__ void dense_relu(const float *W, int wt_off, int bias_
     }
 }
 
-constexpr int kMadeRows = 256;  // rows per tile: 128 threads x 2
+constexpr int kMadeWarps = 12;      // warps per block; one block per SM (shared memory: net + 12 private tiles)
+constexpr int kMadeWarpRows = 64;   // rows per warp tile: 2 per lane
 
-// Persistent blocks: the net is staged once per block, then the block walks tiles of 256 rows.
+// Persistent block, one per SM: the net is staged once, then every WARP walks its own tiles of 64 rows with no
+// block-level synchronisation, so the load / store phases of one warp overlap the arithmetic of the others.
 // lp_mode: 0 none, 1 base log-density of z, 2 log-density + log-det
 template <int D, int H>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(32 * kMadeWarps, 1)
 made_fast_kernel(const float *__restrict__ net, const float *__restrict__ x, float *__restrict__ z,
                  const float *__restrict__ ld_in, float *__restrict__ ld_out, float *__restrict__ lp_out,
                  long long n_rows, int parity, int lp_mode) {
     using L = MadeLayout<D, H>;
     constexpr int S = D + 1;  // padded row stride
     extern __shared__ __align__(16) float smem[];
-    float *W = smem, *tile = smem + L::kFloats;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *W = smem, *tile = smem + L::kFloats + warp * (kMadeWarpRows * S);
     made_stage_net<D, H>(net, W);
-    const long long n_tiles = (n_rows + kMadeRows - 1) / kMadeRows;
-    float *ra = tile + threadIdx.x * S, *rb = ra + 128 * S;
+    __syncthreads();
+    const long long n_tiles = (n_rows + kMadeWarpRows - 1) / kMadeWarpRows;
+    float *ra = tile + lane * S, *rb = ra + 32 * S;
 
 #pragma unroll 1
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const long long row0 = t * kMadeRows;
-        __syncthreads();  // staged net visible; previous tile fully stored
-        for (int e = threadIdx.x; e < kMadeRows * (D / 4); e += 128) {
+    for (long long t = (long long)blockIdx.x * kMadeWarps + warp; t < n_tiles; t += (long long)gridDim.x * kMadeWarps) {
+        const long long row0 = t * kMadeWarpRows;
+        __syncwarp();  // previous tile fully stored
+#pragma unroll 8
+        for (int e = lane; e < kMadeWarpRows * (D / 4); e += 32) {
             const int r = e / (D / 4), c = (e % (D / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < n_rows) v = ld_stream4(reinterpret_cast<const float4 *>(x + (row0 + r) * D + c));
             float *d = tile + r * S + c;
             d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
         }
-        __syncthreads();
+        __syncwarp();
 
         float2 hA[H / 2], hB[H / 2], gA[H / 2], gB[H / 2];
 #pragma unroll
@@ -185,7 +191,7 @@ made_fast_kernel(const float *__restrict__ net, const float *__restrict__ x, flo
                 ssA = fmaf(za, za, ssA), ssB = fmaf(zb, zb, ssB);
             }
         }
-        const long long rowA = row0 + threadIdx.x, rowB = rowA + 128;
+        const long long rowA = row0 + lane, rowB = rowA + 32;
         if (rowA < n_rows) {
             const float l = (ld_in ? ld_in[rowA] : 0.f) + ldA;
             if (ld_out) ld_out[rowA] = l;
@@ -199,8 +205,9 @@ made_fast_kernel(const float *__restrict__ net, const float *__restrict__ x, flo
             if (lp_mode) lp_out[rowB] = lp_mode == 2 ? lp + l : lp;
         }
         if (z == nullptr) continue;
-        __syncthreads();
-        for (int e = threadIdx.x; e < kMadeRows * (D / 4); e += 128) {
+        __syncwarp();
+#pragma unroll 4
+        for (int e = lane; e < kMadeWarpRows * (D / 4); e += 32) {
             const int r = e / (D / 4), c = (e % (D / 4)) * 4;
             if (row0 + r >= n_rows) continue;
             const float *d = tile + r * S;
@@ -211,13 +218,124 @@ made_fast_kernel(const float *__restrict__ net, const float *__restrict__ x, flo
     }
 }
 
+__device__ __forceinline__ float2 lds2(const float *W, int i) { return reinterpret_cast<const float2 *>(W)[i >> 1]; }
+
+// Sequential direction (MAF.forward / IAF.inverse, maf.py:39-51): x_i = (z_f(i) - t_i(x_<i)) exp(-s_i(x_<i)), D passes.
+// The reference re-evaluates the whole MADE on the partially filled x in every pass (D x the density cost); here a
+// pass costs 1/4.7 of that: the first layer's pre-activations are kept in registers and updated with the rank-1
+// term W1[:, i] x_i as soon as x_i is known (the not-yet-filled inputs are zero, so this is exactly the reference's
+// arithmetic), the two hidden layers are recomputed, and only the two outputs (s_i, t_i) of the last layer are formed.
+constexpr int kMadeSeqWarps = 8;  // the sequential kernel keeps three activation sets live: fewer warps, 255 registers
+
+template <int D, int H>
+__global__ void __launch_bounds__(32 * kMadeSeqWarps, 1)
+made_seq_kernel(const float *__restrict__ net, const float *__restrict__ z, float *__restrict__ x,
+                const float *__restrict__ ld_in, float *__restrict__ ld_out, float *__restrict__ lp_out,
+                long long n_rows, int parity, int lp_mode) {
+    using L = MadeLayout<D, H>;
+    constexpr int S = D + 1;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *W = smem, *tile = smem + L::kFloats + warp * (kMadeWarpRows * S);
+    made_stage_net<D, H>(net, W);
+    __syncthreads();
+    const long long n_tiles = (n_rows + kMadeWarpRows - 1) / kMadeWarpRows;
+    float *ra = tile + lane * S, *rb = ra + 32 * S;
+
+#pragma unroll 1
+    for (long long t = (long long)blockIdx.x * kMadeSeqWarps + warp; t < n_tiles; t += (long long)gridDim.x * kMadeSeqWarps) {
+        const long long row0 = t * kMadeWarpRows;
+        __syncwarp();
+#pragma unroll 8
+        for (int e = lane; e < kMadeWarpRows * (D / 4); e += 32) {  // the flip (maf.py:41) happens while staging
+            const int r = e / (D / 4), c = (e % (D / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n_rows) v = ld_stream4(reinterpret_cast<const float4 *>(z + (row0 + r) * D + c));
+            float *d = tile + r * S;
+            if (parity) d[D - 1 - c] = v.x, d[D - 2 - c] = v.y, d[D - 3 - c] = v.z, d[D - 4 - c] = v.w;
+            else d[c] = v.x, d[c + 1] = v.y, d[c + 2] = v.z, d[c + 3] = v.w;
+        }
+        __syncwarp();
+
+        float2 pA[H / 2], pB[H / 2];  // first-layer pre-activations of the partially filled x
+#pragma unroll
+        for (int j = 0; j < H / 2; j += 2) {
+            const float4 b = lds4(W, L::B1 + 2 * j);
+            pA[j] = pB[j] = make_float2(b.x, b.y);
+            pA[j + 1] = pB[j + 1] = make_float2(b.z, b.w);
+        }
+        float ldA = 0.f, ldB = 0.f, ssA = 0.f, ssB = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < D; ++i) {
+            float2 hA[H / 2], hB[H / 2], gA[H / 2], gB[H / 2];
+#pragma unroll
+            for (int j = 0; j < H / 2; ++j) {
+                gA[j] = make_float2(fmaxf(pA[j].x, 0.f), fmaxf(pA[j].y, 0.f));
+                gB[j] = make_float2(fmaxf(pB[j].x, 0.f), fmaxf(pB[j].y, 0.f));
+            }
+            dense_relu<H>(W, L::W2, L::B2, gA, gB, hA, hB);
+            dense_relu<H>(W, L::W3, L::B3, hA, hB, gA, gB);
+            // (s_i, t_i): four partial sums per row keep the dependent FFMA2 chains short
+            float2 oA[4], oB[4];
+            oA[0] = oB[0] = lds2(W, L::B4 + 2 * i);
+#pragma unroll
+            for (int q = 1; q < 4; ++q) oA[q] = oB[q] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float a = (k & 1) ? gA[k >> 1].y : gA[k >> 1].x;
+                const float b = (k & 1) ? gB[k >> 1].y : gB[k >> 1].x;
+                const float2 w = lds2(W, L::W4 + k * 2 * D + 2 * i);
+                oA[k & 3] = ffma2(w, make_float2(a, a), oA[k & 3]);
+                oB[k & 3] = ffma2(w, make_float2(b, b), oB[k & 3]);
+            }
+            const float sA = (oA[0].x + oA[1].x) + (oA[2].x + oA[3].x), tA = (oA[0].y + oA[1].y) + (oA[2].y + oA[3].y);
+            const float sB = (oB[0].x + oB[1].x) + (oB[2].x + oB[3].x), tB = (oB[0].y + oB[1].y) + (oB[2].y + oB[3].y);
+            const float xa = (ra[i] - tA) * sm_exp<true>(-sA), xb = (rb[i] - tB) * sm_exp<true>(-sB);
+            ra[i] = xa, rb[i] = xb;
+            ldA -= sA, ldB -= sB;
+            ssA = fmaf(xa, xa, ssA), ssB = fmaf(xb, xb, ssB);
+            const float2 aa = make_float2(xa, xa), bb = make_float2(xb, xb);
+#pragma unroll
+            for (int j = 0; j < H / 2; j += 2) {  // rank-1 update: x_i enters the first layer
+                const float4 w = lds4(W, L::W1 + i * H + 2 * j);
+                pA[j] = ffma2(make_float2(w.x, w.y), aa, pA[j]);
+                pB[j] = ffma2(make_float2(w.x, w.y), bb, pB[j]);
+                pA[j + 1] = ffma2(make_float2(w.z, w.w), aa, pA[j + 1]);
+                pB[j + 1] = ffma2(make_float2(w.z, w.w), bb, pB[j + 1]);
+            }
+        }
+        const long long rowA = row0 + lane, rowB = rowA + 32;
+        if (rowA < n_rows) {
+            const float l = (ld_in ? ld_in[rowA] : 0.f) + ldA;
+            if (ld_out) ld_out[rowA] = l;
+            const float lp = -0.5f * ssA - 0.5f * (float)D * 1.8378770664093453f;
+            if (lp_mode) lp_out[rowA] = lp_mode == 2 ? lp + l : lp;
+        }
+        if (rowB < n_rows) {
+            const float l = (ld_in ? ld_in[rowB] : 0.f) + ldB;
+            if (ld_out) ld_out[rowB] = l;
+            const float lp = -0.5f * ssB - 0.5f * (float)D * 1.8378770664093453f;
+            if (lp_mode) lp_out[rowB] = lp_mode == 2 ? lp + l : lp;
+        }
+        if (x == nullptr) continue;
+        __syncwarp();
+#pragma unroll 4
+        for (int e = lane; e < kMadeWarpRows * (D / 4); e += 32) {
+            const int r = e / (D / 4), c = (e % (D / 4)) * 4;
+            if (row0 + r >= n_rows) continue;
+            const float *d = tile + r * S;
+            st_stream4(reinterpret_cast<float4 *>(x + (row0 + r) * D + c), make_float4(d[c], d[c + 1], d[c + 2], d[c + 3]));
+        }
+    }
+}
+
 template <int D, int H>
 static bool made_shape_is(const mnf_flow_op &op) {
     return op.n_lin == 4 && op.sizes[0] == D && op.sizes[1] == H && op.sizes[2] == H && op.sizes[3] == H &&
            op.sizes[4] == 2 * D;
 }
 
-// Returns 0 when launched, 1 when the program is not an all-MADE one-pass stack of the supported shape (the
+// Returns 0 when launched, 1 when the program is not an all-MADE stack of the supported shape (the
 // caller falls through to the next path), other values on error.  dir_flags: bit0 inverse, bit1 sum log-det
 // into base_lp.  scratch: [n_rows * dim] floats, needed only when y == NULL and n_ops > 1.
 int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
@@ -230,25 +348,26 @@ int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, con
     for (int k = 0; k < n_ops; ++k) {
         const mnf_flow_op &op = ops[k];
         if (op.type != MNF_OP_MADE || !made_shape_is<D, H>(op)) return 1;
-        const bool sequential = (op.flags & MNF_FLAG_MADE_SEQ) ? !inverse : inverse;
-        if (sequential) return 1;
     }
     if (!y && !inter && n_ops > 1 && !scratch) return 1;
     if (plan_only) return 0;
     const DeviceProps *dp = device_props();
     MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
 
-    const size_t smem = sizeof(float) * (L::kFloats + kMadeRows * (D + 1));
+    const size_t smem = sizeof(float) * (L::kFloats + kMadeWarps * kMadeWarpRows * (D + 1));
     int dev = 0;
     MNF_CUDA(cudaGetDevice(&dev));
     static bool attr_set[64] = {};
     if (!attr_set[dev & 63]) {
         MNF_CUDA(cudaFuncSetAttribute(made_fast_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MNF_CUDA(cudaFuncSetAttribute(made_seq_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev & 63] = true;
     }
-    const long long n_tiles = (n_rows + kMadeRows - 1) / kMadeRows;
-    const long long cap = 2LL * dp->sm_count;  // two resident blocks per SM (shared-memory bound)
-    const unsigned blocks = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    const long long n_tiles = (n_rows + kMadeWarpRows - 1) / kMadeWarpRows;
+    const long long want = (n_tiles + kMadeWarps - 1) / kMadeWarps;
+    const unsigned blocks = (unsigned)(want < dp->sm_count ? want : dp->sm_count);  // one persistent block per SM
+    const long long seq_want = (n_tiles + kMadeSeqWarps - 1) / kMadeSeqWarps;
+    const unsigned seq_blocks = (unsigned)(seq_want < dp->sm_count ? seq_want : dp->sm_count);
     const float *src = x;
     int rc = 0;
     for (int k = 0; k < n_ops; ++k) {
@@ -259,9 +378,15 @@ int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, con
         float *ld_dst = log_det ? log_det : (last ? nullptr : (base_lp && (dir_flags & 2) ? base_lp : nullptr));
         const float *ld_src = k == 0 ? nullptr : (log_det ? log_det : ((dir_flags & 2) ? base_lp : nullptr));
         const int lp_mode = (last && base_lp) ? ((dir_flags & 2) ? 2 : 1) : 0;
-        made_fast_kernel<D, H><<<blocks, 128, smem, stream>>>(params + op.net_off[0], src, dst, ld_src, ld_dst, base_lp,
-                                                              n_rows, (op.flags & MNF_FLAG_PARITY) ? 1 : 0, lp_mode);
-        rc = launch_status("made_fast_kernel");
+        const bool sequential = (op.flags & MNF_FLAG_MADE_SEQ) ? !inverse : inverse;
+        const int parity = (op.flags & MNF_FLAG_PARITY) ? 1 : 0;
+        if (sequential)
+            made_seq_kernel<D, H><<<seq_blocks, 32 * kMadeSeqWarps, smem, stream>>>(params + op.net_off[0], src, dst, ld_src,
+                                                                                ld_dst, base_lp, n_rows, parity, lp_mode);
+        else
+            made_fast_kernel<D, H><<<blocks, 32 * kMadeWarps, smem, stream>>>(params + op.net_off[0], src, dst, ld_src, ld_dst,
+                                                                          base_lp, n_rows, parity, lp_mode);
+        rc = launch_status(sequential ? "made_seq_kernel" : "made_fast_kernel");
         if (rc) break;
         if (last && inter && y)
             MNF_CUDA(cudaMemcpyAsync(y, dst, sizeof(float) * n_rows * D, cudaMemcpyDeviceToDevice, stream));
