@@ -321,6 +321,55 @@ typedef struct mnf_kl_args {
 } mnf_kl_args;
 int mnf_kl_div(const mnf_kl_args *args_host, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Training path of the MNF layers.  The reference differentiates MNFLinear.forward /
+ * kl_div with torch autograd (tests/test_mnf_mnist.py:28-43: loss = nll + 1e-3 kl_div, loss.backward());
+ * the drop-in modules' autograd Functions (torch_mnf/layers/_train.py) are built from these exact-fp32
+ * primitives.  Row-major everywhere; every pointer is a device pointer.
+ * ---------------------------------------------------------------------------------- */
+/* C[M,N] = op(A)[M,K] op(B)[K,N] + bias[N] (optional) + beta C.  trans_a: A is stored [K,M] with leading
+ * dimension lda, else [M,K]; trans_b: B is stored [N,K] (torch's Linear.weight), else [K,N]. */
+int mnf_gemm_f32(int trans_a, int trans_b, int64_t M, int N, int K, const float *A, int64_t lda, const float *B,
+                 int64_t ldb, const float *bias, float beta, float *C, int64_t ldc, void *stream);
+
+enum mnf_ew_op {
+    MNF_EW_MUL = 1,        /* out = a b                                                                    */
+    MNF_EW_MUL_ROWVEC = 2, /* out = a b[col]                       (W_mean * z, mnf_linear.py:69)           */
+    MNF_EW_FMA = 3,        /* out = a + b c                                                                */
+    MNF_EW_SQUARE = 4,     /* out = a^2                            (x**2, mnf_linear.py:54)                 */
+    MNF_EW_EXP = 5,        /* out = exp(a)                         (W_log_var.exp(), :51)                   */
+    MNF_EW_LEAKY = 6,      /* out = LeakyReLU_0.2(a)               (models/mlp.py:9)                        */
+    MNF_EW_LEAKY_BWD = 7,  /* out = a (b > 0 ? 1 : 0.2)            a = gradient, b = pre-activation         */
+    MNF_EW_NOISE_OUT = 8,  /* out = a + sqrt(b) c                  (mean + var.sqrt() * eps, :57)           */
+    MNF_EW_GVAR = 9,       /* out = a c / (2 sqrt(b))              d loss / d var from d loss / d out       */
+    MNF_EW_LIN_IN_BWD = 10,/* out = a c + 2 d b, out2 = a d        a = d/d(xz), b = d/d(x^2), c = z, d = x  */
+    MNF_EW_Z0 = 11,        /* out = a[col] + exp(b[col] / 2) c     (q0_mean + q0_std * eps, :62-64)         */
+};
+/* n elements; operands not used by `op` may be NULL; [col] operands are vectors of ncols entries. */
+int mnf_ew(int op, const float *a, const float *b, const float *c, const float *d, float *out, float *out2, int64_t n,
+           int ncols, void *stream);
+/* out[n] = sum_r a[r,n] * (b ? b[r,n] : 1) */
+int mnf_colsum(const float *a, const float *b, int64_t n_rows, int n_cols, float *out, void *stream);
+
+/* RNVP.forward after the conditioner (rnvp.py:33-40): gate = sigmoid(scale), z_out = (1-mask) z gate +
+ * (1-gate) shift + mask z, log_det[row] = sum (1-mask) log(gate); and its adjoint (grad_z holds only the direct
+ * path, the caller adds mask * d loss / d(mask z) coming back through the conditioner). */
+int mnf_rnvp_gate_forward(const float *z, const float *mask, const float *shift, const float *scale, float *z_out,
+                          float *log_det, int64_t n_rows, int dim, void *stream);
+int mnf_rnvp_gate_backward(const float *z, const float *mask, const float *shift, const float *scale,
+                           const float *grad_out, const float *grad_log_det, float *grad_shift, float *grad_scale,
+                           float *grad_z, int64_t n_rows, int dim, void *stream);
+
+/* Weight-sized part of MNFLinear.kl_div (mnf_linear.py:67-79) with injected eps_w [n_out, n_in]:
+ *   pre[j] = sum_i (W_mean[j,i] z_i + exp(W_log_var[j,i]/2) eps_w[j,i]) r0_c[i]   (the tanh argument, :77)
+ *   kl_rows[j] = 0.5 sum_i (-W_log_var + exp(W_log_var) + (W_mean z)^2 - 1)       (kl_div_W = sum_j, :72)
+ * and the adjoint (grad_W_* overwritten, grad_z / grad_r0_c overwritten). */
+int mnf_kl_rows_forward(const float *z, const float *W_mean, const float *W_log_var, const float *r0_c, const float *eps_w,
+                        float *pre, float *kl_rows, int n_out, int n_in, void *stream);
+int mnf_kl_rows_backward(const float *z, const float *W_mean, const float *W_log_var, const float *r0_c,
+                         const float *eps_w, const float *grad_pre, const float *grad_kl_rows, float *grad_W_mean,
+                         float *grad_W_log_var, float *grad_z, float *grad_r0_c, int n_out, int n_in, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

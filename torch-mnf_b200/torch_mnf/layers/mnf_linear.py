@@ -6,6 +6,7 @@ from torch import nn
 
 from .. import _lib, flows
 from . import _mnf_ops as ops
+from . import _train
 
 
 class MNFLinear(nn.Module):
@@ -70,6 +71,8 @@ class MNFLinear(nn.Module):
         return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=precision)
 
     def forward(self, x, noise=None, row_offset=0, relu=False, precision=None):
+        if _train.needs_grad(self, x):  # training: differentiable exact-fp32 path (layers/_train.py)
+            return _train.linear_forward(self, x, noise, relu)
         x = _lib.require_cuda_f32(x, "input")
         return self._forward_rows(x, x.size(0), self._noise(noise, x.device, row_offset), relu, precision)
 
@@ -79,4 +82,6 @@ class MNFLinear(nn.Module):
         return self._forward_rows(x, x.size(0) * n_samples, self._noise(noise, x.device, row_offset), relu)
 
     def kl_div(self, noise=None):
+        if _train.needs_grad(self):
+            return _train.linear_kl_div(self, noise)
         return ops.kl_div(self, conv=False, tape=noise)
