@@ -344,12 +344,24 @@ enum mnf_ew_op {
     MNF_EW_GVAR = 9,       /* out = a c / (2 sqrt(b))              d loss / d var from d loss / d out       */
     MNF_EW_LIN_IN_BWD = 10,/* out = a c + 2 d b, out2 = a d        a = d/d(xz), b = d/d(x^2), c = z, d = x  */
     MNF_EW_Z0 = 11,        /* out = a[col] + exp(b[col] / 2) c     (q0_mean + q0_std * eps, :62-64)         */
+    MNF_EW_MUL_COLVEC = 12,/* out = a b[row]                       (W_mean * z.view(-1,1,1,1), mnf_conv.py:73) */
+    MNF_EW_ADD_2MUL = 13,  /* out = a + 2 b c                      d/dx of the x^2 branch added to the x branch */
+    MNF_EW_ADD_COLVEC = 14,/* out = a + b[row]                     (conv bias in the [c_out, pixels] GEMM layout) */
 };
 /* n elements; operands not used by `op` may be NULL; [col] operands are vectors of ncols entries. */
 int mnf_ew(int op, const float *a, const float *b, const float *c, const float *d, float *out, float *out2, int64_t n,
            int ncols, void *stream);
 /* out[n] = sum_r a[r,n] * (b ? b[r,n] : 1) */
 int mnf_colsum(const float *a, const float *b, int64_t n_rows, int n_cols, float *out, void *stream);
+
+/* MNFConv2d as GEMM (mnf_conv.py:68-79; stride 1, no padding).  cols_t[(ci,kh,kw)][(r,oh,ow)] = x[r,ci,oh+kh,ow+kw], so
+ * conv(x, W)[c_out, (r,oh,ow)] = W[c_out, fan] cols_t; mnf_col2im_t is the adjoint (d loss / d x from d loss / d cols_t);
+ * mnf_swap01 turns [dim0, dim1, inner] into [dim1, dim0, inner] (GEMM layout <-> NCHW); mnf_rowsum: out[r] = sum_c a[r,c]. */
+int mnf_im2col_t(const float *x, float *cols_t, int64_t n_imgs, int c_in, int height, int width, int ksize, void *stream);
+int mnf_col2im_t(const float *grad_cols_t, float *grad_x, int64_t n_imgs, int c_in, int height, int width, int ksize,
+                 void *stream);
+int mnf_swap01(const float *in, float *out, int64_t dim0, int64_t dim1, int64_t inner, void *stream);
+int mnf_rowsum(const float *a, int64_t n_rows, int64_t n_cols, float *out, void *stream);
 
 /* RNVP.forward after the conditioner (rnvp.py:33-40): gate = sigmoid(scale), z_out = (1-mask) z gate +
  * (1-gate) shift + mask z, log_det[row] = sum (1-mask) log(gate); and its adjoint (grad_z holds only the direct

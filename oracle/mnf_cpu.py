@@ -91,7 +91,7 @@ def conv_forward(p, x, tape):
     z, _ = conv_sample_z(p, tape)
     n_out = p["W_mean"].shape[0]
     W_mean = p["W_mean"] * z.view(-1, 1, 1, 1)
-    mean = F.conv2d(x, weight=W_mean, bias=torch.zeros(n_out))
+    mean = F.conv2d(x, weight=W_mean, bias=torch.zeros(n_out, dtype=W_mean.dtype))
     var = F.conv2d(x**2, weight=p["W_log_var"].exp(), bias=p["b_log_var"].exp())
     eps = tape.normal(var.shape)
     return mean + var.sqrt() * eps

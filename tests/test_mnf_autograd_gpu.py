@@ -77,6 +77,89 @@ def test_mnf_linear_kl_div_gradients(name, n_in, n_out, kw):
     _compare(layer, sd64, name + " kl_div")
 
 
+def test_mnf_conv_gradients():
+    from torch_mnf.layers import MNFConv2d
+
+    g = load_golden("mnf_conv_2x3k3")
+    sd = golden_sd(g)
+    layer = MNFConv2d(2, 3, kernel_size=3)
+    layer.load_state_dict(sd, strict=True)
+    layer.cuda()
+    x = t(g, "x")
+    y_gold = t(g, "fwd/y")
+    w = torch.randn(y_gold.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+
+    sd64 = _sd64(sd)
+    x64 = x.double().requires_grad_()
+    y_ref = mnf_cpu.conv_forward(sd64, x64, golden_tape(g, "fwd_noise/"))
+    ((y_ref * w).sum() + mnf_cpu.conv_kl_div(sd64, golden_tape(g, "kl_noise/"))).backward()
+
+    xg = x.cuda().requires_grad_()
+    y = layer(xg, noise=golden_tape(g, "fwd_noise/"))
+    torch.testing.assert_close(y.detach().cpu(), y_gold, rtol=1e-4, atol=1e-5)
+    kl = layer.kl_div(noise=golden_tape(g, "kl_noise/"))
+    torch.testing.assert_close(kl.detach().cpu(), t(g, "kl/value"), rtol=2e-5, atol=1e-4)
+    ((y * w.cuda().float()).sum() + kl).backward()
+    scale = float(x64.grad.abs().max())
+    assert float((xg.grad.cpu().double() - x64.grad).abs().max()) <= 2e-4 * scale
+    _compare(layer, sd64, "mnf_conv_2x3k3")
+
+
+def test_mnf_lenet_gradients():
+    """The reference's training loss (tests/test_mnf_mnist.py:28-31) on the LeNet fixture: every parameter gradient
+    against the fp64 oracle under the same noise."""
+    from torch_mnf.models import MNFLeNet
+
+    g = load_golden("mnf_lenet")
+    sd = golden_sd(g)
+    net = MNFLeNet()
+    net.load_state_dict(sd, strict=True)
+    net.cuda()
+    x = t(g, "x")
+    labels = torch.arange(x.size(0)) % 10
+
+    sd64 = _sd64(sd)
+    ref = torch.nn.functional.nll_loss(mnf_cpu.lenet_forward(sd64, x.double(), golden_tape(g, "fwd_noise/")), labels)
+    ref = ref + 1e-3 * mnf_cpu.lenet_kl_div(sd64, golden_tape(g, "kl_noise/"))
+    ref.backward()
+
+    logp = net(x.cuda(), noise=golden_tape(g, "fwd_noise/"))
+    torch.testing.assert_close(logp.detach().cpu(), t(g, "fwd/y"), rtol=1e-4, atol=2e-5)
+    loss = torch.nn.functional.nll_loss(logp, labels.cuda()) + 1e-3 * net.kl_div(noise=golden_tape(g, "kl_noise/"))
+    torch.testing.assert_close(loss.detach().cpu().double(), ref.detach(), rtol=1e-5, atol=1e-5)
+    loss.backward()
+    _compare(net, sd64, "mnf_lenet")
+
+
+def test_mnf_lenet_trains():
+    """tests/test_mnf_mnist.py:34-58 on synthetic digits (no dataset offline): noisy copies of 10 fixed templates,
+    batch 32, Adam, loss = nll + 1e-3 * kl_div, stop once a batch reaches 95 %; validation accuracy must exceed 0.8."""
+    from torch_mnf.models import MNFLeNet
+
+    torch.manual_seed(0)
+    templates = t(load_golden("mnf_lenet"), "templates").cuda()
+
+    def batch(n):
+        y = torch.randint(0, 10, (n,), device="cuda")
+        return (templates[y] + 0.25 * torch.randn(n, 1, 28, 28, device="cuda")).clamp(0, 1), y
+
+    net = MNFLeNet().cuda()
+    adam = torch.optim.Adam(net.parameters())
+    for _step in range(400):
+        x, y = batch(32)
+        adam.zero_grad()
+        preds = net(x)
+        loss = torch.nn.functional.nll_loss(preds, y) + 1e-3 * net.kl_div()
+        loss.backward()
+        adam.step()
+        if float((preds.argmax(1) == y).float().mean()) > 0.95:
+            break
+    x_val, y_val = batch(500)
+    with torch.no_grad():
+        val_acc = float((net(x_val).argmax(1) == y_val).float().mean())
+    assert val_acc > 0.8, f"val_acc {val_acc:.3f} after {_step + 1} steps"
+
+
 def test_gemm_f32_all_transpositions():
     from torch_mnf.layers import _train
 

@@ -88,6 +88,9 @@ __global__ void ew_kernel(int op, const float *__restrict__ a, const float *__re
                 out2[i] = a[i] * d[i];
                 break;
             case MNF_EW_Z0: out[i] = fmaf(expf(0.5f * b[col]), c[i], a[col]); break;  // q0_mean + std eps
+            case MNF_EW_MUL_COLVEC: out[i] = a[i] * b[i / ncols]; break;              // per-row scale (W_mean * z[c_out])
+            case MNF_EW_ADD_2MUL: out[i] = fmaf(2.f * b[i], c[i], a[i]); break;       // a + 2 b c
+            case MNF_EW_ADD_COLVEC: out[i] = a[i] + b[i / ncols]; break;              // per-row bias
             default: break;
         }
     }
@@ -189,6 +192,65 @@ __global__ void kl_rows_bwd_kernel(const float *__restrict__ z, const float *__r
     if (j1 > j0) atomicAdd(&gz[i], az), atomicAdd(&gc[i], ac);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// convolution as GEMM (stride 1, no padding): transposed im2col  colsT[(ci,kh,kw)][(r,oh,ow)] = x[r,ci,oh+kh,ow+kw],
+// its adjoint (gather form, no atomics), and the [A,B,inner] -> [B,A,inner] layout swap between the GEMM's
+// [c_out, R*OH*OW] and the module's [R, c_out, OH, OW]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void im2col_t_kernel(const float *__restrict__ x, float *__restrict__ colsT, long long R, int c_in, int H,
+                                int W, int ks) {
+    const int OH = H - ks + 1, OW = W - ks + 1;
+    const long long P = R * OH * OW, total = (long long)c_in * ks * ks * P;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i % P;
+        const int f = (int)(i / P), kw = f % ks, kh = (f / ks) % ks, ci = f / (ks * ks);
+        const int ow = (int)(p % OW), oh = (int)((p / OW) % OH);
+        const long long r = p / ((long long)OW * OH);
+        colsT[i] = x[((r * c_in + ci) * H + oh + kh) * W + ow + kw];
+    }
+}
+
+__global__ void col2im_t_kernel(const float *__restrict__ g_colsT, float *__restrict__ gx, long long R, int c_in, int H,
+                                int W, int ks) {
+    const int OH = H - ks + 1, OW = W - ks + 1;
+    const long long P = R * OH * OW, total = R * c_in * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W), h = (int)((i / W) % H), ci = (int)((i / ((long long)W * H)) % c_in);
+        const long long r = i / ((long long)W * H * c_in);
+        float acc = 0.f;
+        for (int kh = 0; kh < ks; ++kh) {
+            const int oh = h - kh;
+            if (oh < 0 || oh >= OH) continue;
+            for (int kw = 0; kw < ks; ++kw) {
+                const int ow = w - kw;
+                if (ow < 0 || ow >= OW) continue;
+                acc += g_colsT[(long long)((ci * ks + kh) * ks + kw) * P + (r * OH + oh) * OW + ow];
+            }
+        }
+        gx[i] = acc;
+    }
+}
+
+__global__ void swap01_kernel(const float *__restrict__ in, float *__restrict__ out, long long A, long long B,
+                              long long inner) {
+    const long long total = A * B * inner;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i % inner, b = (i / inner) % B, a = i / (inner * B);  // i walks the input [A, B, inner]
+        out[(b * A + a) * inner + t] = in[i];
+    }
+}
+
+// out[r] = sum_c a[r, c]; one warp per row
+__global__ void rowsum_kernel(const float *__restrict__ a, long long rows, long long cols, float *__restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.f;
+    for (long long c = lane; c < cols; c += 32) s += a[row * cols + c];
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+
 static unsigned ew_blocks(long long n) {
     long long b = (n + 255) / 256;
     return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -218,7 +280,7 @@ int mnf_gemm_f32(int trans_a, int trans_b, int64_t M, int N, int K, const float 
 
 int mnf_ew(int op, const float *a, const float *b, const float *c, const float *d, float *out, float *out2, int64_t n,
            int ncols, void *stream) {
-    MNF_REQUIRE(op >= MNF_EW_MUL && op <= MNF_EW_Z0, MNF_E_ARG, "unknown elementwise op %d", op);
+    MNF_REQUIRE(op >= MNF_EW_MUL && op <= MNF_EW_ADD_COLVEC, MNF_E_ARG, "unknown elementwise op %d", op);
     MNF_REQUIRE(a && out && n >= 0 && ncols >= 1, MNF_E_ARG, "bad argument");
     if (n == 0) return 0;
     ew_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(op, a, b, c, d, out, out2, n, ncols);
@@ -234,6 +296,41 @@ int mnf_colsum(const float *a, const float *b, int64_t R, int N, float *out, voi
     if (gy > 128) gy = 128;
     colsum_kernel<<<dim3((N + 127) / 128, (unsigned)gy), 128, 0, st>>>(a, b, R, N, out);
     return launch_status("colsum_kernel");
+}
+
+int mnf_im2col_t(const float *x, float *cols_t, int64_t n_imgs, int c_in, int height, int width, int ksize, void *stream) {
+    MNF_REQUIRE(x && cols_t, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(ksize >= 1 && ksize <= height && ksize <= width, MNF_E_SHAPE, "kernel larger than the image");
+    const long long total = (long long)c_in * ksize * ksize * n_imgs * (height - ksize + 1) * (width - ksize + 1);
+    if (total == 0) return 0;
+    im2col_t_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, cols_t, n_imgs, c_in, height, width, ksize);
+    return launch_status("im2col_t_kernel");
+}
+
+int mnf_col2im_t(const float *grad_cols_t, float *grad_x, int64_t n_imgs, int c_in, int height, int width, int ksize,
+                 void *stream) {
+    MNF_REQUIRE(grad_cols_t && grad_x, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(ksize >= 1 && ksize <= height && ksize <= width, MNF_E_SHAPE, "kernel larger than the image");
+    const long long total = n_imgs * c_in * height * width;
+    if (total == 0) return 0;
+    col2im_t_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(grad_cols_t, grad_x, n_imgs, c_in, height, width, ksize);
+    return launch_status("col2im_t_kernel");
+}
+
+int mnf_swap01(const float *in, float *out, int64_t dim0, int64_t dim1, int64_t inner, void *stream) {
+    MNF_REQUIRE(in && out && in != out, MNF_E_ARG, "NULL or aliased pointer");
+    const long long total = dim0 * dim1 * inner;
+    if (total == 0) return 0;
+    swap01_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(in, out, dim0, dim1, inner);
+    return launch_status("swap01_kernel");
+}
+
+int mnf_rowsum(const float *a, int64_t n_rows, int64_t n_cols, float *out, void *stream) {
+    MNF_REQUIRE(a && out, MNF_E_ARG, "NULL pointer");
+    if (n_rows == 0) return 0;
+    const long long threads = n_rows * 32;
+    rowsum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, n_rows, n_cols, out);
+    return launch_status("rowsum_kernel");
 }
 
 int mnf_rnvp_gate_forward(const float *z, const float *mask, const float *shift, const float *scale, float *z_out,

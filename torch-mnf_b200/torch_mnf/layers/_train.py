@@ -24,9 +24,14 @@ _lib.register({
     "mnf_rnvp_gate_backward": (_int, [_vp] * 9 + [_i64, _int, _vp]),
     "mnf_kl_rows_forward": (_int, [_vp] * 7 + [_int, _int, _vp]),
     "mnf_kl_rows_backward": (_int, [_vp] * 11 + [_int, _int, _vp]),
+    "mnf_im2col_t": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp]),
+    "mnf_col2im_t": (_int, [_vp, _vp, _i64, _int, _int, _int, _int, _vp]),
+    "mnf_swap01": (_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    "mnf_rowsum": (_int, [_vp, _i64, _i64, _vp, _vp]),
 })
 
 EW_MUL, EW_MUL_ROWVEC, EW_FMA, EW_SQUARE, EW_EXP, EW_LEAKY, EW_LEAKY_BWD, EW_NOISE_OUT, EW_GVAR, EW_LIN_IN_BWD, EW_Z0 = range(1, 12)
+EW_MUL_COLVEC, EW_ADD_2MUL, EW_ADD_COLVEC = 12, 13, 14
 
 
 def _p(t):
@@ -103,6 +108,40 @@ def colsum(a, b=None):
         rc = _lib.lib().mnf_colsum(a.data_ptr(), _p(b), R, N, out.data_ptr(), _lib.stream_ptr(a.device))
     _lib.check(rc, "mnf_colsum")
     _lib.launch_count += 1
+    return out
+
+
+def _call(name, *args, device):
+    with torch.cuda.device(device):
+        rc = getattr(_lib.lib(), name)(*args, _lib.stream_ptr(device))
+    _lib.check(rc, name)
+    _lib.launch_count += 1
+
+
+def im2col_t(x, ks):
+    R, c_in, H, W = x.shape
+    out = torch.empty((c_in * ks * ks, R * (H - ks + 1) * (W - ks + 1)), device=x.device, dtype=torch.float32)
+    _call("mnf_im2col_t", x.data_ptr(), out.data_ptr(), R, c_in, H, W, ks, device=x.device)
+    return out
+
+
+def col2im_t(g_cols_t, shape, ks):
+    R, c_in, H, W = shape
+    out = torch.empty(shape, device=g_cols_t.device, dtype=torch.float32)
+    _call("mnf_col2im_t", g_cols_t.data_ptr(), out.data_ptr(), R, c_in, H, W, ks, device=g_cols_t.device)
+    return out
+
+
+def swap01(t, d0, d1, inner):
+    """[d0, d1, inner] -> [d1, d0, inner] (contiguous copy)."""
+    out = torch.empty(d1 * d0 * inner, device=t.device, dtype=torch.float32)
+    _call("mnf_swap01", t.data_ptr(), out.data_ptr(), d0, d1, inner, device=t.device)
+    return out
+
+
+def rowsum(a):
+    out = torch.empty(a.size(0), device=a.device, dtype=torch.float32)
+    _call("mnf_rowsum", a.data_ptr(), a.size(0), a.size(1), out.data_ptr(), device=a.device)
     return out
 
 
@@ -350,6 +389,95 @@ def linear_kl_div(layer, noise=None):
     kl_b = 0.5 * torch.sum(-layer.b_log_var + layer.b_log_var.exp() + layer.b_mean**2 - 1)
     log_q = -ld_q.squeeze() - 0.5 * layer.q0_log_var.sum()
     a = torch.tanh(pre).mean()
+    mean_r, log_var_r = layer.r0_b1 * a, layer.r0_b2 * a
+    z_r, ld_r = rnvp_stack(list(layer.flow_r.flows), z, tape)
+    log_r = ld_r.squeeze() + 0.5 * torch.sum(-log_var_r.exp() * (z_r[0] - mean_r) ** 2 + log_var_r)
+    return kl_W + kl_b + log_q - log_r
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MNFConv2d
+# ------------------------------------------------------------------------------------------------------------------
+class MnfConvOutFn(torch.autograd.Function):
+    """mean = conv(x, W_mean * z[c]), var = conv(x^2, exp(W_log_var)) + exp(b_log_var), out = mean + sqrt(var) eps
+    (mnf_conv.py:68-79) as im2col GEMMs in the [c_out, R*OH*OW] layout, with a hand-written adjoint."""
+
+    @staticmethod
+    def forward(ctx, x, z, W_mean, W_log_var, b_log_var, eps):
+        x, z = _c(x), _c(z)
+        R, c_in, H, W = x.shape
+        c_out, ks = W_mean.shape[0], W_mean.shape[2]
+        S, fan = (H - ks + 1) * (W - ks + 1), c_in * ks * ks
+        cols = im2col_t(x, ks)
+        cols2 = ew(EW_SQUARE, cols)
+        Wm = _c(W_mean).view(c_out, fan)
+        Wz = ew(EW_MUL_COLVEC, Wm, z, ncols=fan)
+        Wv = ew(EW_EXP, _c(W_log_var).view(c_out, fan))
+        bv = ew(EW_EXP, _c(b_log_var))
+        mean = swap01(gemm(Wz, cols), c_out, R, S).view(eps.shape)
+        var_t = ew(EW_ADD_COLVEC, gemm(Wv, cols2), bv, ncols=R * S)
+        var = swap01(var_t, c_out, R, S).view(eps.shape)
+        ctx.save_for_backward(z, Wm, cols, cols2, Wz, Wv, bv, var, eps)
+        ctx.geom = (tuple(x.shape), ks, W_mean.shape)
+        return ew(EW_NOISE_OUT, mean, var, eps)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        z, Wm, cols, cols2, Wz, Wv, bv, var, eps = ctx.saved_tensors
+        xshape, ks, wshape = ctx.geom
+        R, c_out = xshape[0], wshape[0]
+        fan, P = cols.shape
+        S = P // R
+        g = _c(g)
+        g_var = ew(EW_GVAR, g, var, eps)
+        g_t = swap01(g, R, c_out, S).view(c_out, P)
+        gv_t = swap01(g_var, R, c_out, S).view(c_out, P)
+        gWz = gemm(g_t, cols, trans_b=True)
+        gW_mean = ew(EW_MUL_COLVEC, gWz, z, ncols=fan).view(wshape)
+        gz = rowsum(ew(EW_MUL, gWz, Wm))
+        gW_lv = ew(EW_MUL, gemm(gv_t, cols2, trans_b=True), Wv).view(wshape)
+        gb_lv = ew(EW_MUL, rowsum(gv_t), bv)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            g_cols = ew(EW_ADD_2MUL, gemm(Wz, g_t, trans_a=True), gemm(Wv, gv_t, trans_a=True), cols)
+            gx = col2im_t(g_cols, xshape, ks)
+        return gx, gz, gW_mean, gW_lv, gb_lv, None
+
+
+def conv_forward(layer, x, noise=None, relu_pool=False):
+    """MNFConv2d.forward (mnf_conv.py:67-79), differentiable."""
+    x = _lib.require_cuda_f32(x, "input")
+    tape = _tape(noise, x.device)
+    z, _ = sample_z(layer, -1, tape, layer.n_out)
+    ks = layer.kernel_size
+    eps = _draw(tape, "normal", (x.size(0), layer.n_out, x.size(2) - ks + 1, x.size(3) - ks + 1), x.device)
+    out = MnfConvOutFn.apply(x, z[0], layer.W_mean, layer.W_log_var, layer.b_log_var, eps)
+    return torch.nn.functional.max_pool2d(torch.relu(out), 2) if relu_pool else out
+
+
+def conv_kl_div(layer, noise=None):
+    """MNFConv2d.kl_div (mnf_conv.py:90-133), differentiable.  The flows and the two r0_c contractions run on the
+    CUDA primitives; the remaining terms are elementwise over the (small) conv weights and left to torch."""
+    dev = layer.W_mean.device
+    if dev.type != "cuda":
+        raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
+    tape = _tape(noise, dev)
+    n_out = layer.n_out
+    z, ld_q = sample_z(layer, -1, tape, n_out)
+    W_var, b_var = layer.W_log_var.exp(), layer.b_log_var.exp()
+    Wz = layer.W_mean * z.view(-1, 1, 1, 1)
+    kl_W = 0.5 * torch.sum(-layer.W_log_var + W_var + Wz**2 - 1)
+    kl_b = 0.5 * torch.sum(-layer.b_log_var + b_var - 1)  # the reference's b_mean is a fixed zero
+    log_q = -ld_q.squeeze() - 0.5 * layer.q0_log_var.sum()
+    c_row = layer.r0_c.view(1, -1)
+    act_mean = LinearFn.apply(Wz.reshape(-1, n_out), c_row, None)[:, 0]            # eq. (11)
+    act_std = LinearFn.apply(W_var.sqrt().reshape(-1, n_out), c_row, None)[:, 0]   # eq. (12)
+    eps_w = _draw(tape, "normal", act_std.shape, dev)
+    act = act_mean + act_std * eps_w
+    eps_b = _draw(tape, "normal", (), dev)
+    act = act + torch.sum(b_var * layer.r0_c**2).sqrt() * eps_b
+    a = act.mean()
     mean_r, log_var_r = layer.r0_b1 * a, layer.r0_b2 * a
     z_r, ld_r = rnvp_stack(list(layer.flow_r.flows), z, tape)
     log_r = ld_r.squeeze() + 0.5 * torch.sum(-log_var_r.exp() * (z_r[0] - mean_r) ** 2 + log_var_r)

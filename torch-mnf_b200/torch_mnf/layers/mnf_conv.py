@@ -7,6 +7,7 @@ from torch import nn
 
 from .. import _lib, flows
 from . import _mnf_ops as ops
+from . import _train
 
 
 class MNFConv2d(nn.Module):
@@ -51,10 +52,16 @@ class MNFConv2d(nn.Module):
     def forward(self, x, noise=None, row_offset=0, relu_pool=False, n_imgs=None):
         """relu_pool=True fuses the ReLU + MaxPool2d(2) that follow this layer in MNFLeNet;
         n_imgs > len(x) replicates the images (image r reads x[r % len(x)])."""
+        if _train.needs_grad(self, x):  # training: differentiable exact-fp32 path (layers/_train.py)
+            if n_imgs is not None and n_imgs != x.size(0):
+                x = x.repeat(n_imgs // x.size(0), 1, 1, 1)
+            return _train.conv_forward(self, x, noise, relu_pool)
         x = _lib.require_cuda_f32(x, "input")
         noise = noise if isinstance(noise, ops.Noise) else ops.Noise(noise, x.device, row_offset)
         z, _ = self.sample_z(noise)
         return ops.conv_forward(self, x, z, noise, n_imgs=n_imgs, relu_pool=relu_pool)
 
     def kl_div(self, noise=None):
+        if _train.needs_grad(self):
+            return _train.conv_kl_div(self, noise)
         return ops.kl_div(self, conv=True, tape=noise)

@@ -8,6 +8,7 @@ from torch import nn
 from .. import _lib
 from ..layers import MNFConv2d, MNFLinear
 from ..layers import _mnf_ops as ops
+from ..layers import _train
 
 
 class MNFLeNet(nn.Sequential):
@@ -37,6 +38,13 @@ class MNFLeNet(nn.Sequential):
 
     def forward(self, x, noise=None, n_samples: int = 1, row_offset: int = 0, seed=None):
         x = _lib.require_cuda_f32(x, "input")
+        if _train.needs_grad(self, x):  # training: every layer takes its differentiable path, one shared tape
+            tape = _train._tape(noise, x.device)
+            h = x.repeat(n_samples, 1, 1, 1) if n_samples > 1 else x
+            h = _train.conv_forward(self[0], h, tape, relu_pool=True)
+            h = _train.conv_forward(self[3], h, tape, relu_pool=True)
+            h = _train.linear_forward(self[7], h.flatten(1), tape, relu=True)
+            return torch.log_softmax(_train.linear_forward(self[9], h, tape), dim=-1)
         R = x.size(0) * n_samples
         nz = ops.Noise(noise, x.device, row_offset, seed=seed)
         if self.precision != "fp32" and R >= self.TC_MIN_ROWS:
