@@ -68,14 +68,22 @@ x3 = torch.randn(n, 64, device=dev, generator=torch.Generator(device=dev).manual
 best, med = gpu_time(lambda: model3.inverse(x3), iters=5)
 xc = torch.randn(1 << 16, 64)
 cpu = cpu_time(lambda: flows_cpu.stack(sd3, specs3, xc, True))
-record(config="cfg3 MAF x9 D=64 density, batch 2^20 (TF32 tensor-core chain)", gpu_ms=best, gpu_rows_per_s=n / (best * 1e-3),
+record(config="cfg3 MAF x9 D=64 density, batch 2^20 (exact-fp32 shared-memory MADE kernel, the default)", gpu_ms=best, gpu_rows_per_s=n / (best * 1e-3),
        hbm_gbs_algorithmic=516 * n / (best * 1e-3) / 1e9, cpu_rows_per_s=(1 << 16) / cpu, cpu_sample="2^16 rows", cpu_cores=cores)
 for f in model3.flows:
-    f.precision = "fp32"
-x3s = x3[: 1 << 17].contiguous()
-best, med = gpu_time(lambda: model3.inverse(x3s), iters=3)
-record(config="cfg3 same, exact-fp32 interpreter (parity path)", gpu_ms=best, gpu_rows_per_s=(1 << 17) / (best * 1e-3), sample="2^17 rows")
-del x3, x3s
+    f.precision = "tf32"
+best, med = gpu_time(lambda: model3.inverse(x3), iters=5)
+record(config="cfg3 same, TF32 tensor-core GEMM chain (precision='tf32')", gpu_ms=best, gpu_rows_per_s=n / (best * 1e-3))
+x3s = x3[: 1 << 16].contiguous()
+best, med = gpu_time(lambda: model3._program().run(x3s, True, kernel="generic"), iters=3)
+record(config="cfg3 same, generic interpreter (parity path)", gpu_ms=best, gpu_rows_per_s=(1 << 16) / (best * 1e-3), sample="2^16 rows")
+for f in model3.flows:
+    f.precision = "auto"
+z3 = torch.randn(1 << 18, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+best, med = gpu_time(lambda: model3.forward(z3), iters=3)
+record(config="cfg3 stack, sampling direction (MAF.forward: 64 sequential passes per flow), batch 2^18", gpu_ms=best,
+       gpu_rows_per_s=(1 << 18) / (best * 1e-3), note="reference on CPU: 8.4 k rows/s (SURVEY.md 8f-2 probe)")
+del x3, x3s, z3
 
 # ---- cfg4: MNF-LeNet, 1024 images x 500 MC samples ----
 from torch_mnf.models import MNFLeNet

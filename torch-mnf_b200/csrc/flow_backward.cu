@@ -23,6 +23,14 @@ struct FlowProgram {
 
 constexpr int kMaxNetOut = 1024;  // widest conditioner output the backward pass handles
 
+// Parameter-gradient accumulation: the 32 lanes of a warp always add to the SAME parameter (control flow around every
+// call is warp-uniform: op sequence, layer sizes and loop bounds come from the program, rows past the end run on
+// zeros), so the lanes are summed with shuffles first and one lane issues the atomic.
+__device__ __forceinline__ void red_add(float *addr, float v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(addr, v);
+}
+
 // ---------------------------------------------------------------------------------------
 // 7-wide forward-mode dual numbers
 // ---------------------------------------------------------------------------------------
@@ -250,10 +258,10 @@ __device__ __noinline__ void mlp_backward(const NetRef &net, const float *in, fl
         for (int i = 0; i < n_i; ++i) gprev[i] = 0.f;
         for (int j = 0; j < n_o; ++j) {
             const float gp = g[j];
-            if (gp == 0.f) continue;
-            atomicAdd(&gbias[j], gp);
+            if (__all_sync(0xffffffffu, gp == 0.f)) continue;
+            red_add(&gbias[j], gp);
             for (int i = 0; i < n_i; ++i) {
-                atomicAdd(&gW[j * n_i + i], gp * in_l[i]);
+                red_add(&gW[j * n_i + i], gp * in_l[i]);
                 gprev[i] = fmaf(W[j * n_i + i], gp, gprev[i]);
             }
         }
@@ -284,13 +292,13 @@ __device__ void bw_affine_const(const mnf_flow_op &op, const float *P, float *G,
     for (int d = 0; d < D; ++d) {
         if (inverse) {  // out = (in - t) e^{-s}; ld -= s
             const float e = expf(-s[d]), out = (in[d] - t[d]) * e;
-            atomicAdd(&gs[d], -g[d] * out - gl);
-            atomicAdd(&gt[d], -g[d] * e);
+            red_add(&gs[d], -g[d] * out - gl);
+            red_add(&gt[d], -g[d] * e);
             g[d] *= e;
         } else {  // out = in e^{s} + t; ld += s
             const float e = expf(s[d]);
-            atomicAdd(&gs[d], g[d] * in[d] * e + gl);
-            atomicAdd(&gt[d], g[d]);
+            red_add(&gs[d], g[d] * in[d] * e + gl);
+            red_add(&gt[d], g[d]);
             g[d] *= e;
         }
     }
@@ -307,12 +315,12 @@ __device__ void bw_glow(const mnf_flow_op &op, const float *P, float *G, const f
         float acc = 0.f;
         for (int j = 0; j < D; ++j) {
             acc = fmaf(M[i * D + j], g[j], acc);
-            atomicAdd(&gM[i * D + j], in[i] * g[j]);
+            red_add(&gM[i * D + j], in[i] * g[j]);
         }
         gin[i] = acc;
     }
     for (int i = 0; i < D; ++i) g[i] = gin[i];
-    atomicAdd(&G[op.aux_off + 2 * D * D], inverse ? -gl : gl);
+    red_add(&G[op.aux_off + 2 * D * D], inverse ? -gl : gl);
 }
 
 __device__ void bw_affine_half(const mnf_flow_op &op, const float *P, float *G, const float *in, float *g, float gl,
@@ -413,7 +421,7 @@ __device__ void bw_nsf_ar_inverse(const mnf_flow_op &op, const float *P, float *
             for (int o = 0; o < nb; ++o) sc.gout[o] = 0.f;
             gin[0] += rq_spline_backward(P + op.aux_off, op.K, op.bound, op.edge_deriv, false, in[0], g[0], gl, sc.gout);
             for (int o = 0; o < nb; ++o)
-                if (sc.gout[o] != 0.f) atomicAdd(&G[op.aux_off + o], sc.gout[o]);
+                red_add(&G[op.aux_off + o], sc.gout[o]);
         } else {
             sizes[0] = i;
             NetRef net{P + woff, G + woff, op.n_lin, sizes, false};
@@ -473,21 +481,31 @@ __device__ void bw_made(const mnf_flow_op &op, const float *P, float *G, const f
 
 __global__ void __launch_bounds__(64)
 flow_backward_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
-                     float *__restrict__ gparams, const float *__restrict__ x, const float *__restrict__ inter,
+                     float *gparams, const float *__restrict__ x, const float *__restrict__ inter,
                      const float *__restrict__ gy, const float *__restrict__ gld, const float *__restrict__ ginter,
-                     float *__restrict__ gx, long long n_rows, int D, int inverse) {
+                     float *__restrict__ gx, long long n_rows, int D, int inverse, int n_params, int grads_in_smem) {
+    // parameter gradients are summed per block in shared memory when the blob fits (one flush of global atomics
+    // per block instead of one global atomic per point and weight)
+    extern __shared__ float smem_grad[];
+    float *const gout = gparams;
+    if (grads_in_smem) {
+        for (int i = threadIdx.x; i < n_params; i += blockDim.x) smem_grad[i] = 0.f;
+        __syncthreads();
+        gparams = smem_grad;
+    }
     Scratch sc;
     float g[MNF_MAX_DIM], in[MNF_MAX_DIM];
-    for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows;
-         row += (long long)gridDim.x * blockDim.x) {
-        for (int d = 0; d < D; ++d) g[d] = gy ? gy[row * D + d] : 0.f;
-        const float gl = gld ? gld[row] : 0.f;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n_rows; base += (long long)gridDim.x * blockDim.x) {
+        const long long row = base + threadIdx.x;
+        const bool valid = row < n_rows;  // lanes past the end run on zeros so that the warp stays converged
+        for (int d = 0; d < D; ++d) g[d] = (valid && gy) ? gy[row * D + d] : 0.f;
+        const float gl = (valid && gld) ? gld[row] : 0.f;
         for (int kk = prog.n_ops - 1; kk >= 0; --kk) {
             const mnf_flow_op &op = prog.ops[inverse ? prog.n_ops - 1 - kk : kk];
-            if (ginter)  // the caller also used this flow's output directly (an element of the returned list)
+            if (ginter && valid)  // the caller also used this flow's output directly (an element of the returned list)
                 for (int d = 0; d < D; ++d) g[d] += ginter[((size_t)kk * n_rows + row) * D + d];
             const float *src = kk == 0 ? x + row * D : inter + ((size_t)(kk - 1) * n_rows + row) * D;
-            for (int d = 0; d < D; ++d) in[d] = src[d];
+            for (int d = 0; d < D; ++d) in[d] = valid ? src[d] : 0.f;
             switch (op.type) {
                 case MNF_OP_AFFINE_CONST: bw_affine_const(op, params, gparams, in, g, gl, D, inverse); break;
                 case MNF_OP_GLOW: bw_glow(op, params, gparams, in, g, gl, D, inverse); break;
@@ -498,8 +516,13 @@ flow_backward_kernel(const __grid_constant__ FlowProgram prog, const float *__re
                 default: break;
             }
         }
-        if (gx)
+        if (gx && valid)
             for (int d = 0; d < D; ++d) gx[row * D + d] = g[d];
+    }
+    if (grads_in_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_params; i += blockDim.x)
+            if (smem_grad[i] != 0.f) atomicAdd(&gout[i], smem_grad[i]);
     }
 }
 
@@ -533,11 +556,18 @@ int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float 
     FlowProgram prog;
     prog.n_ops = n_ops;
     for (int k = 0; k < n_ops; ++k) prog.ops[k] = ops_host[k];
+    const DeviceProps *dp = device_props();
+    MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
+    const size_t smem = sizeof(float) * (size_t)n_params;
+    const int in_smem = smem <= 96 * 1024;
+    if (in_smem && smem > 48 * 1024)
+        MNF_CUDA(cudaFuncSetAttribute(flow_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long blocks = (n_rows + 63) / 64;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    flow_backward_kernel<<<(unsigned)blocks, 64, 0, (cudaStream_t)stream>>>(prog, params, grad_params, x, intermediates,
-                                                                          grad_y, grad_log_det, grad_intermediates,
-                                                                          grad_x, n_rows, dim, inverse);
+    const long long cap = (long long)dp->sm_count * 4;  // few, long-lived blocks: one gradient flush each
+    if (blocks > cap) blocks = cap;
+    flow_backward_kernel<<<(unsigned)blocks, 64, in_smem ? smem : 0, (cudaStream_t)stream>>>(
+        prog, params, grad_params, x, intermediates, grad_y, grad_log_det, grad_intermediates, grad_x, n_rows, dim, inverse,
+        (int)n_params, in_smem);
     return launch_status("flow_backward_kernel");
 }
 
