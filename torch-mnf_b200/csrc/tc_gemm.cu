@@ -585,6 +585,55 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
     return launch_bn<256>(A, B, M, N, K, ep, dp, stream);
 }
 
+
+// ---- conv tail after the two GEMMs: out = maxpool2(relu(mean + sd * eps)) from pool-major GEMM rows ----
+// mean / sd: [M, Np] with row m = 4 * window + 2 * (oy & 1) + (ox & 1), window = (img * PH + py) * PW + px.
+// A thread owns one channel of a 2 x 4 patch (two pool windows): the four outputs of a Philox call are four
+// consecutive ox of one row, so two calls cover the patch (the GEMM-epilogue form of this stage, mode 5, spends a
+// whole Philox call per element on 8 warps per SM and took 3x longer than this full-occupancy pass).
+// Needs OW % 4 == 0.  Channels are the fastest thread index: loads of mean / sd are contiguous across the warp.
+__global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd,
+                                            const float *__restrict__ eps, uint64_t seed, uint32_t noise_stream,
+                                            uint64_t row_offset, float *__restrict__ out, long long n_imgs, int C, int Np,
+                                            int OH, int OW) {
+    const int PH = OH >> 1, PW = OW >> 1, GX = OW >> 2;
+    const long long total = n_imgs * PH * GX * C;
+    const Philox rng(seed);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % C);
+        long long t = i / C;
+        const int gx = (int)(t % GX);
+        t /= GX;
+        const int py = (int)(t % PH);
+        const long long img = t / PH;
+        float best0 = 0.f, best1 = 0.f;  // ReLU folded into the max
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int oy = 2 * py + r;
+            const long long le = ((img * C + n) * OH + oy) * OW + 4 * gx;
+            float nz[4];
+            if (eps) {
+                const float4 e = *reinterpret_cast<const float4 *>(eps + le);
+                nz[0] = e.x, nz[1] = e.y, nz[2] = e.z, nz[3] = e.w;
+            } else {
+                const uint4 rr = rng((uint64_t)(le + (long long)row_offset * C * OH * OW) >> 2, noise_stream);
+                const float2 a = box_muller(rr.x, rr.y), b = box_muller(rr.z, rr.w);
+                nz[0] = a.x, nz[1] = a.y, nz[2] = b.x, nz[3] = b.y;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long w = (img * PH + py) * PW + 2 * gx + (u >> 1);
+                const size_t e = (size_t)(4 * w + 2 * r + (u & 1)) * Np + n;
+                const float v = fmaf(sd[e], nz[u], mean[e]);
+                if (u < 2) best0 = fmaxf(best0, v);
+                else best1 = fmaxf(best1, v);
+            }
+        }
+        float *o = out + ((img * C + n) * PH + py) * PW + 2 * gx;
+        o[0] = best0, o[1] = best1;
+    }
+}
+
 }  // namespace tc
 }  // namespace mnf
 
@@ -1007,6 +1056,19 @@ int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, c
     rc = tc::launch(a_var, Bv, (int)M, Np, Kp, ev, st);
     if (rc) return rc;
     tc::Epilogue em{};
+    if (OW % 4 == 0) {
+        // plain mean GEMM into the (now dead) x^2 operand buffer, then the full-occupancy noise / ReLU / pool pass
+        float *mean = a_var;
+        em.mode = 0, em.out = mean;
+        rc = tc::launch(a_mean, Bm, (int)M, Np, Kp, em, st);
+        if (rc) return rc;
+        const long long total = n_imgs * (OH / 2) * (OW / 4) * c_out;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sd, eps, seed, noise_stream, row_offset, out,
+                                                                       n_imgs, c_out, Np, OH, OW);
+        return launch_status("conv_rows_noise_pool_kernel");
+    }
     em.mode = 5, em.sd = sd, em.sd_rows = 1, em.eps = eps, em.seed = seed, em.noise_stream = noise_stream;
     em.row_offset = row_offset, em.out = out, em.conv_c = c_out, em.conv_oh = OH, em.conv_ow = OW;
     return tc::launch(a_mean, Bm, (int)M, Np, Kp, em, st);
