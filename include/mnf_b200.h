@@ -282,8 +282,11 @@ int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const flo
  * mnf_conv2d_moments: the sample-independent mean and standard deviation of an MNFConv2d (z is shared by the
  *   call, mnf_conv.py:72), [n_imgs, c_out, OH, OW] each.
  * mnf_conv_noise_relu_pool: out[r] = maxpool2(relu(mean[r % n_unique] + sd[r % n_unique] * eps[r])).
- * mnf_conv2d_forward_tc: MNFConv2d.forward + ReLU + MaxPool2d(2) as im2col + two TF32 tensor-core GEMMs
- *   (workspace: mnf_conv_tc_workspace() floats; tolerance class 2e-3). */
+ * mnf_conv2d_forward_tc: MNFConv2d.forward + ReLU + MaxPool2d(2) on the TF32 tensor cores (workspace:
+ *   mnf_conv_tc_workspace() floats; tolerance class 2e-3).  When 128 is a multiple of OH*OW, c_out <= 64 and OW % 4 == 0
+ *   (MNF-LeNet's second conv) it is an implicit GEMM: x is read once, the x and x^2 operand tiles are generated in
+ *   shared memory and both moments come out of one kernel; otherwise im2col + two GEMMs.
+ * mnf_conv_tc_stage: packed TF32 weights (and, unless a_mean = a_var = NULL, the materialised im2col operands). */
 int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, const float *W_log_var,
                        const float *b_log_var, float *mean_out, float *sd_out, int64_t n_imgs, int c_in,
                        int height, int width, int c_out, int ksize, void *stream);

@@ -128,3 +128,28 @@ def test_mnf_lenet_mc_pipeline_tensor_cores():
     net.precision = "fp32"
     y32 = net(x.cuda(), noise=seeded_tape(lenet_draws(R), 3), n_samples=S).cpu()
     torch.testing.assert_close(y32, ref, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("n_imgs", [1, 7, 300])
+def test_implicit_gemm_conv_matches_exact_path(n_imgs):
+    """MNF-LeNet's second conv (20 -> 50 channels, 5x5 on 12x12) through the implicit-GEMM tensor-core kernel (operand tiles
+    generated in shared memory, odd image counts leave a half-filled last tile) against the exact-fp32 kernel with the
+    same injected noise; tf32 tolerance class."""
+    from tests.test_mnf_gpu import seeded_tape
+    from torch_mnf import _lib
+    from torch_mnf.layers import MNFConv2d
+    from torch_mnf.layers import _mnf_ops as ops
+
+    torch.manual_seed(1)
+    layer = MNFConv2d(20, 50, kernel_size=5).cuda()
+    with torch.no_grad():
+        layer.W_log_var.add_(6.0)  # visible variance term
+    assert _lib.lib().mnf_conv_tc_workspace(n_imgs, 20, 12, 12, 50, 5) < 3 * n_imgs * 64 * 64 + 2 * 64 * 512 + 200
+    x = torch.rand(n_imgs, 20, 12, 12, generator=torch.Generator().manual_seed(2)).cuda()
+    draws = [("normal", (50,)), ("bernoulli", (1, 50)), ("bernoulli", (1, 50)), ("normal", (n_imgs, 50, 8, 8))]
+    ref = layer(x, noise=seeded_tape(draws, 5), relu_pool=True)
+    noise = ops.Noise(seeded_tape(draws, 5), x.device)
+    z, _ = layer.sample_z(noise)
+    got = ops.conv_forward_tc(layer, x, z, noise)
+    assert got.shape == ref.shape == (n_imgs, 50, 4, 4)
+    torch.testing.assert_close(got, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().mean()))

@@ -407,12 +407,14 @@ int mnf_conv_tc_stage(const float *x, const float *z, const float *W_mean, const
                       const float *b_log_var, float *a_mean, float *a_var, float *Bm, float *Bv, float *bvar_p,
                       int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize, int Np, int Kp,
                       void *stream) {
-    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && a_mean && a_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE((a_mean == nullptr) == (a_var == nullptr), MNF_E_ARG, "a_mean and a_var must both be given or both be NULL");
     const int OH = height - ksize + 1, OW = width - ksize + 1, K = c_in * ksize * ksize;
     MNF_REQUIRE(OH >= 2 && OW >= 2 && OH % 2 == 0 && OW % 2 == 0 && Kp % 4 == 0 && Kp >= K && Np >= c_out, MNF_E_SHAPE,
                 "bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     conv_pack_weights_kernel<<<64, 256, 0, st>>>(W_mean, W_log_var, b_log_var, z, c_out, K, Np, Kp, Bm, Bv, bvar_p);
+    if (a_mean == nullptr) return launch_status("conv_pack_weights_kernel");  // weights only (implicit-GEMM conv)
     const size_t smem = sizeof(float) * ((size_t)c_in * height * width + Kp);
     MNF_REQUIRE(smem <= 200 * 1024, MNF_E_SHAPE, "image of %d x %d x %d floats does not fit shared memory", c_in, height, width);
     if (smem > 48 * 1024)

@@ -586,6 +586,218 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 }
 
 
+// =====================================================================================================================
+// Implicit-GEMM MNFConv2d (no im2col in HBM): both moments of the local reparameterisation from ONE pass over x.
+//   mean[m, n] = sum_k A[m, k] Bm[n, k]          A[m, k]  = tf32(x[img, ci, oy + ky, ox + kx])     (generated in smem)
+//   sd[m, n]   = sqrt(sum_k A2[m, k] Bv[n, k] + exp(b_log_var[n]))    A2 = tf32(x^2)
+// rows m are pool-major (4 * window + 2 * (oy & 1) + (ox & 1)), k = (ci * ks + ky) * ks + kx padded to Kp.
+// A tile is 128 rows = IMGS whole images (128 % (OH * OW) == 0).  Roles (384 threads): warp 0 = TMA producer of the
+// two weight tiles, warp 1 = single-thread tcgen05.mma issuer (two MMAs per k-step into two 64-column TMEM
+// accumulators), warp 2 = TMEM allocator, warps 4-7 = A generators (a thread owns a tile row: it gathers the row's
+// taps from the images staged in shared memory by cp.async one tile ahead, and writes the A and A2 tiles in the
+// 128-byte-swizzle K-major layout the UMMA descriptor expects, then fence.proxy.async + mbarrier arrive), warps
+// 8-11 = epilogue (tcgen05.ld -> mean, sd rows).  The materialised im2col this replaces wrote and re-read
+// 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
+// =====================================================================================================================
+constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64;
+constexpr uint32_t CONV_B_BYTES = CONV_BN * BK * 4, CONV_STAGE_BYTES = 2 * A_BYTES + 2 * CONV_B_BYTES;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_constant__ CUtensorMap map_bv,
+                     const float *__restrict__ x, const float *__restrict__ bvar_log, float *__restrict__ mean,
+                     float *__restrict__ sd, long long n_imgs, int C, int H, int W, int ks, int Kp, int Np) {
+    extern __shared__ uint8_t smem_raw[];
+    const int OH = H - ks + 1, OW = W - ks + 1, RPI = OH * OW, IMGS = BM / RPI, CHW = C * H * W, K = C * ks * ks;
+    const int PW = OW >> 1;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + CONV_STAGES * CONV_STAGE_BYTES;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (CONV_STAGES + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * CONV_STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (3 * CONV_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (3 * CONV_STAGES + CONV_ACC + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * CONV_STAGES + 2 * CONV_ACC);
+    uint8_t *gen = smem_raw + (bars + 256u - smem_u32(smem_raw));  // generic pointers past the barrier block
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    int *koff = reinterpret_cast<int *>(gen);                       // [Kp]
+    float *sbv = reinterpret_cast<float *>(gen) + Kp;               // [CONV_BN] exp(b_log_var)
+    float *xs = sbv + CONV_BN;                                      // 2 x [IMGS * CHW] staged images (16-byte aligned)
+    const uint32_t xs_u32 = smem_u32(xs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
+        koff[k] = k < K ? (ci * H + ky) * W + kx : -1;
+    }
+    for (int n = threadIdx.x; n < CONV_BN; n += blockDim.x) sbv[n] = n < Np ? expf(bvar_log[n]) : 0.f;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bm) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bv) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < CONV_STAGES; ++s) {
+            mbar_init(full_a(s), 128);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int a = 0; a < CONV_ACC; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const long long M = n_imgs * RPI;
+    const long long n_tiles = (n_imgs + IMGS - 1) / IMGS;
+    const int n_kblk = Kp / BK;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer: the two weight tiles of every k-block ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                mbar_wait(empty(stage), phase ^ 1u);
+                mbar_expect_tx(full_b(stage), 2 * CONV_B_BYTES);
+                const uint32_t sb = base + stage * CONV_STAGE_BYTES + 2 * A_BYTES;
+                tma_load_2d(sb, &map_bm, full_b(stage), kb * BK, 0);
+                tma_load_2d(sb + CONV_B_BYTES, &map_bv, full_b(stage), kb * BK, 0);
+                if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(acc_empty(acc), acc_phase ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_mean = tmem_base + (uint32_t)(acc * 2 * CONV_BN), d_var = d_mean + CONV_BN;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                mbar_wait(full_a(stage), phase);
+                mbar_wait(full_b(stage), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + stage * CONV_STAGE_BYTES;
+                const uint64_t a1 = make_smem_desc(sa), a2 = make_smem_desc(sa + A_BYTES);
+                const uint64_t b1 = make_smem_desc(sa + 2 * A_BYTES), b2 = make_smem_desc(sa + 2 * A_BYTES + CONV_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    umma_tf32(d_mean, a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), (kb | k) != 0, Cfg<CONV_BN>::kInstrDesc);
+                    umma_tf32(d_var, a2 + (uint64_t)(2 * k), b2 + (uint64_t)(2 * k), (kb | k) != 0, Cfg<CONV_BN>::kInstrDesc);
+                }
+                umma_commit(empty(stage));
+                if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
+            }
+            umma_commit(acc_full(acc));
+            if (++acc == CONV_ACC) acc = 0, acc_phase ^= 1u;
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---------------- A generators: 128 threads, thread = tile row ----------------
+        const int gt = threadIdx.x - 128, ml = gt;
+        const int img_l = ml / RPI, p = ml % RPI, q = p & 3, w = p >> 2;
+        const int row_base = img_l * CHW + (2 * (w / PW) + (q >> 1)) * W + 2 * (w % PW) + (q & 1);
+        const uint32_t row_smem = (uint32_t)((ml >> 3) * 1024 + (ml & 7) * 128);
+        const int swz = ml & 7;
+        const int n16_full = IMGS * CHW / 4;
+        auto prefetch = [&](long long tile, int buf) {
+            const long long img0 = tile * IMGS;
+            long long left = (n_imgs - img0) * (long long)(CHW / 4);
+            const int n16 = (int)(left < n16_full ? left : n16_full);
+            const float *src = x + (size_t)img0 * CHW;
+            const uint32_t dst = xs_u32 + (uint32_t)buf * (uint32_t)(IMGS * CHW * 4);
+            for (int i = gt; i < n16; i += 128) cp_async16(dst + 16u * i, src + 4 * i);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int stage = 0, buf = 0;
+        uint32_t phase = 0;
+        if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long next = tile + gridDim.x;
+            if (next < n_tiles) prefetch(next, buf ^ 1);  // the other buffer was released by the barrier below
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // every generator's copies of this tile have landed
+            const float *xt = xs + (size_t)buf * IMGS * CHW;
+            const bool row_ok = tile * IMGS + img_l < n_imgs;
+            for (int kb = 0; kb < n_kblk; ++kb) {
+                mbar_wait(empty(stage), phase ^ 1u);
+                uint8_t *sa = smem_raw + (base + stage * CONV_STAGE_BYTES - smem_u32(smem_raw)) + row_smem;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int4 o = *reinterpret_cast<const int4 *>(koff + kb * BK + 4 * c4);
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                    if (row_ok) {
+                        v0 = o.x >= 0 ? xt[row_base + o.x] : 0.f;
+                        v1 = o.y >= 0 ? xt[row_base + o.y] : 0.f;
+                        v2 = o.z >= 0 ? xt[row_base + o.z] : 0.f;
+                        v3 = o.w >= 0 ? xt[row_base + o.w] : 0.f;
+                    }
+                    const int pos = (c4 ^ swz) * 16;
+                    *reinterpret_cast<float4 *>(sa + pos) = make_float4(rn_tf32(v0), rn_tf32(v1), rn_tf32(v2), rn_tf32(v3));
+                    *reinterpret_cast<float4 *>(sa + A_BYTES + pos) =
+                        make_float4(rn_tf32(v0 * v0), rn_tf32(v1 * v1), rn_tf32(v2 * v2), rn_tf32(v3 * v3));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+                mbar_arrive(full_a(stage));
+                if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // all rows of this tile generated: its image buffer is free
+            buf ^= 1;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp >= 8) {
+        // ---------------- epilogue: TMEM -> mean, sd rows ----------------
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(acc_full(acc), acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long m = tile * BM + quarter * 32 + lane;
+            const uint32_t trow = tmem_base + (uint32_t)(acc * 2 * CONV_BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < CONV_BN / 32 && c * 32 < Np; ++c) {
+                uint32_t rm[32], rv[32];
+                tmem_ld32(trow + (uint32_t)(c * 32), rm);
+                tmem_ld32(trow + (uint32_t)(CONV_BN + c * 32), rv);
+                if (m < M) {
+                    float *mrow = mean + (size_t)m * Np + c * 32, *srow = sd + (size_t)m * Np + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        *reinterpret_cast<float4 *>(mrow + j) = make_float4(__uint_as_float(rm[j]), __uint_as_float(rm[j + 1]),
+                                                                            __uint_as_float(rm[j + 2]), __uint_as_float(rm[j + 3]));
+                        const float4 bv = *reinterpret_cast<const float4 *>(sbv + c * 32 + j);
+                        *reinterpret_cast<float4 *>(srow + j) =
+                            make_float4(sqrtf(__uint_as_float(rv[j]) + bv.x), sqrtf(__uint_as_float(rv[j + 1]) + bv.y),
+                                        sqrtf(__uint_as_float(rv[j + 2]) + bv.z), sqrtf(__uint_as_float(rv[j + 3]) + bv.w));
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty(acc));
+            if (++acc == CONV_ACC) acc = 0, acc_phase ^= 1u;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---- conv tail after the two GEMMs: out = maxpool2(relu(mean + sd * eps)) from pool-major GEMM rows ----
 // mean / sd: [M, Np] with row m = 4 * window + 2 * (oy & 1) + (ox & 1), window = (img * PH + py) * PW + px.
 // A thread owns one channel of a 2 x 4 patch (two pool windows): the four outputs of a Philox call are four
@@ -632,6 +844,38 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
         float *o = out + ((img * C + n) * PH + py) * PW + 2 * gx;
         o[0] = best0, o[1] = best1;
     }
+}
+
+// smem of conv_implicit_kernel for this geometry (0 = not eligible)
+static size_t conv_implicit_smem(int c_in, int height, int width, int ksize, int Kp, int Np) {
+    const int OH = height - ksize + 1, OW = width - ksize + 1, RPI = OH * OW, CHW = c_in * height * width;
+    if (RPI <= 0 || BM % RPI != 0 || Np > CONV_BN || Np % 32 != 0 || CHW % 4 != 0 || Kp % BK != 0) return 0;
+    const size_t bytes = (size_t)CONV_STAGES * CONV_STAGE_BYTES + 1024 + 256 + sizeof(float) * ((size_t)Kp + CONV_BN) +
+                         sizeof(float) * 2 * (size_t)(BM / RPI) * CHW + 16;
+    return bytes <= 227 * 1024 ? bytes : 0;
+}
+
+static int launch_conv_implicit(const float *x, const float *Bm, const float *Bv, const float *bvar_log, float *mean, float *sd,
+                                long long n_imgs, int c_in, int height, int width, int ksize, int Kp, int Np,
+                                cudaStream_t stream) {
+    const DeviceProps *dp = device_props();
+    MNF_REQUIRE(dp != nullptr && dp->cc_major == 10, MNF_E_DEVICE, "tcgen05 path needs an sm_100 device");
+    const size_t smem = conv_implicit_smem(c_in, height, width, ksize, Kp, Np);
+    MNF_REQUIRE(smem != 0, MNF_E_SHAPE, "geometry not eligible for the implicit-GEMM conv");
+    MNF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)mean % 16) == 0 && ((uintptr_t)sd % 16) == 0, MNF_E_ALIGN,
+                "pointers must be 16-byte aligned");
+    CUtensorMap mbm, mbv;
+    int rc = make_map(&mbm, Bm, Np, Kp, CONV_BN);
+    if (rc) return rc;
+    rc = make_map(&mbv, Bv, Np, Kp, CONV_BN);
+    if (rc) return rc;
+    MNF_CUDA(cudaFuncSetAttribute(conv_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int RPI = (height - ksize + 1) * (width - ksize + 1), IMGS = BM / RPI;
+    const long long n_tiles = (n_imgs + IMGS - 1) / IMGS;
+    const unsigned grid = (unsigned)(n_tiles < dp->sm_count ? n_tiles : dp->sm_count);
+    conv_implicit_kernel<<<grid, THREADS, smem, stream>>>(mbm, mbv, x, bvar_log, mean, sd, n_imgs, c_in, height, width, ksize,
+                                                          Kp, Np);
+    return launch_status("conv_implicit_kernel");
 }
 
 }  // namespace tc
@@ -1027,6 +1271,8 @@ int64_t mnf_conv_tc_workspace(int64_t n_imgs, int c_in, int height, int width, i
     const int OH = height - ksize + 1, OW = width - ksize + 1;
     const int64_t Kp = (c_in * ksize * ksize + 31) / 32 * 32, Np = (c_out + 31) / 32 * 32;
     const int64_t M = n_imgs * OH * OW;
+    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, (int)Kp, (int)Np) != 0)
+        return 2 * M * Np + 2 * Np * Kp + Np + 64;  // implicit GEMM: mean, sd, packed weights -- no im2col
     return 2 * M * Kp + M * Np + 2 * Np * Kp + Np + 64;
 }
 
@@ -1046,6 +1292,22 @@ int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, c
     MNF_REQUIRE(n_imgs >= 0 && M <= 0x7fffffff - 256, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
     if (n_imgs == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, Kp, Np) != 0) {
+        // implicit GEMM: x is read once, the A / A^2 tiles are generated in shared memory
+        float *mean = workspace, *sdp = mean + (size_t)M * Np, *Bm = sdp + (size_t)M * Np, *Bv = Bm + (size_t)Np * Kp,
+              *bvar_p = Bv + (size_t)Np * Kp;
+        int rc = mnf_conv_tc_stage(x, z, W_mean, W_log_var, b_log_var, nullptr, nullptr, Bm, Bv, bvar_p, n_imgs, c_in, height,
+                                   width, c_out, ksize, Np, Kp, stream);
+        if (rc) return rc;
+        rc = tc::launch_conv_implicit(x, Bm, Bv, bvar_p, mean, sdp, n_imgs, c_in, height, width, ksize, Kp, Np, st);
+        if (rc) return rc;
+        const long long total = n_imgs * (OH / 2) * (OW / 4) * c_out;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sdp, eps, seed, noise_stream, row_offset, out,
+                                                                       n_imgs, c_out, Np, OH, OW);
+        return launch_status("conv_rows_noise_pool_kernel");
+    }
     float *a_mean = workspace, *a_var = a_mean + (size_t)M * Kp, *sd = a_var + (size_t)M * Kp, *Bm = sd + (size_t)M * Np,
           *Bv = Bm + (size_t)Np * Kp, *bvar_p = Bv + (size_t)Np * Kp;
     int rc = mnf_conv_tc_stage(x, z, W_mean, W_log_var, b_log_var, a_mean, a_var, Bm, Bv, bvar_p, n_imgs, c_in, height,
