@@ -591,27 +591,30 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 //   mean[m, n] = sum_k A[m, k] Bm[n, k]          A[m, k]  = tf32(x[img, ci, oy + ky, ox + kx])     (generated in smem)
 //   sd[m, n]   = sqrt(sum_k A2[m, k] Bv[n, k] + exp(b_log_var[n]))    A2 = tf32(x^2)
 // rows m are pool-major (4 * window + 2 * (oy & 1) + (ox & 1)), k = (ci * ks + ky) * ks + kx padded to Kp.
-// A tile is 128 rows = IMGS whole images (128 % (OH * OW) == 0).  Roles (384 threads): warp 0 = TMA producer of the
+// A tile is 128 rows = IMGS whole images (128 % (OH * OW) == 0).  Roles (512 threads): warp 0 = TMA producer of the
 // two weight tiles, warp 1 = single-thread tcgen05.mma issuer (two MMAs per k-step into two 64-column TMEM
-// accumulators), warp 2 = TMEM allocator, warps 4-7 = A generators (a thread owns a tile row: it gathers the row's
-// taps from the images staged in shared memory by cp.async one tile ahead, and writes the A and A2 tiles in the
-// 128-byte-swizzle K-major layout the UMMA descriptor expects, then fence.proxy.async + mbarrier arrive), warps
-// 8-11 = epilogue (tcgen05.ld -> mean, sd rows).  The materialised im2col this replaces wrote and re-read
+// accumulators), warp 2 = TMEM allocator, warps 4-11 = A generators (two threads per tile row: they gather the row's
+// taps from the images staged in shared memory by cp.async one tile ahead -- tap offsets come from a kernel-parameter
+// table through the uniform datapath -- and write the A and A2 tiles in the 128-byte-swizzle K-major layout the UMMA
+// descriptor expects, then fence.proxy.async + mbarrier arrive), warps 12-15 = epilogue (tcgen05.ld -> mean, sd rows).  The materialised im2col this replaces wrote and re-read
 // 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
 // =====================================================================================================================
-constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64;
+constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_THREADS = 512, CONV_MAX_KP = 512;
+struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image, -1 for the zero padding of K; travels as a
+    int off[CONV_MAX_KP];  // kernel parameter so that the generators read it through the uniform datapath
+};
 constexpr uint32_t CONV_B_BYTES = CONV_BN * BK * 4, CONV_STAGE_BYTES = 2 * A_BYTES + 2 * CONV_B_BYTES;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_constant__ CUtensorMap map_bv,
-                     const float *__restrict__ x, const float *__restrict__ bvar_log, float *__restrict__ mean,
+                     const __grid_constant__ ConvTaps taps, const float *__restrict__ x, const float *__restrict__ bvar_log, float *__restrict__ mean,
                      float *__restrict__ sd, long long n_imgs, int C, int H, int W, int ks, int Kp, int Np) {
     extern __shared__ uint8_t smem_raw[];
-    const int OH = H - ks + 1, OW = W - ks + 1, RPI = OH * OW, IMGS = BM / RPI, CHW = C * H * W, K = C * ks * ks;
+    const int OH = H - ks + 1, OW = W - ks + 1, RPI = OH * OW, IMGS = BM / RPI, CHW = C * H * W;
     const int PW = OW >> 1;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + CONV_STAGES * CONV_STAGE_BYTES;
@@ -623,16 +626,11 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
     const uint32_t tmem_slot = bars + 8u * (3 * CONV_STAGES + 2 * CONV_ACC);
     uint8_t *gen = smem_raw + (bars + 256u - smem_u32(smem_raw));  // generic pointers past the barrier block
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    int *koff = reinterpret_cast<int *>(gen);                       // [Kp]
-    float *sbv = reinterpret_cast<float *>(gen) + Kp;               // [CONV_BN] exp(b_log_var)
-    float *xs = sbv + CONV_BN;                                      // 2 x [IMGS * CHW] staged images (16-byte aligned)
+    float *sbv = reinterpret_cast<float *>(gen);  // [CONV_BN] exp(b_log_var)
+    float *xs = sbv + CONV_BN;                    // 2 x [IMGS * CHW] staged images (16-byte aligned)
     const uint32_t xs_u32 = smem_u32(xs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
-        koff[k] = k < K ? (ci * H + ky) * W + kx : -1;
-    }
     for (int n = threadIdx.x; n < CONV_BN; n += blockDim.x) sbv[n] = n < Np ? expf(bvar_log[n]) : 0.f;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bm) : "memory");
@@ -640,7 +638,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < CONV_STAGES; ++s) {
-            mbar_init(full_a(s), 128);
+            mbar_init(full_a(s), 256);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
@@ -703,9 +701,9 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             umma_commit(acc_full(acc));
             if (++acc == CONV_ACC) acc = 0, acc_phase ^= 1u;
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ---------------- A generators: 128 threads, thread = tile row ----------------
-        const int gt = threadIdx.x - 128, ml = gt;
+    } else if (warp >= 4 && warp < 12) {
+        // ---------------- A generators: 256 threads, two per tile row (four 16-byte chunks of the k-block each) ----------------
+        const int gt = threadIdx.x - 128, ml = gt & 127, half = gt >> 7;
         const int img_l = ml / RPI, p = ml % RPI, q = p & 3, w = p >> 2;
         const int row_base = img_l * CHW + (2 * (w / PW) + (q >> 1)) * W + 2 * (w % PW) + (q & 1);
         const uint32_t row_smem = (uint32_t)((ml >> 3) * 1024 + (ml & 7) * 128);
@@ -717,7 +715,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             const int n16 = (int)(left < n16_full ? left : n16_full);
             const float *src = x + (size_t)img0 * CHW;
             const uint32_t dst = xs_u32 + (uint32_t)buf * (uint32_t)(IMGS * CHW * 4);
-            for (int i = gt; i < n16; i += 128) cp_async16(dst + 16u * i, src + 4 * i);
+            for (int i = gt; i < n16; i += 256) cp_async16(dst + 16u * i, src + 4 * i);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         int stage = 0, buf = 0;
@@ -728,15 +726,17 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             if (next < n_tiles) prefetch(next, buf ^ 1);  // the other buffer was released by the barrier below
             else asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // every generator's copies of this tile have landed
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // every generator's copies of this tile have landed
             const float *xt = xs + (size_t)buf * IMGS * CHW;
             const bool row_ok = tile * IMGS + img_l < n_imgs;
             for (int kb = 0; kb < n_kblk; ++kb) {
                 mbar_wait(empty(stage), phase ^ 1u);
                 uint8_t *sa = smem_raw + (base + stage * CONV_STAGE_BYTES - smem_u32(smem_raw)) + row_smem;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int4 o = *reinterpret_cast<const int4 *>(koff + kb * BK + 4 * c4);
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c4 = half * 4 + cc;
+                    const int kk = kb * BK + 4 * c4;
+                    const int4 o = make_int4(taps.off[kk], taps.off[kk + 1], taps.off[kk + 2], taps.off[kk + 3]);
                     float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
                     if (row_ok) {
                         v0 = o.x >= 0 ? xt[row_base + o.x] : 0.f;
@@ -753,11 +753,11 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                 mbar_arrive(full_a(stage));
                 if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // all rows of this tile generated: its image buffer is free
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows of this tile generated: its image buffer is free
             buf ^= 1;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp >= 8) {
+    } else if (warp >= 12) {
         // ---------------- epilogue: TMEM -> mean, sd rows ----------------
         const int quarter = warp & 3;
         int acc = 0;
@@ -850,7 +850,8 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
 static size_t conv_implicit_smem(int c_in, int height, int width, int ksize, int Kp, int Np) {
     const int OH = height - ksize + 1, OW = width - ksize + 1, RPI = OH * OW, CHW = c_in * height * width;
     if (RPI <= 0 || BM % RPI != 0 || Np > CONV_BN || Np % 32 != 0 || CHW % 4 != 0 || Kp % BK != 0) return 0;
-    const size_t bytes = (size_t)CONV_STAGES * CONV_STAGE_BYTES + 1024 + 256 + sizeof(float) * ((size_t)Kp + CONV_BN) +
+    if (Kp > CONV_MAX_KP) return 0;
+    const size_t bytes = (size_t)CONV_STAGES * CONV_STAGE_BYTES + 1024 + 256 + sizeof(float) * CONV_BN +
                          sizeof(float) * 2 * (size_t)(BM / RPI) * CHW + 16;
     return bytes <= 227 * 1024 ? bytes : 0;
 }
@@ -873,8 +874,14 @@ static int launch_conv_implicit(const float *x, const float *Bm, const float *Bv
     const int RPI = (height - ksize + 1) * (width - ksize + 1), IMGS = BM / RPI;
     const long long n_tiles = (n_imgs + IMGS - 1) / IMGS;
     const unsigned grid = (unsigned)(n_tiles < dp->sm_count ? n_tiles : dp->sm_count);
-    conv_implicit_kernel<<<grid, THREADS, smem, stream>>>(mbm, mbv, x, bvar_log, mean, sd, n_imgs, c_in, height, width, ksize,
-                                                          Kp, Np);
+    ConvTaps taps;
+    const int K = c_in * ksize * ksize;
+    for (int k = 0; k < CONV_MAX_KP; ++k) {
+        const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
+        taps.off[k] = k < K ? (ci * height + ky) * width + kx : -1;
+    }
+    conv_implicit_kernel<<<grid, CONV_THREADS, smem, stream>>>(mbm, mbv, taps, x, bvar_log, mean, sd, n_imgs, c_in, height,
+                                                               width, ksize, Kp, Np);
     return launch_status("conv_implicit_kernel");
 }
 
