@@ -497,14 +497,14 @@ def run_lenet(args):
             "data": "synthetic",
             "config": {"workload": f"cfg4: MNF-LeNet (696,950 params), 1024 images x {S} MC samples per GPU per step",
                        "parallelism": f"MC samples sharded over {world} GPU(s); all_reduce of [1024,10] probability sums",
-                       "l2": "activations (11.5 KB/sample after conv1, 131 KB/sample of im2col) far exceed L2"},
+                       "l2": "activations (46 KB/sample before the pool of conv1, 11.5 KB/sample after it) far exceed L2"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": total / (e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": n_img * 784 * 4,
                     "d2h_bytes_per_step": n_img * 40, "ms_per_step": e_ms},
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": peaks()[2].get("bf16_tflops_sustained", 1400.0) / 2,
                          "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / world / (peaks()[2].get("bf16_tflops_sustained", 1400.0) / 2),
                          "traffic": None, "note": "dense-equivalent 8.2 MFLOP/sample against the TF32 peak (= half the measured bf16 "
-                                                  "sustained peak); the pipeline is bound by im2col / noise traffic, not by the tensor pipe"},
+                                                  "sustained peak); the pipeline is bound by operand generation in shared memory (implicit-GEMM conv2) and Philox noise, not by the tensor pipe"},
             "cpu_baseline": None,
         }
         print(json.dumps(out))
