@@ -16,11 +16,6 @@
 
 namespace mnf {
 
-struct FlowProgram {
-    int n_ops;
-    mnf_flow_op ops[MNF_MAX_OPS];
-};
-
 constexpr int kMaxNetOut = 1024;  // widest conditioner output the backward pass handles
 
 // Parameter-gradient accumulation: the 32 lanes of a warp always add to the SAME parameter (control flow around every

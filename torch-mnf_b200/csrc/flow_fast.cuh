@@ -30,11 +30,6 @@ namespace mnf {
 #define MNF_SPLINE_FAST 1
 #endif
 
-struct FlowProgram {
-    int n_ops;
-    mnf_flow_op ops[MNF_MAX_OPS];
-};
-
 // shared-memory offsets (in floats) of each op's nets, computed on the host
 struct FastLayout {
     int net_slot[MNF_MAX_OPS][2];

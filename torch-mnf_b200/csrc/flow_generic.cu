@@ -8,11 +8,6 @@
 
 namespace mnf {
 
-struct FlowProgram {
-    int n_ops;
-    mnf_flow_op ops[MNF_MAX_OPS];
-};
-
 struct Net {
     const float *w;  // start of the packed net
     int n_lin;

@@ -12,6 +12,12 @@
 
 namespace mnf {
 
+// a flow stack as it travels to the kernels: descriptors by value (__grid_constant__), parameters in a device blob
+struct FlowProgram {
+    int n_ops;
+    mnf_flow_op ops[MNF_MAX_OPS];
+};
+
 constexpr float kMinBin = 1e-3f;    // spline_flow.py:17-18
 constexpr float kMinDeriv = 1e-3f;  // spline_flow.py:19
 
