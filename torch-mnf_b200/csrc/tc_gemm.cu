@@ -600,7 +600,7 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 // 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
 // =====================================================================================================================
 constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_THREADS = 512, CONV_MAX_KP = 512;
-struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image, -1 for the zero padding of K; travels as a
+struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image (0 for the zero padding of K); travels as a
     int off[CONV_MAX_KP];  // kernel parameter so that the generators read it through the uniform datapath
 };
 constexpr uint32_t CONV_B_BYTES = CONV_BN * BK * 4, CONV_STAGE_BYTES = 2 * A_BYTES + 2 * CONV_B_BYTES;
@@ -728,29 +728,36 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");  // every generator's copies of this tile have landed
             const float *xt = xs + (size_t)buf * IMGS * CHW;
-            const bool row_ok = tile * IMGS + img_l < n_imgs;
+            // software pipeline: the 16 taps of the NEXT k-block are gathered into registers right after this one is
+            // published, so their shared-memory latency overlaps the wait for the stage to come back from the MMAs
+            float v[16];
+            // no validity checks: the zero padding of K is done by the WEIGHT tiles (their columns >= K are zero and the
+            // padded taps point at offset 0, a finite value), and rows past the last image of a half-filled tile read
+            // whatever the buffer holds -- their outputs are never stored and rows do not mix in an MMA
+            const float *xrow = xt + row_base;
+            auto gather = [&](int kb) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int kk = kb * BK + 4 * (half * 4 + cc);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[4 * cc + u] = xrow[taps.off[kk + u]];
+                }
+            };
+            gather(0);
             for (int kb = 0; kb < n_kblk; ++kb) {
                 mbar_wait(empty(stage), phase ^ 1u);
                 uint8_t *sa = smem_raw + (base + stage * CONV_STAGE_BYTES - smem_u32(smem_raw)) + row_smem;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int c4 = half * 4 + cc;
-                    const int kk = kb * BK + 4 * c4;
-                    const int4 o = make_int4(taps.off[kk], taps.off[kk + 1], taps.off[kk + 2], taps.off[kk + 3]);
-                    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-                    if (row_ok) {
-                        v0 = o.x >= 0 ? xt[row_base + o.x] : 0.f;
-                        v1 = o.y >= 0 ? xt[row_base + o.y] : 0.f;
-                        v2 = o.z >= 0 ? xt[row_base + o.z] : 0.f;
-                        v3 = o.w >= 0 ? xt[row_base + o.w] : 0.f;
-                    }
-                    const int pos = (c4 ^ swz) * 16;
+                    const int pos = ((half * 4 + cc) ^ swz) * 16;
+                    const float v0 = v[4 * cc], v1 = v[4 * cc + 1], v2 = v[4 * cc + 2], v3 = v[4 * cc + 3];
                     *reinterpret_cast<float4 *>(sa + pos) = make_float4(rn_tf32(v0), rn_tf32(v1), rn_tf32(v2), rn_tf32(v3));
                     *reinterpret_cast<float4 *>(sa + A_BYTES + pos) =
                         make_float4(rn_tf32(v0 * v0), rn_tf32(v1 * v1), rn_tf32(v2 * v2), rn_tf32(v3 * v3));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
                 mbar_arrive(full_a(stage));
+                if (kb + 1 < n_kblk) gather(kb + 1);
                 if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows of this tile generated: its image buffer is free
@@ -878,7 +885,7 @@ static int launch_conv_implicit(const float *x, const float *Bm, const float *Bv
     const int K = c_in * ksize * ksize;
     for (int k = 0; k < CONV_MAX_KP; ++k) {
         const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
-        taps.off[k] = k < K ? (ci * height + ky) * width + kx : -1;
+        taps.off[k] = k < K ? (ci * height + ky) * width + kx : 0;  // padded taps: any valid address (weights are zero there)
     }
     conv_implicit_kernel<<<grid, CONV_THREADS, smem, stream>>>(mbm, mbv, taps, x, bvar_log, mean, sd, n_imgs, c_in, height,
                                                                width, ksize, Kp, Np);
