@@ -41,6 +41,22 @@ def _worker(rank, world, port, n_rows, out_dir):
     mine = lp[:4] if rank == 0 else lp[4:]
     probs = reduce_mc_probs(mine.reshape(-1, 10), 5)
     ok = ok and torch.allclose(probs, lp.exp().mean(0), atol=1e-6)
+    # ActNorm data-dependent init: rank 0 initialises (stood in by a function that writes s, t), everyone ends up equal
+    import torch_mnf.flows as nf
+    from torch_mnf.distributed import sync_actnorm_init
+
+    torch.manual_seed(100 + rank)  # different random init per rank on purpose
+    model = nf.NormalizingFlow([nf.ActNormFlow(3), nf.Glow(3), nf.ActNormFlow(3)])
+
+    def fake_init(m):
+        for i, f in enumerate(m.flows):
+            if hasattr(f, "data_dep_init_done"):
+                f.s.data.fill_(0.25 * (i + 1))
+                f.t.data.fill_(-1.5 * (i + 1))
+
+    n_sync = sync_actnorm_init(model, init_fn=fake_init)
+    ok = ok and n_sync == 2 and all(f.data_dep_init_done for f in model.flows if hasattr(f, "data_dep_init_done"))
+    ok = ok and bool((model.flows[0].s == 0.25).all()) and bool((model.flows[2].t == -4.5).all())
     torch.save(ok, os.path.join(out_dir, f"ok{rank}.pt"))
     dist.destroy_process_group()
 

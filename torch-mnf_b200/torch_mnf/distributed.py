@@ -55,6 +55,32 @@ def reduce_mc_probs(log_probs: torch.Tensor, n_images: int, group=None) -> torch
     return sums / count
 
 
+def sync_actnorm_init(model, x_init=None, group=None, src: int = 0, init_fn=None) -> int:
+    """Data-dependent ActNorm initialisation for a model replicated over ranks: the statistics must
+    be those of ONE batch, not of each rank's shard.  Rank ``src`` runs the first ``inverse`` on ``x_init`` (which
+    initialises every pending ActNormFlow from its own input, affine_constant_flow.py:42-50), then ``s`` and ``t`` of
+    all ActNorm flows are broadcast and marked initialised everywhere.  ``init_fn(model)`` replaces the default
+    ``model.inverse(x_init)`` (used by the CPU tests).  Returns the number of flows synchronised."""
+    flows = [f for f in model.flows if hasattr(f, "data_dep_init_done")]
+    if not flows:
+        return 0
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else src
+    if rank == src and any(not f.data_dep_init_done for f in flows):
+        with torch.no_grad():
+            if init_fn is not None:
+                init_fn(model)
+            else:
+                model.inverse(x_init)
+    for f in flows:
+        if multi:
+            for t in (f.s, f.t):
+                dist.broadcast(t.data, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+        f.data_dep_init_done = True
+        f.__dict__["_program_salt"] = f.__dict__.get("_program_salt", 0) + 1  # cached flow programs re-pack s, t
+    return len(flows)
+
+
 class PeerGather:
     """Gather buffer in NVLink peer memory (torch symmetric memory) for per-row results of a sharded batch.
 
