@@ -136,8 +136,8 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
  *   grad_params    [n_params] (in/out): parameter gradients are ADDED at the offsets the parameters have in
  *                  `params` (zero it first); for a Glow op it receives d/dW, d/dW^-1 and d/dlogdet of the assembled
  *                  block and the host chains them to L, S, U.
- * flags: MNF_RUN_INVERSE or 0 -- the direction of the forward run.  Every flow type and direction except
- * NSF_AR.forward.  Exact-fp32 arithmetic, one thread per point. */
+ * flags: MNF_RUN_INVERSE or 0 -- the direction of the forward run.  Every flow type in both directions.
+ * Exact-fp32 arithmetic, one thread per point. */
 int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params,
                             float *grad_params, const float *x, const float *intermediates,
                             const float *grad_y, const float *grad_log_det, const float *grad_intermediates,

@@ -430,6 +430,49 @@ __device__ void bw_nsf_ar_inverse(const mnf_flow_op &op, const float *P, float *
     for (int i = 0; i < D; ++i) g[i] = gin[i];
 }
 
+__device__ void bw_nsf_ar_forward(const mnf_flow_op &op, const float *P, float *G, const float *in, float *g, float gl,
+                                  int D, Scratch &sc) {
+    // NSF_AR.forward (spline_flow.py:199-216): out_i = RQS^-1(in_i; theta_i(out_<i)) -- the spline parameters depend on
+    // the flow's own OUTPUTS.  Rebuild the outputs, then walk i downwards: the gradient reaching out_i is complete
+    // once every i' > i has pushed its conditioner gradient back (same scheme as the sequential MADE direction).
+    const int nb = 3 * op.K - 1;
+    int sizes[MNF_MAX_LIN + 1];
+    for (int l = 0; l <= op.n_lin; ++l) sizes[l] = op.sizes[l];
+    int woff[MNF_MAX_DIM];
+    float outv[MNF_MAX_DIM], gin[MNF_MAX_DIM];
+    {
+        int w = op.net_off[0];
+        for (int i = 0; i < D; ++i) {
+            woff[i] = w;
+            float ld_dummy = 0.f, x = in[i];
+            if (i == 0) {
+                rq_spline<0, false>(P + op.aux_off, op.K, op.bound, op.edge_deriv, true, x, ld_dummy);
+            } else {
+                sizes[0] = i;
+                NetRef net{P + w, G + w, op.n_lin, sizes, false};
+                mlp_forward_tape(net, outv, sc.acts, sc.out);
+                rq_spline<0, false>(sc.out, op.K, op.bound, op.edge_deriv, true, x, ld_dummy);
+                for (int l = 0; l < op.n_lin; ++l) w += sizes[l + 1] * sizes[l] + sizes[l + 1];
+            }
+            outv[i] = x;
+        }
+    }
+    for (int i = D - 1; i >= 0; --i) {
+        for (int o = 0; o < nb; ++o) sc.gout[o] = 0.f;
+        if (i == 0) {
+            gin[0] = rq_spline_backward(P + op.aux_off, op.K, op.bound, op.edge_deriv, true, in[0], g[0], gl, sc.gout);
+            for (int o = 0; o < nb; ++o) red_add(&G[op.aux_off + o], sc.gout[o]);
+        } else {
+            sizes[0] = i;
+            NetRef net{P + woff[i], G + woff[i], op.n_lin, sizes, false};
+            mlp_forward_tape(net, outv, sc.acts, sc.out);
+            gin[i] = rq_spline_backward(sc.out, op.K, op.bound, op.edge_deriv, true, in[i], g[i], gl, sc.gout);
+            mlp_backward(net, outv, sc.acts, sc.gout, g);  // adds to d loss / d out_<i
+        }
+    }
+    for (int i = 0; i < D; ++i) g[i] = gin[i];
+}
+
 __device__ void bw_made(const mnf_flow_op &op, const float *P, float *G, const float *in, float *g, float gl, int D,
                         bool inverse, Scratch &sc) {
     const bool parity = op.flags & MNF_FLAG_PARITY;
@@ -506,7 +549,10 @@ flow_backward_kernel(const __grid_constant__ FlowProgram prog, const float *__re
                 case MNF_OP_GLOW: bw_glow(op, params, gparams, in, g, gl, D, inverse); break;
                 case MNF_OP_AFFINE_HALF: bw_affine_half(op, params, gparams, in, g, gl, D, inverse, sc); break;
                 case MNF_OP_NSF_CL: bw_nsf_cl(op, params, gparams, in, g, gl, D, inverse, sc); break;
-                case MNF_OP_NSF_AR: bw_nsf_ar_inverse(op, params, gparams, in, g, gl, D, sc); break;
+                case MNF_OP_NSF_AR:
+                    if (inverse) bw_nsf_ar_inverse(op, params, gparams, in, g, gl, D, sc);
+                    else bw_nsf_ar_forward(op, params, gparams, in, g, gl, D, sc);
+                    break;
                 case MNF_OP_MADE: bw_made(op, params, gparams, in, g, gl, D, inverse, sc); break;
                 default: break;
             }
@@ -541,8 +587,6 @@ int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float 
     const int inverse = flags & MNF_RUN_INVERSE;
     for (int k = 0; k < n_ops; ++k) {
         const mnf_flow_op &op = ops_host[k];
-        MNF_REQUIRE(op.type != MNF_OP_NSF_AR || inverse, MNF_E_SHAPE,
-                    "backward of NSF_AR.forward (the sequential direction) is not implemented");
         if (op.type >= MNF_OP_AFFINE_HALF)
             MNF_REQUIRE(op.sizes[op.n_lin] <= kMaxNetOut || op.type == MNF_OP_NSF_AR, MNF_E_SHAPE,
                         "conditioner output %d wider than %d", op.sizes[op.n_lin], kMaxNetOut);
