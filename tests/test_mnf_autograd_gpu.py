@@ -160,6 +160,33 @@ def test_mnf_lenet_trains():
     assert val_acc > 0.8, f"val_acc {val_acc:.3f} after {_step + 1} steps"
 
 
+def test_graphed_training_step():
+    """The whole MNF-LeNet training step (forward, kl_div, backward, Adam) captured in one CUDA graph and replayed."""
+    from torch_mnf.graphs import graphed_training_step
+    from torch_mnf.models import MNFLeNet
+
+    torch.manual_seed(0)
+    templates = t(load_golden("mnf_lenet"), "templates").cuda()
+
+    def batch(n):
+        y = torch.randint(0, 10, (n,), device="cuda")
+        return (templates[y] + 0.25 * torch.randn(n, 1, 28, 28, device="cuda")).clamp(0, 1), y
+
+    net = MNFLeNet().cuda()
+    adam = torch.optim.Adam(net.parameters(), capturable=True)
+
+    def loss_fn(model, x, y):
+        return torch.nn.functional.nll_loss(model(x), y) + 1e-3 * model.kl_div()
+
+    step = graphed_training_step(net, loss_fn, adam, batch(32))
+    losses = [float(step(*batch(32))) for _ in range(150)]
+    assert all(l == l for l in losses) and sum(losses[-10:]) < sum(losses[:10])
+    x_val, y_val = batch(500)
+    with torch.no_grad():
+        val_acc = float((net(x_val).argmax(1) == y_val).float().mean())
+    assert val_acc > 0.8, f"val_acc {val_acc:.3f}"
+
+
 def test_gemm_f32_all_transpositions():
     from torch_mnf.layers import _train
 

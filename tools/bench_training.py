@@ -100,6 +100,13 @@ def lcstep():
 
 
 c = cpu_ms(lcstep, iters=5)
-out["mnf_lenet_train_step_b32"] = {"gpu_ms": g, "cpu_port_ms": c, "cpu_threads": torch.get_num_threads()}
-print(f"MNF-LeNet training step, batch 32: GPU {g:.3f} ms, CPU oracle+autograd {c:.1f} ms", flush=True)
+# the same step captured in a CUDA graph (torch_mnf.graphs)
+from torch_mnf.graphs import graphed_training_step
+
+net2 = MNFLeNet().cuda()
+adam2 = torch.optim.Adam(net2.parameters(), capturable=True)
+gstep = graphed_training_step(net2, lambda m, a, b: torch.nn.functional.nll_loss(m(a), b) + 1e-3 * m.kl_div(), adam2, (xg, yg))
+gg = gpu_ms(lambda: gstep(xg, yg))
+out["mnf_lenet_train_step_b32"] = {"gpu_ms": g, "gpu_graph_ms": gg, "cpu_port_ms": c, "cpu_threads": torch.get_num_threads()}
+print(f"MNF-LeNet training step, batch 32: GPU {g:.3f} ms eager, {gg:.3f} ms as one CUDA graph, CPU oracle+autograd {c:.1f} ms", flush=True)
 print(json.dumps(out))

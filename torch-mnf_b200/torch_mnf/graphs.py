@@ -1,0 +1,42 @@
+"""CUDA-graph capture of a whole training step (additive helper, not part of the reference API).
+
+The differentiable paths of the drop-in modules are chains of small launches -- an MNF-LeNet step with the reference's
+loss (nll + 1e-3 * kl_div) is ~600 kernels of a few microseconds each, so at the reference's batch size of 32 the
+step is bound by launch overhead on the host, not by the GPU.  Every launch goes to torch's current stream, allocates
+through torch's caching allocator and draws noise from torch's graph-safe generator, so forward + backward +
+optimizer step can be captured once and replayed."""
+
+from __future__ import annotations
+
+import torch
+
+
+def graphed_training_step(model, loss_fn, optimizer, example_inputs, warmup: int = 3):
+    """Returns ``step(*inputs) -> loss`` that replays one captured ``loss_fn(model, *inputs).backward();
+    optimizer.step()``.  ``example_inputs``: CUDA tensors with the shapes / dtypes every later call will use (they are
+    trained on during warm-up).  The optimizer must be capturable (e.g. ``torch.optim.Adam(..., capturable=True)``).
+    Data-dependent initialisation (ActNormFlow) has to be done before calling this."""
+    static_inputs = tuple(t.clone() for t in example_inputs)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):  # lazy initialisation (kernel attributes, optimizer state) happens outside the capture
+            optimizer.zero_grad(set_to_none=True)
+            loss_fn(model, *static_inputs).backward()
+            optimizer.step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    optimizer.zero_grad(set_to_none=True)
+    with torch.cuda.graph(graph):
+        static_loss = loss_fn(model, *static_inputs)
+        static_loss.backward()
+        optimizer.step()
+
+    def step(*inputs):
+        for dst, src in zip(static_inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return static_loss.detach()
+
+    step.graph = graph
+    return step
