@@ -187,6 +187,20 @@ def test_made_sequential_kernel():
     torch.testing.assert_close(ld_back, -ld_f, rtol=1e-4, atol=1e-3)
 
 
+def test_graphed_log_prob_small_batch():
+    """BASELINE config 1 (RNVP x9, batch 4096) replayed from a CUDA graph gives the eager result."""
+    from torch_mnf.graphs import graphed_inference
+
+    g = load_golden("rnvp9_moons")
+    model = load_flow_model(golden_spec(g), golden_sd(g))
+    x = t(g, "inv/x").cuda()
+    x = x.repeat((4096 + x.size(0) - 1) // x.size(0), 1)[:4096].contiguous()
+    call = graphed_inference(lambda v: model.log_prob(v), (x,))
+    torch.testing.assert_close(call(x), model.log_prob(x), rtol=0, atol=0)
+    x2 = x.flip(0).contiguous()
+    torch.testing.assert_close(call(x2), model.log_prob(x2), rtol=0, atol=0)
+
+
 def test_model_sample_draws_on_device():
     """NormalizingFlowModel.sample (core.py:51-55): base draw + forward; same distribution as pushing torch's own
     standard-normal draws through forward()."""

@@ -52,7 +52,12 @@ xd = x.cuda()
 best, med = gpu_time(lambda: model.log_prob(xd), iters=50)
 cpu = cpu_time(lambda: flows_cpu.log_prob(sd, specs, x), reps=5)
 record(config="cfg1 RNVP x9 (AffineHalfFlow), batch 4096, log_prob", gpu_us_per_call=med * 1e3, gpu_points_per_s=4096 / (med * 1e-3),
-       cpu_points_per_s=4096 / cpu, cpu_cores=cores, note="launch-latency bound: 80 KB of traffic, one kernel + host call")
+       cpu_points_per_s=4096 / cpu, cpu_cores=cores, note="latency-bound inside the kernel: 2048 threads on 16 CTAs (a CUDA-graph replay takes the same time)")
+from torch_mnf.graphs import graphed_inference
+call = graphed_inference(lambda v: model.log_prob(v), (xd,))
+best, med = gpu_time(lambda: call(xd), iters=200)
+record(config="cfg1 same, replayed from a CUDA graph (torch_mnf.graphs.graphed_inference)", gpu_us_per_call=med * 1e3,
+       gpu_points_per_s=4096 / (med * 1e-3), note="input copied into the graph's static buffer, one replay per call")
 xb = x.repeat(4096, 1).cuda()[: 1 << 24].contiguous()
 best, med = gpu_time(lambda: model.log_prob(xb), iters=5)
 record(config="cfg1 stack at batch 2^24 (throughput regime)", gpu_ms=best, gpu_points_per_s=(1 << 24) / (best * 1e-3),
