@@ -9,4 +9,4 @@ CUDA fp32 and the library must be built (``python torch-mnf_b200/build.py``).
 
 __version__ = "0.1.0"
 
-from . import flows, layers, models  # noqa: F401,E402
+from . import data, flows, layers, models  # noqa: F401,E402

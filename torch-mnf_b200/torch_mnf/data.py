@@ -1,7 +1,11 @@
 """Toy 2-D densities used by the reference's tests and notebooks (reference: torch_mnf/data.py:21-31).
 Host-side helpers; the samples are CPU tensors, move them to the GPU before calling a flow."""
 
+import os
+
 import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # reference: torch_mnf/utils.py:13, re-exported by data
 
 
 def sample_moons(n_samples: int) -> torch.Tensor:
