@@ -413,6 +413,32 @@ def run_ours(args):
                      "frac_mlp_only": mlp_tflops / fp32_peak, "fma_per_point_mlp": MLP_FMA_PER_POINT,
                      "note": "conditioner-MLP FMAs only; spline arithmetic shares the same pipe"},
     }
+    if world == 1:
+        # The conditioner-free part of the same stack ([ActNormFlow, Glow] x 3) is the flow workload that IS HBM-bound:
+        # reported next to the headline so that the HBM roofline of the streaming path can be read off this line too.
+        try:
+            from tests.helpers import load_flow_model, random_flow_sd
+
+            sub_specs = [s_ for s_ in specs() if s_["type"] != "NSF_CL"]
+            sub = load_flow_model(sub_specs, random_flow_sd(sub_specs, seed=0), device=dev, return_intermediates=False)
+            ys, lds = torch.empty_like(x), torch.empty(n, device=dev)
+            prog = sub._program()
+            for _ in range(3):
+                prog.run(x, True, out=ys, log_det=lds)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(20):
+                prog.run(x, True, out=ys, log_det=lds)
+            b_.record()
+            torch.cuda.synchronize(dev)
+            sub_ms = a_.elapsed_time(b_) / 20
+            out["hbm_bound_substack"] = {
+                "workload": "[ActNormFlow, Glow] x3 (the conditioner-free flows of the headline stack), inverse with z and log_det stored",
+                "bytes_per_point": 20, "ms": sub_ms, "achieved": 20 * n / (sub_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": 20 * n / (sub_ms * 1e-3) / 1e9 / hbm_peak, "kernel": "affine_stream_kernel"}
+            del ys, lds, sub
+        except Exception as e:  # noqa: BLE001  (diagnostic extra, never fails the bench)
+            out["hbm_bound_substack"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -529,6 +555,23 @@ def run_lenet(args):
                                                   "sustained peak); the pipeline is bound by operand generation in shared memory (implicit-GEMM conv2) and Philox noise, not by the tensor pipe"},
             "cpu_baseline": None,
         }
+        if world == 1 and not args.no_cpu:
+            # the reference's CPU path (oracle port: same ATen ops) on a bounded sample: 8 images x 250 MC samples
+            from oracle import mnf_cpu
+            from oracle.noise import FreshNoise
+
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+            xc = imgs_host[:8].repeat(250, 1, 1, 1)
+            best = float("inf")
+            with torch.no_grad():
+                for _ in range(3):
+                    t_0 = time.perf_counter()
+                    mnf_cpu.lenet_forward(sd_cpu, xc, FreshNoise())
+                    best = min(best, time.perf_counter() - t_0)
+            out["cpu_baseline"] = {"value": xc.size(0) / best, "unit": "samples/s", "cores": cores, "kind": "port",
+                                   "sample": "8 images x 250 MC samples (2000 rows), best of 3"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
