@@ -254,7 +254,7 @@ struct WSel {
     static __device__ __forceinline__ WShared make(const float *smem, int slot) { return WShared{smem + slot}; }
 };
 
-template <int H, int K, int VARIANT>
+template <int H, int K, int VARIANT, bool ONE = false>
 __device__ __forceinline__ void spline_half(const float *smem, int slot, const mnf_flow_op &op, float2 cond,
                                             float2 &trans, bool rqs_inverse, float2 &ld) {
     constexpr int NB = 3 * K - 1;
@@ -271,7 +271,7 @@ __device__ __forceinline__ void spline_half(const float *smem, int slot, const m
             op_dense<H, NP2>(Wa, wo, wo + H * 2 * NP2, hA, hB, rA, rB);
         }
 #pragma unroll 1
-        for (int pt = 0; pt < 2; ++pt) {
+        for (int pt = 0; pt < (ONE ? 1 : 2); ++pt) {
             float raw[NB];
 #pragma unroll
             for (int o = 0; o < NB; ++o) {
@@ -327,38 +327,53 @@ template <int H, int VARIANT>
 __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *dst, int n_out) {
     const int hidden = 2 * H + 2 * (H * H + H);
     const int n = hidden + n_out * H + n_out;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const float w = src[e];
-        int d = e;
-        if constexpr (VARIANT >= 2) {
-            if (e >= 2 * H && e < hidden) {  // the two H x H layers: transpose weight blocks
-                const int r = (e - 2 * H) % (H * H + H), base = e - r;
-                if (r < H * H) d = base + (r % H) * H + (r / H);
-            } else if (e >= hidden && n_out > 1) {
-                const int nop = round4(n_out), r = e - hidden;
-                d = r < n_out * H ? hidden + (r % H) * nop + (r / H) : hidden + H * nop + (r - n_out * H);
-            }
+    // eight independent loads in flight per thread: with one load per trip the copy runs at one L2 latency per
+    // element and thread (measured: ~45 us to stage the 18 nets of BASELINE config 1, most of a small-batch call)
+    for (int e0 = threadIdx.x; e0 < n; e0 += 8 * blockDim.x) {
+        float w8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * blockDim.x;
+            w8[u] = e < n ? src[e] : 0.f;
         }
-        dst[d] = w;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e >= n) continue;
+            int d = e;
+            if constexpr (VARIANT >= 2) {
+                if (e >= 2 * H && e < hidden) {  // the two H x H layers: transpose weight blocks
+                    const int r = (e - 2 * H) % (H * H + H), base = e - r;
+                    if (r < H * H) d = base + (r % H) * H + (r / H);
+                } else if (e >= hidden && n_out > 1) {
+                    const int nop = round4(n_out), r = e - hidden;
+                    d = r < n_out * H ? hidden + (r % H) * nop + (r / H) : hidden + H * nop + (r - n_out * H);
+                }
+            }
+            dst[d] = w8[u];
+        }
     }
 }
 
-// everything that happens to one pair of points: load, all flows, store
-template <int H, int K, int VARIANT>
+// everything that happens to one pair of points: load, all flows, store.
+// ONE: small-batch mode -- `pair` is a POINT index, the B lane of every float2 is a dead copy that the compiler removes
+// (nothing is stored from it), so a thread walks half the dependent FFMA2 chain and twice as many warps share the work.
+template <int H, int K, int VARIANT, bool ONE = false>
 __device__ __forceinline__ void process_pair(const FlowProgram &prog, const FastLayout &lay,
                                              const float *__restrict__ params, const float *smem,
                                              const float *__restrict__ x, float *__restrict__ y,
                                              float *__restrict__ log_det, float *__restrict__ base_lp,
                                              float *__restrict__ inter, long long n_rows, int inverse, bool sum_lp,
                                              long long pair, bool live) {
-    const bool has_b = 2 * pair + 1 < n_rows;
+    const bool has_b = ONE ? false : 2 * pair + 1 < n_rows;
+    const long long first_pt = ONE ? pair : 2 * pair;  // index of point A
     float2 v0, v1;  // v0 = first coordinate of points (A, B), v1 = second coordinate
     if (has_b) {
         const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
         v0 = make_float2(q.x, q.z);
         v1 = make_float2(q.y, q.w);
     } else {
-        const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + 2 * pair);
+        const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + first_pt);
         v0 = make_float2(q.x, q.x);
         v1 = make_float2(q.y, q.y);
     }
@@ -425,12 +440,12 @@ __device__ __forceinline__ void process_pair(const FlowProgram &prog, const Fast
                 const bool use_f1 = (step == 0) != (inverse != 0);
                 const float2 cond = use_f1 ? v0 : v1;
                 float2 tr = use_f1 ? v1 : v0;
-                spline_half<H, K, VARIANT>(smem, lay.net_slot[k][use_f1 ? 0 : 1], op, cond, tr, inverse != 0, ld);
+                spline_half<H, K, VARIANT, ONE>(smem, lay.net_slot[k][use_f1 ? 0 : 1], op, cond, tr, inverse != 0, ld);
                 if (use_f1) v1 = tr; else v0 = tr;
             }
         }
         if (inter && live) {
-            float *dst = inter + ((size_t)kk * n_rows + 2 * pair) * 2;
+            float *dst = inter + ((size_t)kk * n_rows + first_pt) * 2;
             if (has_b)
                 st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
             else
@@ -448,13 +463,13 @@ __device__ __forceinline__ void process_pair(const FlowProgram &prog, const Fast
         if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
         if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
     } else {
-        if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
-        if (log_det) log_det[2 * pair] = ld.x;
-        if (base_lp) base_lp[2 * pair] = lp.x;
+        if (y) st_stream2(reinterpret_cast<float2 *>(y) + first_pt, make_float2(v0.x, v1.x));
+        if (log_det) log_det[first_pt] = ld.x;
+        if (base_lp) base_lp[first_pt] = lp.x;
     }
 }
 
-template <int H, int K, int VARIANT>
+template <int H, int K, int VARIANT, bool ONE = false>
 __global__ void __launch_bounds__(128, 4)
 flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant__ FastLayout lay,
                  const float *__restrict__ params, const float *__restrict__ x, float *__restrict__ y,
@@ -477,19 +492,27 @@ flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant
     }
     __syncthreads();
 
-    const long long n_pairs = (n_rows + 1) >> 1;
+    const long long n_pairs = ONE ? n_rows : (n_rows + 1) >> 1;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // persistent grid-stride loop: the nets are staged once per CTA
     for (long long pair = first; pair < n_pairs; pair += (long long)gridDim.x * blockDim.x)
-        process_pair<H, K, VARIANT>(prog, lay, params, smem, x, y, log_det, base_lp, inter, n_rows, inverse, sum_lp,
-                                    pair, true);
+        process_pair<H, K, VARIANT, ONE>(prog, lay, params, smem, x, y, log_det, base_lp, inter, n_rows, inverse, sum_lp,
+                                         pair, true);
 }
 
-template <int H, int K, int VARIANT>
+// batches below this many points take the one-point-per-thread form of variant 2 (latency, not throughput, matters)
+constexpr long long kOnePointMaxRows = 148LL * 128;
+
+template <int H, int K, int VARIANT, bool ONE = false>
 int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,
                 const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows,
                 int inverse, const DeviceProps *dp, cudaStream_t stream) {
-    auto kern = flow_fast_kernel<H, K, VARIANT>;
+    if constexpr (VARIANT == 2 && !ONE) {
+        if (n_rows <= kOnePointMaxRows)
+            return launch_inst<H, K, 2, true>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse, dp,
+                                              stream);
+    }
+    auto kern = flow_fast_kernel<H, K, VARIANT, ONE>;
     static thread_local int occ_cache = -1;
     static thread_local size_t occ_smem = 0;
     if (occ_cache < 0 || occ_smem != smem_bytes) {
@@ -501,13 +524,15 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
         occ_cache = occ;
         occ_smem = smem_bytes;
     }
-    const long long n_pairs = (n_rows + 1) / 2;
-    long long blocks = (n_pairs + 127) / 128;
+    const long long n_pairs = ONE ? n_rows : (n_rows + 1) / 2;
+    const int threads = 128;  // measured on config 1: CTAs of 32 / 64 threads lose more to the per-CTA staging of the nets
+                              // (128 / 80 us per call) than they gain from spreading the points over more SMs (63 us)
+    long long blocks = (n_pairs + threads - 1) / threads;
     const long long cap = (long long)dp->sm_count * occ_cache;  // persistent: one wave, a multiple of the SM count
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 128, smem_bytes, stream>>>(prog, lay, params, x, y, log_det, base_lp, inter, n_rows,
-                                                        inverse);
+    kern<<<(unsigned)blocks, threads, smem_bytes, stream>>>(prog, lay, params, x, y, log_det, base_lp, inter, n_rows,
+                                                            inverse);
     return launch_status("flow_fast_kernel");
 }
 

@@ -46,20 +46,25 @@ __device__ __forceinline__ void made_stage_net(const float *__restrict__ src, fl
     using L = MadeLayout<D, H>;
     const float *w1 = src, *b1 = w1 + H * D, *w2 = b1 + H, *b2 = w2 + H * H, *w3 = b2 + H, *b3 = w3 + H * H,
                 *w4 = b3 + H, *b4 = w4 + 2 * D * H;
+#pragma unroll 4
     for (int e = threadIdx.x; e < D * H; e += blockDim.x) dst[L::W1 + (e % D) * H + e / D] = w1[e];
+#pragma unroll 4
     for (int e = threadIdx.x; e < H * H; e += blockDim.x) {
         dst[L::W2 + (e % H) * H + e / H] = w2[e];
         dst[L::W3 + (e % H) * H + e / H] = w3[e];
     }
+#pragma unroll 4
     for (int e = threadIdx.x; e < H; e += blockDim.x) {
         dst[L::B1 + e] = b1[e];
         dst[L::B2 + e] = b2[e];
         dst[L::B3 + e] = b3[e];
     }
+#pragma unroll 4
     for (int e = threadIdx.x; e < 2 * D * H; e += blockDim.x) {
         const int row = e / H, k = e % H, c = row / D, i = row % D;  // c = 0: s rows, 1: t rows
         dst[L::W4 + k * 2 * D + 2 * i + c] = w4[e];
     }
+#pragma unroll 4
     for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) dst[L::B4 + 2 * (e % D) + e / D] = b4[e];
 }
 
