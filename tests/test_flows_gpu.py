@@ -284,6 +284,31 @@ def test_empty_and_single_row():
     close(zs[-1], t(g, "inv/z")[:1], "single row", atol_scale=2e-5)
 
 
+@pytest.mark.parametrize("n_rows", [2, 3, 127, 129, 18944, 18945, 18947])
+def test_small_and_ragged_batches_match_interpreter(n_rows):
+    """Batches up to 148 x 128 points take the one-point-per-thread form of the dim-2 kernel, larger ones the paired form
+    (odd sizes leave a half-filled last pair); both must agree with the exact-fp32 interpreter on every output."""
+    for name in ("cfg2_shape", "cfg1_shape"):
+        specs = ORACLE_CASES[name]
+        model = load_flow_model(specs, random_flow_sd(specs, seed=4, scale=0.4))
+        x = 1.2 * torch.randn(n_rows, 2, generator=torch.Generator().manual_seed(n_rows)).cuda()
+        prog = model._program()
+        for inverse in (True, False):
+            y, ld, inter, lp = prog.run(x, inverse, want_inter=True, want_base_lp=True)
+            yg, ldg, interg, lpg = prog.run(x, inverse, want_inter=True, want_base_lp=True, kernel="generic")
+            # indexing test: the tolerance is the fast-math noise floor (see close_vs_oracle), a wrong row would be O(1)
+            torch.testing.assert_close(y, yg, rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(inter, interg, rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(ld, ldg, rtol=1e-4, atol=3e-4)
+            torch.testing.assert_close(lp, lpg, rtol=1e-4, atol=3e-4)
+        torch.testing.assert_close(model.log_prob(x), ldg_lp(prog, x), rtol=1e-4, atol=5e-4)
+
+
+def ldg_lp(prog, x):
+    _, ld, _, lp = prog.run(x, True, want_base_lp=True, kernel="generic")
+    return ld + lp
+
+
 def test_all_points_outside_spline_domain_is_identity():
     """The reference crashes here (spline_flow.py:85); the drop-in maps to identity."""
     import torch_mnf.flows as nf
