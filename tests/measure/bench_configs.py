@@ -1,7 +1,7 @@
 """All five BASELINE.json configurations: CUDA path (this repo) next to the CPU oracle port on the box's
 host cores.  Prints one JSON object per config and writes gpurun_out/configs.json + configs.md."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
 

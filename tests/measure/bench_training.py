@@ -2,7 +2,7 @@
 (tests/test_flows.py) and (b) MNF-LeNet with loss = nll + 1e-3 kl_div (tests/test_mnf_mnist.py), on the CUDA path and,
 for comparison, on the CPU oracle port with torch autograd (same arithmetic as the reference) on the host cores."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
 from torch.distributions import MultivariateNormal

@@ -1,6 +1,6 @@
 """Error statistics of the CUDA flow kernels vs the fp32 oracle and an fp64 evaluation of it."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(ROOT, "torch-mnf_b200"), ROOT]
 import torch
 

@@ -19,7 +19,7 @@ RTOL = 1e-5
 def close(a, b, what, rtol=RTOL, atol_scale=1e-5):
     """Direct comparison with recorded reference outputs: rtol 1e-5 plus an absolute floor of
     atol_scale x (mean magnitude).  Log-dets use 4e-5: the reference's own fp32 log-det on the
-    spline fixtures is only good to 2.1e-5 (|oracle32 - oracle64|, tools/flow_error_stats.py)."""
+    spline fixtures is only good to 2.1e-5 (|oracle32 - oracle64|, tests/measure/flow_error_stats.py)."""
     a = a.detach().float().cpu()
     scale = max(1.0, float(b.abs().mean()))
     torch.testing.assert_close(a, b, rtol=rtol, atol=atol_scale * scale, msg=lambda m: f"{what}: {m}")
@@ -34,7 +34,7 @@ def close_vs_oracle(a, sd, specs, x, inverse, what):
     """Parity against the oracle at the precision the reference itself has.
 
     The reference evaluates in fp32; on these stacks its own outputs differ from an exact (fp64)
-    evaluation of the same formulas by 1e-5 .. 1e-4 (measured: tools/flow_error_stats.py), so a
+    evaluation of the same formulas by 1e-5 .. 1e-4 (measured: tests/measure/flow_error_stats.py), so a
     bare rtol of 1e-5 against fp32 outputs is below the reference's noise floor.  The test
     therefore asks three things of the CUDA result `got`, with r32 / r64 the oracle in fp32 / fp64:
       (1) elementwise |got - r32| <= 1e-5*|r64| + 1e-5*scale + 4*|r32 - r64|  for >= 99.9% of elements

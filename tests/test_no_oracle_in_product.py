@@ -26,6 +26,23 @@ def test_product_never_references_the_oracle():
     assert not bad, f"product files referencing the oracle / reference checkout: {bad}"
 
 
+def test_only_tests_smoke_and_bench_cpu_legs_use_the_oracle():
+    """Outside tests/, the oracle may appear only in __graft_entry__.smoke() and in bench.py's CPU legs."""
+    bad = []
+    for base, dirs, files in os.walk(ROOT):
+        dirs[:] = [d for d in dirs if d not in (".git", "tests", "oracle", "gpurun_out", "__pycache__", "build", "baseline")]
+        for f in files:
+            path = os.path.join(base, f)
+            if not f.endswith(".py") or os.path.relpath(path, ROOT) in ("bench.py", "__graft_entry__.py"):
+                continue
+            if re.search(r"^\s*(from|import)\s+oracle\b", open(path).read(), flags=re.M):
+                bad.append(os.path.relpath(path, ROOT))
+    assert not bad, f"files outside tests/ importing the oracle: {bad}"
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    # every oracle import in bench.py sits inside a function of the CPU legs (no module-level import)
+    assert not re.search(r"^(from|import)\s+oracle\b", bench, flags=re.M)
+
+
 def test_missing_library_fails_loudly():
     code = (
         "import sys; sys.path.insert(0, %r)\n"
