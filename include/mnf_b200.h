@@ -151,8 +151,18 @@ int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 #define MNF_RUN_INVERSE 1
 #define MNF_RUN_GENERIC 2
 #define MNF_RUN_LOGPROB 4
+#define MNF_RUN_STAGED 8  /* `workspace` holds the image written by mnf_flow_stack_stage for these params (below) */
 #define MNF_RUN_VARIANT_MASK 0x70
 #define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2,3} */
+
+/* Small batches of a dim-2 stack spend most of their kernel time re-laying the conditioner nets out in every CTA's
+ * shared memory.  mnf_flow_stack_stage writes that layout ONCE (call it again whenever a parameter changes) into a
+ * caller-owned, 16-byte aligned buffer of mnf_flow_stack_stage_size() floats (0 = the program has no such form);
+ * mnf_flow_stack_run with MNF_RUN_STAGED and that buffer as `workspace` then starts with a plain vector copy.  Only for
+ * runs of fewer than 65 536 rows (larger runs of spline stacks use `workspace` for the constant-bank variant). */
+int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
+int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
+                         float *staged, void *stream);
 
 /* Which kernel mnf_flow_stack_run would pick: 0 = generic interpreter, 1 = specialised
  * D=2 register-resident kernel, 2 = the constant-bank MADE kernel (all-MAF/IAF stacks of the BASELINE

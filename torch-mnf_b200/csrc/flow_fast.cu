@@ -8,6 +8,9 @@ namespace mnf {
 int launch_fast_16_8(MNF_FLOW_FAST_ARGS);
 int launch_fast_24_8(MNF_FLOW_FAST_ARGS);
 int launch_fast_8_5(MNF_FLOW_FAST_ARGS);
+int stage_image_16_8(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
+int stage_image_24_8(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
+int stage_image_8_5(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
 
 // ---- host side: plan + launch ---------------------------------------------------------
 
@@ -144,6 +147,29 @@ static int launch_affine_stream(const FlowProgram &prog, const float *params, co
     return launch_status("affine_stream_kernel");
 }
 
+// Pre-staged shared-memory image of a program's conditioner nets (variant-2 layout): floats needed, 0 if the program
+// has no such form.  Small-batch calls spend most of their kernel time re-laying the nets out in every CTA; with the
+// image (built once per parameter change) the prologue is a plain vector copy.
+int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim) {
+    FastPlan p = plan_fast(ops, n_ops, dim, 2);
+    bool has_net = false;
+    for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
+    if (!p.ok || !has_net || (size_t)p.lay.total_slots * sizeof(float) > 227 * 1024) return 0;
+    return p.lay.total_slots;
+}
+
+int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream) {
+    FastPlan p = plan_fast(ops, n_ops, dim, 2);
+    MNF_REQUIRE(p.ok && flow_stage_size(ops, n_ops, dim) > 0, MNF_E_SHAPE, "program has no staged form");
+    MNF_REQUIRE(params && image && ((uintptr_t)image % 16) == 0, MNF_E_ARG, "NULL or misaligned pointer");
+    FlowProgram prog;
+    prog.n_ops = n_ops;
+    for (int k = 0; k < n_ops; ++k) prog.ops[k] = ops[k];
+    if (p.H == 16 && p.K == 8) return stage_image_16_8(prog, p.lay, params, image, stream);
+    if (p.H == 24 && p.K == 8) return stage_image_24_8(prog, p.lay, params, image, stream);
+    return stage_image_8_5(prog, p.lay, params, image, stream);
+}
+
 // returns 1 if the program is not eligible (caller falls back to the generic kernel)
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
@@ -159,6 +185,7 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     bool has_net = false;
     for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
     if (!has_net && mode == 3) mode = 2;
+    if (mode != 2) inverse &= ~4;  // a staged image (bit 2) is in the variant-2 layout; other variants use workspace differently
     FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
     if (mode == 3 && inter && (n_rows % 2)) return 1;
@@ -177,7 +204,7 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     prog.n_ops = n_ops;
     for (int k = 0; k < n_ops; ++k) prog.ops[k] = ops[k];
     (void)n_params;
-    if (!has_net && variant < 0 && !inter && workspace && n_rows % 2 == 0 && n_rows >= 2)
+    if (!has_net && variant < 0 && !inter && workspace && !(inverse & 4) && n_rows % 2 == 0 && n_rows >= 2)
         return launch_affine_stream(prog, params, x, y, log_det, base_lp, n_rows, inverse, workspace, dp, stream);
     if (p.H == 16 && p.K == 8)
         return launch_fast_16_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,

@@ -355,6 +355,30 @@ __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *
     }
 }
 
+// all nets of a program into an image laid out by `lay` (shared memory in the kernel, global memory when pre-staging)
+template <int H, int VARIANT>
+__device__ __forceinline__ void stage_program(const FlowProgram &prog, const FastLayout &lay,
+                                              const float *__restrict__ params, float *image) {
+    if constexpr (VARIANT == 2) {  // padding lanes of the last layers must read zeros
+        for (int e = threadIdx.x; e < lay.total_slots; e += blockDim.x) image[e] = 0.f;
+        __syncthreads();
+    }
+    for (int k = 0; k < prog.n_ops; ++k) {
+        const mnf_flow_op &op = prog.ops[k];
+        if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
+        for (int which = 0; which < 2; ++which) {
+            if (op.type == MNF_OP_AFFINE_HALF && !(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
+            stage_net<H, VARIANT>(params + op.net_off[which], image + lay.net_slot[k][which], op.sizes[op.n_lin]);
+        }
+    }
+}
+
+template <int H>
+__global__ void flow_stage_image_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant__ FastLayout lay,
+                                        const float *__restrict__ params, float *__restrict__ image) {
+    stage_program<H, 2>(prog, lay, params, image);
+}
+
 // everything that happens to one pair of points: load, all flows, store.
 // ONE: small-batch mode -- `pair` is a POINT index, the B lane of every float2 is a dead copy that the compiler removes
 // (nothing is stored from it), so a thread walks half the dependent FFMA2 chain and twice as many warps share the work.
@@ -474,21 +498,27 @@ __global__ void __launch_bounds__(128, 4)
 flow_fast_kernel(const __grid_constant__ FlowProgram prog, const __grid_constant__ FastLayout lay,
                  const float *__restrict__ params, const float *__restrict__ x, float *__restrict__ y,
                  float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
-                 long long n_rows, int dir_flags) {
+                 long long n_rows, int dir_flags, const float *__restrict__ staged) {
     extern __shared__ __align__(16) float smem[];
     const int inverse = dir_flags & 1;
     const bool sum_lp = dir_flags & 2;
-    if constexpr (VARIANT == 2) {  // padding lanes of the last layers must read zeros
-        for (int e = threadIdx.x; e < lay.total_slots; e += blockDim.x) smem[e] = 0.f;
-        __syncthreads();
-    }
-    for (int k = 0; k < prog.n_ops; ++k) {
-        const mnf_flow_op &op = prog.ops[k];
-        if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
-        for (int which = 0; which < 2; ++which) {
-            if (op.type == MNF_OP_AFFINE_HALF && !(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) continue;
-            stage_net<H, VARIANT>(params + op.net_off[which], smem + lay.net_slot[k][which], op.sizes[op.n_lin]);
+    if (staged != nullptr) {
+        // the shared-memory image was laid out once by flow_stage_image_kernel (mnf_flow_stack_stage): plain 16-byte
+        // copy, eight loads in flight per thread (total_slots is a multiple of 4)
+        const float4 *src = reinterpret_cast<const float4 *>(staged);
+        float4 *dst = reinterpret_cast<float4 *>(smem);
+        const int n4 = lay.total_slots >> 2;
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * blockDim.x < n4) v[u] = src[i0 + u * blockDim.x];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * blockDim.x < n4) dst[i0 + u * blockDim.x] = v[u];
         }
+    } else {
+        stage_program<H, VARIANT>(prog, lay, params, smem);
     }
     __syncthreads();
 
@@ -506,11 +536,11 @@ constexpr long long kOnePointMaxRows = 148LL * 128;
 template <int H, int K, int VARIANT, bool ONE = false>
 int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,
                 const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows,
-                int inverse, const DeviceProps *dp, cudaStream_t stream) {
+                int inverse, const DeviceProps *dp, cudaStream_t stream, const float *staged = nullptr) {
     if constexpr (VARIANT == 2 && !ONE) {
         if (n_rows <= kOnePointMaxRows)
             return launch_inst<H, K, 2, true>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse, dp,
-                                              stream);
+                                              stream, staged);
     }
     auto kern = flow_fast_kernel<H, K, VARIANT, ONE>;
     static thread_local int occ_cache = -1;
@@ -532,7 +562,7 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, threads, smem_bytes, stream>>>(prog, lay, params, x, y, log_det, base_lp, inter, n_rows,
-                                                            inverse);
+                                                            inverse & 3, VARIANT == 2 ? staged : nullptr);
     return launch_status("flow_fast_kernel");
 }
 
@@ -850,7 +880,12 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
             return launch_cbank<HH, KK>(prog, params, x, y, log_det, base_lp, inter, n_rows, inverse, workspace, \
                                         gather, stream);                                                        \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \
-                                      inverse, dp, stream);                                                     \
+                                      inverse, dp, stream, (inverse & 4) ? workspace : nullptr);                \
+    }                                                                                                           \
+    int stage_image_##HH##_##KK(const FlowProgram &prog, const FastLayout &lay, const float *params,            \
+                                float *image, cudaStream_t stream) {                                            \
+        flow_stage_image_kernel<HH><<<1, 256, 0, stream>>>(prog, lay, params, image);                           \
+        return launch_status("flow_stage_image_kernel");                                                        \
     }
 
 }  // namespace mnf

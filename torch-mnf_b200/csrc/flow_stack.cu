@@ -11,6 +11,8 @@ int launch_flow_generic(const mnf_flow_op *ops, int n_ops, const float *params, 
 int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int64_t n_params, const float *x,
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int mode, float *workspace, const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
+int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim);
+int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream);
 int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
                      float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
                      cudaStream_t stream, bool plan_only);
@@ -112,9 +114,11 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
     int rc = validate_program(ops_host, n_ops, dim, n_params);
     if (rc) return rc;
     MNF_REQUIRE(n_rows >= 0, MNF_E_ARG, "n_rows=%lld is negative", (long long)n_rows);
-    MNF_REQUIRE((flags & ~(MNF_RUN_INVERSE | MNF_RUN_GENERIC | MNF_RUN_LOGPROB | MNF_RUN_VARIANT_MASK)) == 0, MNF_E_ARG,
+    MNF_REQUIRE((flags & ~(MNF_RUN_INVERSE | MNF_RUN_GENERIC | MNF_RUN_LOGPROB | MNF_RUN_STAGED | MNF_RUN_VARIANT_MASK)) == 0, MNF_E_ARG,
                 "unknown bits in flags=0x%x", flags);
-    const int inverse = (flags & MNF_RUN_INVERSE) | ((flags & MNF_RUN_LOGPROB) ? 2 : 0);  // bit1: sum into base_lp
+    // bit1: sum into base_lp; bit2: workspace holds the pre-staged image (dim-2 shared-memory kernel only)
+    const int inverse = (flags & MNF_RUN_INVERSE) | ((flags & MNF_RUN_LOGPROB) ? 2 : 0) |
+                        ((flags & MNF_RUN_STAGED) && workspace && dim == 2 ? 4 : 0);
     const int variant = ((flags & MNF_RUN_VARIANT_MASK) >> 4) - 1;  // -1 = library default
     if (n_rows == 0) return 0;
     MNF_REQUIRE(x != nullptr, MNF_E_ARG, "x is NULL");
@@ -134,7 +138,19 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
     MNF_REQUIRE(!gather || (gather->n_peers == 0 && !gather->multicast_ptr), MNF_E_SHAPE,
                 "peer-memory gather output needs the constant-bank dim-2 kernel (spline stack, >= 65536 rows)");
     return launch_flow_generic(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
-                               n_rows, dim, inverse, st);
+                               n_rows, dim, inverse & 3, st);
+}
+
+int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params) {
+    if (validate_program(ops_host, n_ops, dim, n_params)) return 0;
+    return flow_stage_size(ops_host, n_ops, dim);
+}
+
+int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
+                         float *staged, void *stream) {
+    int rc = validate_program(ops_host, n_ops, dim, n_params);
+    if (rc) return rc;
+    return flow_stage_image(ops_host, n_ops, params, dim, staged, (cudaStream_t)stream);
 }
 
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim) {

@@ -22,7 +22,7 @@ MAX_OPS, MAX_LIN, MAX_DIM, MAX_HIDDEN, MAX_BINS = 32, 6, 64, 128, 32
 
 OP_AFFINE_CONST, OP_GLOW, OP_AFFINE_HALF, OP_NSF_CL, OP_NSF_AR, OP_MADE = 1, 2, 3, 4, 5, 6
 FLAG_PARITY, FLAG_SCALE, FLAG_SHIFT, FLAG_MADE_SEQ = 1, 2, 4, 8
-RUN_INVERSE, RUN_GENERIC, RUN_LOGPROB = 1, 2, 4
+RUN_INVERSE, RUN_GENERIC, RUN_LOGPROB, RUN_STAGED = 1, 2, 4, 8
 
 launch_count = 0  # kernels launched through this binding (bench.py reports it)
 
@@ -68,6 +68,8 @@ _SIGS = {
         [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
          C.c_int64, C.c_int, C.c_int, C.c_void_p],
     ),
+    "mnf_flow_stack_stage_size": (C.c_int64, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
+    "mnf_flow_stack_stage": (C.c_int, [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, C.c_int, _f32p, C.c_void_p]),
     "mnf_flow_stack_workspace": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "mnf_flow_stack_plan": (C.c_int, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
     "mnf_glow_assemble": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p]),

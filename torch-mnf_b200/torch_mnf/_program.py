@@ -192,7 +192,27 @@ class FlowProgram:
         self._ops = (_lib.FlowOp * max(len(ops), 1))(*ops)
         self._n_ops = len(ops)
         self._blob = blob
+        self._staged = {}  # dim -> pre-staged shared-memory image of the nets (or False), rebuilt with the blob
         self._key = key
+
+    STAGED_MAX_ROWS = (1 << 16) - 1  # above this the dim-2 spline stacks switch to the constant-bank variant
+
+    def _staged_image(self, lib, n_rows, dim, kernel):
+        """Pre-staged net image for small dim-2 batches (mnf_flow_stack_stage), cached until a parameter changes."""
+        if dim != 2 or n_rows > self.STAGED_MAX_ROWS or kernel not in (None, 2) or not 0 < self._n_ops <= _lib.MAX_OPS:
+            return None
+        img = self._staged.get(dim)
+        if img is None:
+            size = lib.mnf_flow_stack_stage_size(self._ops, self._n_ops, dim, self._blob.numel())
+            img = False
+            if size > 0:
+                img = torch.empty(size, device=self._blob.device, dtype=torch.float32)
+                with torch.cuda.device(self._blob.device):
+                    rc = lib.mnf_flow_stack_stage(self._ops, self._n_ops, self._blob.data_ptr(), self._blob.numel(), dim,
+                                                  img.data_ptr(), _lib.stream_ptr(self._blob.device))
+                _lib.check(rc, "mnf_flow_stack_stage")
+            self._staged[dim] = img
+        return img if img is not False else None
 
     @staticmethod
     def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False):
@@ -249,7 +269,11 @@ class FlowProgram:
                 flags |= _lib.RUN_GENERIC
             elif kernel is not None:
                 flags |= ((int(kernel) + 1) << 4) & 0x70
-            ws = self._workspace(lib, n, B, D, dev)
+            ws = self._staged_image(lib, B, D, kernel)
+            if ws is not None:
+                flags |= _lib.RUN_STAGED
+            else:
+                ws = self._workspace(lib, n, B, D, dev)
             with torch.cuda.device(dev):
                 rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
                                             None, None, lp.data_ptr(), None, B, D, flags, _lib.ptr(ws),
@@ -271,6 +295,9 @@ class FlowProgram:
             flags |= _lib.RUN_GENERIC
         elif kernel is not None:
             flags |= ((int(kernel) + 1) << 4) & 0x70
+        staged = self._staged_image(lib, B, D, kernel)
+        if staged is not None:
+            ws, flags = staged, flags | _lib.RUN_STAGED
         with torch.cuda.device(dev):
             # stacks longer than MNF_MAX_OPS run in chunks, log-dets summed across chunks
             done, src, first = 0, x, True
