@@ -104,3 +104,61 @@ def test_shard_range_covers_rows_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_differentiable_blob_matches_cached_layout_and_reaches_parameters():
+    """Training path: the blob handed to mnf_flow_stack_backward is an autograd function of the nn.Parameters with the
+    SAME layout as the cached inference blob (MADE masks applied by torch), so d loss / d blob lands on them."""
+    from torch_mnf._program import FlowProgram, ParamPacker
+
+    flows = [build_flow({"type": "MAF", "dim": 8, "parity": True, "h_sizes": [16, 16]}),
+             build_flow({"type": "NSF_CL", "dim": 8, "K": 5, "B": 3, "n_h": 8}),
+             build_flow({"type": "AffineConstantFlow", "dim": 8, "scale": True, "shift": False})]
+    prog = FlowProgram(flows)
+    prog._build(torch.device("cpu"))
+    with torch.enable_grad():  # the suite's default is inference mode (tests/conftest.py)
+        pk = ParamPacker(torch.device("cpu"), differentiable=True)
+        ops = [f._emit(pk) for f in flows]
+        blob = pk.finish()
+        assert blob.requires_grad and torch.equal(blob.detach(), prog._blob)
+        assert [o.net_off[0] for o in ops] == [prog._ops[k].net_off[0] for k in range(3)]
+        w = torch.arange(blob.numel(), dtype=torch.float32)
+        (blob * w).sum().backward()
+        assert prog.needs_grad(torch.zeros(2, 8))
+    lin0 = flows[0].net[0]
+    off = ops[0].net_off[0]
+    expect = w[off: off + 16 * 8].view(16, 8) * lin0.mask.float().T  # masked entries receive no gradient
+    assert torch.equal(lin0.weight.grad, expect)
+    assert flows[2].s.grad is not None and flows[1].f1[0].weight.grad is not None
+    with torch.no_grad():
+        assert not prog.needs_grad(torch.zeros(2, 8))
+
+
+def test_glow_torch_assembly_matches_oracle():
+    """Glow's differentiable assembly (training path) == the oracle's W, and its inverse / log-det are consistent."""
+    g = load_golden("nsfcl3_stack")
+    sd = golden_sd(g)
+    glow = build_flow({"type": "Glow", "dim": 2})
+    glow.load_state_dict({k[len("flows.1."):]: v for k, v in sd.items() if k.startswith("flows.1.") and not k.endswith(".P")})
+    glow.P.copy_(sd["flows.1.P"])
+    with torch.enable_grad():
+        out = glow._assemble_torch()
+    W = flows_cpu.glow_W(flows_cpu.sub(sd, "flows.1."))
+    torch.testing.assert_close(out[:4].detach().view(2, 2), W, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(out[4:8].detach().view(2, 2) @ W, torch.eye(2), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out[8].detach(), torch.log(torch.abs(sd["flows.1.S"])).sum(), rtol=1e-6, atol=1e-7)
+    with torch.enable_grad():
+        out.sum().backward()
+    assert all(p.grad is not None for p in (glow.L, glow.S, glow.U))
+
+
+def test_sync_actnorm_init_single_process():
+    import torch_mnf.flows as nf
+    from torch_mnf.distributed import sync_actnorm_init
+
+    model = nf.NormalizingFlow([nf.ActNormFlow(3), nf.Glow(3)])
+    called = []
+    assert sync_actnorm_init(model, init_fn=lambda m: called.append(1)) == 1
+    assert called == [1] and model.flows[0].data_dep_init_done
+    assert sync_actnorm_init(model, init_fn=lambda m: called.append(2)) == 1 and called == [1]  # already initialised
+    assert sync_actnorm_init(nf.NormalizingFlow([nf.Glow(3)])) == 0
