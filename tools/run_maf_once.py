@@ -13,7 +13,8 @@ for f in model.flows:
     f.precision = os.environ.get("PREC", "fp32")
 n = int(os.environ.get("N", 1 << 20))
 x = torch.randn(n, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+sampling = os.environ.get("DIR", "inverse") == "forward"  # forward = the 64-pass sampling direction
 for _ in range(int(os.environ.get("ITERS", 2))):
-    zs, ld = model.inverse(x)
+    zs, ld = model.forward(x) if sampling else model.inverse(x)
 torch.cuda.synchronize()
 print("done", float(ld.mean()))

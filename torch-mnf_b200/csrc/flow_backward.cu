@@ -517,7 +517,7 @@ __device__ void bw_made(const mnf_flow_op &op, const float *P, float *G, const f
     }
 }
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 flow_backward_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
                      float *gparams, const float *__restrict__ x, const float *__restrict__ inter,
                      const float *__restrict__ gy, const float *__restrict__ gld, const float *__restrict__ ginter,
@@ -601,10 +601,14 @@ int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float 
     const int in_smem = smem <= 96 * 1024;
     if (in_smem && smem > 48 * 1024)
         MNF_CUDA(cudaFuncSetAttribute(flow_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = (n_rows + 63) / 64;
-    const long long cap = (long long)dp->sm_count * 4;  // few, long-lived blocks: one gradient flush each
+    // the kernel is latency-bound (local-memory scratch, shuffles): 8 blocks x 4 warps per SM where the per-block gradient
+    // copy allows it (ncu at 2 warps x 4 blocks: issue slots 15 % busy, profiles/r01_flow_backward_ncu_full.md)
+    long long blocks = (n_rows + 127) / 128;
+    long long per_sm = in_smem ? (long long)(200 * 1024 / (smem > 0 ? smem : 1)) : 8;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const long long cap = (long long)dp->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
-    flow_backward_kernel<<<(unsigned)blocks, 64, in_smem ? smem : 0, (cudaStream_t)stream>>>(
+    flow_backward_kernel<<<(unsigned)blocks, 128, in_smem ? smem : 0, (cudaStream_t)stream>>>(
         prog, params, grad_params, x, intermediates, grad_y, grad_log_det, grad_intermediates, grad_x, n_rows, dim, inverse,
         (int)n_params, in_smem);
     return launch_status("flow_backward_kernel");
