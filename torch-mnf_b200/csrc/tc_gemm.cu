@@ -60,20 +60,6 @@ struct Epilogue {
     const float *ld_in;  // optional running log-det
     float *ld_out;
     int parity;
-    // mode 4 (RNVP gate, rnvp.py:32-39): columns interleaved (shift_0, scale_0, shift_1, scale_1, ...), N = 2*dim;
-    // bias interleaved likewise.  z is updated in place, (1-mask)*log(gate) is summed into ld_acc with one
-    // atomicAdd per row and tile.  Optional extra outputs feed the next GEMM without another pass over z:
-    // mz_next = tf32(mask_next * z_new) (next flow's conditioner input), xz_out = tf32(x[m % x_rows] * z_new)
-    // (A operand of the MNFLinear mean GEMM).
-    float *z;
-    float *ld_acc;
-    const float *mask;  // injected [M, dim] or nullptr -> Philox bits (noise_stream)
-    float *mz_next;
-    const float *mask_next;
-    uint32_t next_stream;
-    const float *xmul;
-    int xmul_rows;
-    float *xz_out;
     // mode 5 (MNFConv2d tail on an im2col GEMM whose rows are pool-major): v = acc + sd[m, n] * eps, ReLU, max over
     // the 4 consecutive rows of a 2x2 window (4 adjacent TMEM lanes -> two shuffles), out[r, n, py, px].
     // sd: [M, N] (row stride N); eps indexed like the un-pooled [R, conv_c, conv_oh, conv_ow] tensor.
@@ -342,77 +328,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
                         if (q == 0 && m < M && n < Cc) ep.out[((rr * Cc + n) * PH + py) * PW + px] = v;
                     }
-                } else if (ep.mode == 4) {
-                    if (m < M) {
-                        const int D = N >> 1, j0 = n0 >> 1;  // this chunk = 16 consecutive dims of row m
-                        const size_t e0 = (size_t)m * D + j0;
-                        float zin[16], bs[32], mk[16];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = *reinterpret_cast<const float4 *>(ep.z + e0 + 4 * q);
-                            zin[4 * q] = v.x, zin[4 * q + 1] = v.y, zin[4 * q + 2] = v.z, zin[4 * q + 3] = v.w;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 v = *reinterpret_cast<const float4 *>(ep.bias + n0 + 4 * q);
-                            bs[4 * q] = v.x, bs[4 * q + 1] = v.y, bs[4 * q + 2] = v.z, bs[4 * q + 3] = v.w;
-                        }
-                        const uint64_t g0 = (uint64_t)ep.row_offset * D + e0;
-                        if (ep.mask) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 v = *reinterpret_cast<const float4 *>(ep.mask + e0 + 4 * q);
-                                mk[4 * q] = v.x, mk[4 * q + 1] = v.y, mk[4 * q + 2] = v.z, mk[4 * q + 3] = v.w;
-                            }
-                        } else {
-                            const uint32_t bits = philox_bits16(rng, g0, ep.noise_stream);
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) mk[u] = (float)((bits >> u) & 1u);
-                        }
-                        float zn[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const float shift = __uint_as_float(r[2 * u]) + bs[2 * u];
-                            const float scale = __uint_as_float(r[2 * u + 1]) + bs[2 * u + 1];
-                            const float gate = __fdividef(1.f, 1.f + __expf(-scale));  // torch.sigmoid, rnvp.py:35
-                            const float z1 = (1.f - mk[u]) * zin[u], z2 = mk[u] * zin[u];
-                            zn[u] = (z1 * gate + (1.f - gate) * shift) + z2;  // rnvp.py:37
-                            s_sum += (1.f - mk[u]) * __logf(gate);           // rnvp.py:36
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4 *>(ep.z + e0 + 4 * q) =
-                                make_float4(zn[4 * q], zn[4 * q + 1], zn[4 * q + 2], zn[4 * q + 3]);
-                        if (ep.mz_next) {
-                            float mn[16];
-                            if (ep.mask_next) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float4 v = *reinterpret_cast<const float4 *>(ep.mask_next + e0 + 4 * q);
-                                    mn[4 * q] = v.x, mn[4 * q + 1] = v.y, mn[4 * q + 2] = v.z, mn[4 * q + 3] = v.w;
-                                }
-                            } else {
-                                const uint32_t bits = philox_bits16(rng, g0, ep.next_stream);
-#pragma unroll
-                                for (int u = 0; u < 16; ++u) mn[u] = (float)((bits >> u) & 1u);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<float4 *>(ep.mz_next + e0 + 4 * q) =
-                                    make_float4(rn_tf32(mn[4 * q] * zn[4 * q]), rn_tf32(mn[4 * q + 1] * zn[4 * q + 1]),
-                                                rn_tf32(mn[4 * q + 2] * zn[4 * q + 2]), rn_tf32(mn[4 * q + 3] * zn[4 * q + 3]));
-                        }
-                        if (ep.xz_out) {
-                            const float *xr = ep.xmul + (size_t)(m % ep.xmul_rows) * D + j0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 xv = *reinterpret_cast<const float4 *>(xr + 4 * q);
-                                *reinterpret_cast<float4 *>(ep.xz_out + e0 + 4 * q) =
-                                    make_float4(rn_tf32(xv.x * zn[4 * q]), rn_tf32(xv.y * zn[4 * q + 1]),
-                                                rn_tf32(xv.z * zn[4 * q + 2]), rn_tf32(xv.w * zn[4 * q + 3]));
-                            }
-                        }
-                    }
                 } else if (m < M && n0 + 32 <= N && (N & 3) == 0) {
                     // fast path: whole 32-column chunk in range.  All global operands of the chunk are fetched
                     // with independent float4 loads BEFORE any arithmetic, so the epilogue pays one memory
@@ -498,7 +413,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
             if (ep.mode == 3 && m < M) atomicAdd(&ep.ld_out[m], s_sum);  // maf.py:61 (ld_out pre-initialised by the host)
-            if (ep.mode == 4 && m < M) atomicAdd(&ep.ld_acc[m], s_sum);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty(acc));
             if (++acc == ACC_STAGES) {
