@@ -274,7 +274,7 @@ class FlowProgram:
                 flags |= _lib.RUN_STAGED
             else:
                 ws = self._workspace(lib, n, B, D, dev)
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
                                             None, None, lp.data_ptr(), None, B, D, flags, _lib.ptr(ws),
                                             C.byref(gather) if gather is not None else None, _lib.stream_ptr(dev))
