@@ -360,6 +360,8 @@ enum mnf_ew_op {
     MNF_EW_MUL_COLVEC = 12,/* out = a b[row]                       (W_mean * z.view(-1,1,1,1), mnf_conv.py:73) */
     MNF_EW_ADD_2MUL = 13,  /* out = a + 2 b c                      d/dx of the x^2 branch added to the x branch */
     MNF_EW_ADD_COLVEC = 14,/* out = a + b[row]                     (conv bias in the [c_out, pixels] GEMM layout) */
+    MNF_EW_RELU = 15,      /* out = max(a, 0)                      (nn.ReLU between MaskedLinears, made.py:43)      */
+    MNF_EW_RELU_BWD = 16,  /* out = b > 0 ? a : 0                  a = gradient, b = pre-activation                 */
 };
 /* n elements; operands not used by `op` may be NULL; [col] operands are vectors of ncols entries. */
 int mnf_ew(int op, const float *a, const float *b, const float *c, const float *d, float *out, float *out2, int64_t n,

@@ -6,8 +6,6 @@ import os
 import numpy as np
 import torch
 
-from oracle.noise import NoiseTape
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -25,6 +23,8 @@ def golden_spec(npz):
 
 
 def golden_tape(npz, prefix):
+    from oracle.noise import NoiseTape  # lazy: bench.py's product arm imports this module for the model builders only
+
     return NoiseTape.from_npz(npz, prefix)
 
 

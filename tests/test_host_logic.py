@@ -162,3 +162,129 @@ def test_sync_actnorm_init_single_process():
     assert called == [1] and model.flows[0].data_dep_init_done
     assert sync_actnorm_init(model, init_fn=lambda m: called.append(2)) == 1 and called == [1]  # already initialised
     assert sync_actnorm_init(nf.NormalizingFlow([nf.Glow(3)])) == 0
+
+
+# ---------------------------------------------------------------------------------------
+# cache hygiene: launch caches must neither break copy/pickle nor survive parameter changes
+# ---------------------------------------------------------------------------------------
+def test_modules_deepcopy_and_pickle_with_populated_caches():
+    """After a call the modules hold ctypes descriptors with raw pointers (RnvpFlow structs, MADE plans, flow
+    programs).  ctypes objects with pointers cannot be pickled, so the caches must be dropped by __getstate__ --
+    the reference's modules copy and pickle fine (EMA copies, torch.save(model))."""
+    import copy
+    import ctypes
+    import io
+    import pickle
+
+    import torch_mnf.flows as nf
+    from torch_mnf._program import FlowProgram
+    from torch_mnf.layers import MNFLinear
+    from torch_mnf.layers._mnf_ops import RnvpFlow
+    from torch_mnf.layers.made import MadeLayer
+
+    with pytest.raises(ValueError):  # the failure mode being guarded against
+        pickle.dumps(RnvpFlow())
+    layer = MNFLinear(8, 4)
+    for f in list(layer.flow_q.flows) + list(layer.flow_r.flows):
+        f.__dict__["_rnvp_struct_cache"] = (("cuda:0", (1, 2)), RnvpFlow(), 50)
+    layer.__dict__["_last_kl_terms"] = torch.zeros(5)
+    stack = nf.NormalizingFlowModel(torch.distributions.MultivariateNormal(torch.zeros(4), torch.eye(4)),
+                                    [nf.MAF(4, parity=bool(i % 2), h_sizes=(8, 8)) for i in range(2)])
+    stack.__dict__["_prog"] = FlowProgram(list(stack.flows))
+    stack.__dict__["_tc_plan"] = (True, (MadeLayer * 1)(MadeLayer()))
+    stack.flows[0].__dict__["_tc_plan"] = (MadeLayer * 1)(MadeLayer())
+    stack.flows[0].__dict__["_single_prog"] = FlowProgram([stack.flows[0]])
+    for m in (layer, stack):
+        c = copy.deepcopy(m)
+        assert set(c.state_dict()) == set(m.state_dict())
+        for k, v in m.state_dict().items():
+            assert torch.equal(c.state_dict()[k], v)
+        buf = io.BytesIO()
+        torch.save(m, buf)
+        buf.seek(0)
+        r = torch.load(buf, weights_only=False)
+        assert set(r.state_dict()) == set(m.state_dict())
+        for mod in c.modules():
+            assert not any(isinstance(v, (ctypes.Structure, ctypes.Array)) for v in mod.__dict__.values())
+    assert stack.__dict__["_prog"] is not None  # the original keeps its caches
+    assert copy.deepcopy(stack)._program() is not stack._program()
+
+
+def test_flow_program_key_sees_every_kind_of_parameter_change():
+    """(versions, all data pointers, per-flow salt, parameter epoch): in-place updates, `p.data = ...` on ANY tensor,
+    load_state_dict(assign=True), Module.to() and CUDA-graph replays all invalidate the packed blob."""
+    import torch_mnf.flows as nf
+    from torch_mnf import _program
+    from torch_mnf._program import FlowProgram, _state_key
+
+    flows = [nf.AffineHalfFlow(2, parity=bool(i % 2), h_sizes=(4, 4)) for i in range(3)]
+    prog = FlowProgram(flows)
+    dev = torch.device("cpu")
+
+    def key():
+        k = _state_key(prog.flows, dev, prog._tensors)
+        if k != getattr(key, "last", None):  # what FlowProgram._build does on a mismatch
+            prog._refresh_tensors()
+            k = _state_key(prog.flows, dev, prog._tensors)
+        key.last = k
+        return k
+
+    k0 = key()
+    assert key() == k0
+    with torch.no_grad():
+        flows[1].s_net[2].weight.add_(1.0)  # in-place: version counter
+    k1 = key()
+    assert k1 != k0
+    mid = flows[1].t_net[2].weight  # neither the first nor the last tensor of the program
+    v = mid._version
+    mid.data = mid.data.clone()
+    assert mid._version == v
+    k2 = key()
+    assert k2 != k1
+    sd = {k: v.clone() + 1 for k, v in flows[2].state_dict().items()}
+    old = flows[2].s_net[0].weight
+    flows[2].load_state_dict(sd, assign=True)
+    assert flows[2].s_net[0].weight is not old
+    k3 = key()
+    assert k3 != k2
+    assert any(t is flows[2].s_net[0].weight for t in prog._tensors)  # the list was re-read from the modules
+    flows[0].requires_grad_(False), flows[1].requires_grad_(False), flows[2].requires_grad_(False)
+    with torch.enable_grad():
+        assert not prog.needs_grad(torch.zeros(1, 2))
+    flows[0].double().float()  # Module._apply
+    k4 = key()
+    assert k4 != k3
+    _program.bump_param_epoch()
+    assert key() != k4
+
+
+def test_made_plan_key_sees_pointer_changes_and_epoch():
+    import torch_mnf.flows as nf
+    from torch_mnf import _program
+    from torch_mnf.layers.made import MadeStackPlan
+
+    f = nf.MAF(8, parity=False, h_sizes=(8, 8))
+    plan = MadeStackPlan([f])
+
+    def key():
+        ts = plan._tensors()
+        return (tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts), _program.param_epoch())
+
+    k0 = key()
+    w = f.net[2].weight
+    w.data = w.data.clone()
+    assert key() != k0
+    k1 = key()
+    _program.bump_param_epoch()
+    assert key() != k1
+
+
+def test_non_default_leaky_slope_is_rejected_not_ignored():
+    import torch_mnf.flows as nf
+    from torch_mnf._program import ParamPacker
+    from torch_mnf.models import MLP
+
+    f = nf.NSF_CL(2, K=4, B=3, n_h=4, net_class=lambda *s: MLP(*s, leaky_a=0.1))
+    with pytest.raises(NotImplementedError, match="leaky_a"):
+        f._emit(ParamPacker(torch.device("cpu")))
+    nf.NSF_CL(2, K=4, B=3, n_h=4)._emit(ParamPacker(torch.device("cpu")))

@@ -91,6 +91,8 @@ __global__ void ew_kernel(int op, const float *__restrict__ a, const float *__re
             case MNF_EW_MUL_COLVEC: out[i] = a[i] * b[i / ncols]; break;              // per-row scale (W_mean * z[c_out])
             case MNF_EW_ADD_2MUL: out[i] = fmaf(2.f * b[i], c[i], a[i]); break;       // a + 2 b c
             case MNF_EW_ADD_COLVEC: out[i] = a[i] + b[i / ncols]; break;              // per-row bias
+            case MNF_EW_RELU: out[i] = fmaxf(a[i], 0.f); break;                       // nn.ReLU between MaskedLinears
+            case MNF_EW_RELU_BWD: out[i] = b[i] > 0.f ? a[i] : 0.f; break;            // a = grad, b = pre-activation
             default: break;
         }
     }
@@ -280,7 +282,7 @@ int mnf_gemm_f32(int trans_a, int trans_b, int64_t M, int N, int K, const float 
 
 int mnf_ew(int op, const float *a, const float *b, const float *c, const float *d, float *out, float *out2, int64_t n,
            int ncols, void *stream) {
-    MNF_REQUIRE(op >= MNF_EW_MUL && op <= MNF_EW_ADD_COLVEC, MNF_E_ARG, "unknown elementwise op %d", op);
+    MNF_REQUIRE(op >= MNF_EW_MUL && op <= MNF_EW_RELU_BWD, MNF_E_ARG, "unknown elementwise op %d", op);
     MNF_REQUIRE(a && out && n >= 0 && ncols >= 1, MNF_E_ARG, "bad argument");
     if (n == 0) return 0;
     ew_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(op, a, b, c, d, out, out2, n, ncols);

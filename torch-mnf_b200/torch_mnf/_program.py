@@ -81,6 +81,15 @@ def net_tensors(linears, masks=None):
     return out
 
 
+def check_leaky(*nets):
+    """The kernels evaluate conditioner MLPs with the reference's LeakyReLU slope (models/mlp.py:4: leaky_a=0.2)."""
+    for net in nets:
+        a = getattr(net, "leaky_a", 0.2) if net is not None else 0.2
+        if a != 0.2:
+            raise NotImplementedError(
+                f"conditioner MLP with leaky_a={a}: the CUDA kernels implement LeakyReLU(0.2) only (models/mlp.py:4)")
+
+
 def new_op(type_, flags=0, K=0, bound=0.0, sizes=(), net_off=(0, 0), aux_off=0, edge_deriv=0.0):
     if len(sizes) - 1 > _lib.MAX_LIN:
         raise ValueError(f"conditioner has {len(sizes) - 1} Linear layers; at most {_lib.MAX_LIN} supported")
@@ -110,14 +119,41 @@ def _tensors_of(flows):
     return out
 
 
+#: bumped by anything that rewrites parameters behind autograd's back without touching ``_version`` (CUDA-graph replays
+#: of a captured optimizer step, torch_mnf.graphs): every cached blob / plan / descriptor includes it in its key
+_param_epoch = 0
+
+
+def bump_param_epoch() -> None:
+    global _param_epoch
+    _param_epoch += 1
+
+
+def param_epoch() -> int:
+    return _param_epoch
+
+
+_data_ptr_of = __import__("operator").methodcaller("data_ptr")
+
+#: per-module caches that hold ctypes descriptors / device blobs: never copied or pickled with the module
+CACHE_KEYS = ("_prog", "_single_prog", "_tc_plan", "_fused_plan", "_rnvp_struct_cache", "_std_base", "_last_kl_terms",
+              "_kl_plan")
+
+
+def state_without_caches(module):
+    """``__getstate__`` of the drop-in modules: the module's ``__dict__`` minus the launch caches (ctypes structs with
+    raw device pointers cannot be pickled or deep-copied; the reference's modules can, so ours must too)."""
+    return {k: v for k, v in module.__dict__.items() if k not in CACHE_KEYS}
+
+
 def _state_key(flows, device, tensors):
-    """Cheap per-call fingerprint of everything the packed blob depends on: in-place updates bump
-    ``_version``; re-assigned storage (``.to()``, ``.data = ...``) shows in the data pointers; kernels
-    that write parameters behind autograd's back (ActNorm init) bump ``_program_salt``."""
+    """Per-call fingerprint of everything the packed blob depends on: in-place updates bump ``_version``;
+    re-assigned storage (``.to()``, ``p.data = ...``, ``load_state_dict(assign=True)``) shows in the data pointers of
+    EVERY tensor; kernels that write parameters behind autograd's back bump ``_program_salt`` (ActNorm init) or the
+    global parameter epoch (CUDA-graph replays of an optimizer step)."""
     return (
-        str(device), tuple(map(_version_of, tensors)),
-        tensors[0].data_ptr() if tensors else 0, tensors[-1].data_ptr() if tensors else 0,
-        tuple(f.__dict__.get("_program_salt", 0) for f in flows),
+        str(device), tuple(map(_version_of, tensors)), tuple(map(_data_ptr_of, tensors)),
+        tuple(f.__dict__.get("_program_salt", 0) for f in flows), _param_epoch,
     )
 
 
@@ -171,7 +207,7 @@ class FlowProgram:
 
     def __init__(self, flows):
         self.flows = list(flows)
-        self._tensors = _tensors_of(self.flows)
+        self._refresh_tensors()
         self._key = None
         self._ops = None
         self._blob = None
@@ -183,7 +219,10 @@ class FlowProgram:
         key = _state_key(self.flows, device, self._tensors)
         if key == self._key:
             return
-        self._tensors = _tensors_of(self.flows)  # buffers are re-created by Module.to(): refresh
+        # something changed: re-enumerate (Module.to() re-creates buffers, load_state_dict(assign=True) replaces the
+        # Parameter objects -- both bump the flows' _program_salt through the hooks in flows/_base.py, so the stale
+        # list can never produce a matching key)
+        self._refresh_tensors()
         key = _state_key(self.flows, device, self._tensors)
         pk = ParamPacker(device)
         ops = [f._emit(pk) for f in self.flows]
@@ -227,8 +266,18 @@ class FlowProgram:
         n = min(self._n_ops, _lib.MAX_OPS)
         return _lib.lib().mnf_flow_stack_plan(self._ops, n, dim, self._blob.numel())
 
+    def _refresh_tensors(self):
+        self._tensors = _tensors_of(self.flows)
+        self._salts = tuple(f.__dict__.get("_program_salt", 0) for f in self.flows)
+
     def needs_grad(self, x) -> bool:
-        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._tensors))
+        if not torch.is_grad_enabled():
+            return False
+        if x.requires_grad:
+            return True
+        if self._salts != tuple(f.__dict__.get("_program_salt", 0) for f in self.flows):
+            self._refresh_tensors()  # parameters were replaced (load_state_dict(assign=True), .to()): re-read flags
+        return any(p.requires_grad for p in self._tensors)
 
     def run_autograd(self, x, inverse: bool):
         """(log_det [B], outputs of every flow [n_ops, B, D]) with the autograd graph attached

@@ -4,7 +4,11 @@ from __future__ import annotations
 
 from torch import nn
 
-from .._program import FlowProgram
+from .._program import FlowProgram, state_without_caches
+
+
+def _bump_salt(module, *_):
+    module.__dict__["_program_salt"] = module.__dict__.get("_program_salt", 0) + 1
 
 
 class Flow(nn.Module):
@@ -13,6 +17,19 @@ class Flow(nn.Module):
     ``forward(z) -> (x, log_det)`` and ``inverse(x) -> (z, log_det)`` run a one-op program;
     inside a ``NormalizingFlow`` the container fuses all ops into a single launch instead.
     """
+
+    def __init__(self) -> None:
+        super().__init__()
+        # load_state_dict(assign=True) swaps the Parameter objects without touching version counters or the old
+        # tensors' storage: invalidate every cached program that packed this flow's parameters
+        self.register_load_state_dict_post_hook(_bump_salt)
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): buffers (MADE masks, Glow.P) are re-created
+        out = super()._apply(fn, *args, **kwargs)
+        _bump_salt(self)
+        return out
+
+    __getstate__ = state_without_caches  # copy.deepcopy / pickle / torch.save(model) drop the launch caches
 
     def _emit(self, pk):  # -> _lib.FlowOp
         raise NotImplementedError

@@ -5,7 +5,7 @@ from __future__ import annotations
 from collections.abc import Sequence
 
 from .. import _lib
-from .._program import net_tensors, new_op
+from .._program import check_leaky, net_tensors, new_op
 from ..models.mlp import MLP
 from ._base import Flow
 
@@ -25,6 +25,7 @@ class AffineHalfFlow(Flow):
         self._sizes = (dim // 2, *h_sizes, dim // 2)
 
     def _emit(self, pk):
+        check_leaky(self.s_net, self.t_net)
         flags = _lib.FLAG_PARITY if self.parity else 0
         offs = [0, 0]
         for i, (net, flag) in enumerate(((self.s_net, _lib.FLAG_SCALE), (self.t_net, _lib.FLAG_SHIFT))):

@@ -10,7 +10,7 @@ from torch import Tensor, nn
 from torch.distributions import Distribution, Independent, MultivariateNormal, Normal
 
 from .. import _lib
-from .._program import FlowProgram
+from .._program import FlowProgram, state_without_caches
 from ._base import Flow
 
 
@@ -32,6 +32,8 @@ class NormalizingFlow(nn.Module):
         self.flows = nn.ModuleList(flows)
         self.return_intermediates = return_intermediates
         self.__dict__["_prog"] = None
+
+    __getstate__ = state_without_caches  # copy.deepcopy / pickle drop the launch caches (ctypes descriptors)
 
     def _program(self) -> FlowProgram:
         prog = self.__dict__.get("_prog")
@@ -150,7 +152,7 @@ class NormalizingFlowModel(NormalizingFlow):
         self.__dict__["_std_base"] = {}
 
     def _base_is_std(self, dim):
-        cache = self.__dict__["_std_base"]
+        cache = self.__dict__.setdefault("_std_base", {})
         if dim not in cache:
             cache[dim] = _is_std_normal(self.base, dim)
         return cache[dim]

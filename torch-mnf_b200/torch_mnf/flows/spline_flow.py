@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from .._program import net_tensors, new_op, spline_edge_derivative
+from .._program import check_leaky, net_tensors, new_op, spline_edge_derivative
 from ..models.mlp import MLP
 from ._base import Flow
 
@@ -24,6 +24,7 @@ class NSF_CL(Flow):
         self.f2 = net_class(dim // 2, n_h, n_h, n_h, n_out)
 
     def _emit(self, pk):
+        check_leaky(self.f1, self.f2)
         lin1, lin2 = self.f1.linears(), self.f2.linears()
         sizes = [lin1[0].in_features] + [m.out_features for m in lin1]
         offs = (pk.add(*net_tensors(lin1)), pk.add(*net_tensors(lin2)))
@@ -49,6 +50,7 @@ class NSF_AR(Flow):
         nn.init.uniform_(self.init_param, -1 / 2, 1 / 2)
 
     def _emit(self, pk):
+        check_leaky(*self.layers)
         aux = pk.add(self.init_param)
         sizes, off = [1, 3 * self.K - 1], 0  # dim == 1: no conditioner, descriptor unused
         if len(self.layers):

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import torch
 
+from ._program import bump_param_epoch
+
 
 def graphed_training_step(model, loss_fn, optimizer, example_inputs, warmup: int = 3):
     """Returns ``step(*inputs) -> loss`` that replays one captured ``loss_fn(model, *inputs).backward();
@@ -36,6 +38,7 @@ def graphed_training_step(model, loss_fn, optimizer, example_inputs, warmup: int
         for dst, src in zip(static_inputs, inputs):
             dst.copy_(src, non_blocking=True)
         graph.replay()
+        bump_param_epoch()  # the replay updated parameters without touching their version counters: drop packed blobs
         return static_loss.detach()
 
     step.graph = graph
@@ -46,7 +49,9 @@ def graphed_inference(fn, example_inputs, warmup: int = 3):
     """Returns ``call(*inputs) -> outputs`` replaying one captured ``fn(*inputs)`` under ``torch.no_grad()``.
     Useful where a call is a chain of small launches (e.g. MNF layers at small batch sizes); a single fused flow
     kernel gains nothing (BASELINE config 1 measures 80 us per call either way: the time is inside the kernel).
-    The outputs are static buffers that the next call overwrites."""
+    The outputs are static buffers that the next call overwrites.  Stochastic modules (MNF layers, RNVP) draw their
+    noise from torch's graph-safe CUDA generator while a capture is in progress (layers/_mnf_ops.py::Noise), so every
+    replay sees fresh z, masks and eps; the in-kernel Philox path takes its seed by value and is not used under capture."""
     static_inputs = tuple(t.clone() for t in example_inputs)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())

@@ -74,6 +74,13 @@ class Noise:
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        if tape is None and seed is None and device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: a Philox seed passed by value would be frozen into the graph and every replay would
+            # repeat the same z / masks / eps.  Materialise the draws with torch's graph-safe generator instead (its
+            # offset advances per replay), in the reference's draw order.
+            from ._train import DeviceTape
+
+            tape = DeviceTape(device)
         self.tape, self.device, self.row_offset = tape, device, int(row_offset)
         self.streams = 0
         if tape is None and seed is None:
@@ -131,13 +138,16 @@ def sample_z0(q0_mean, q0_log_var, n_rows, noise: Noise):
 
 
 def _rnvp_struct(flow, dev, keep):
+    from .._program import check_leaky
+
+    check_leaky(flow.net)
     lin = flow.net.linears()
     if len(lin) > RNVP_MAX_NET:
         raise ValueError(f"RNVP conditioner with {len(lin)} layers; at most {RNVP_MAX_NET} supported")
     # fast path: the descriptor only holds raw pointers, so it stays valid while the parameters keep their storage
     # (optimizer steps update in place); rebuilding it was a third of the host time of a kl_div() call
     tensors = [t for m in lin for t in (m.weight, m.bias)] + [flow.t.weight, flow.t.bias, flow.s.weight, flow.s.bias]
-    key = (dev, tuple(t.data_ptr() for t in tensors))
+    key = (str(dev), tuple(t.data_ptr() for t in tensors))
     cached = flow.__dict__.get("_rnvp_struct_cache")
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]
@@ -231,8 +241,22 @@ def rnvp_stack_tc(flows, z, noise: Noise, x=None, x_rows=None, xz_out=None, q0=N
 
 
 def rnvp_stack(flows, z, tape, want_inter):
-    """NormalizingFlow([RNVP...]).forward: returns (list incl. the input, log_det[B])."""
+    """NormalizingFlow([RNVP...]).forward: returns (list incl. the input, log_det[B]).  With grad enabled and
+    trainable parameters (or a z that requires grad) the differentiable primitives of layers/_train.py run, as the
+    reference's version is differentiable (rnvp.py:25-39 under torch autograd)."""
     z = _lib.require_cuda_f32(z, "input")
+    flows = list(flows)
+    if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for f in flows for p in f.parameters())):
+        from . import _train
+
+        t = _train._tape(tape, z.device)
+        xs, ld = [z], torch.zeros(z.size(0), device=z.device)
+        for f in flows:
+            mask = _train._draw(t, "bernoulli", z.shape, z.device)
+            nxt, l = _train.rnvp_flow(f, xs[-1], mask)
+            xs.append(nxt)
+            ld = ld + l
+        return (xs if want_inter else [z, xs[-1]]), ld
     noise = tape if isinstance(tape, Noise) else Noise(tape, z.device)
     out = z.clone()
     ld, inter = rnvp_stack_inplace(list(flows), out, noise, want_inter)

@@ -31,7 +31,7 @@ _lib.register({
 })
 
 EW_MUL, EW_MUL_ROWVEC, EW_FMA, EW_SQUARE, EW_EXP, EW_LEAKY, EW_LEAKY_BWD, EW_NOISE_OUT, EW_GVAR, EW_LIN_IN_BWD, EW_Z0 = range(1, 12)
-EW_MUL_COLVEC, EW_ADD_2MUL, EW_ADD_COLVEC = 12, 13, 14
+EW_MUL_COLVEC, EW_ADD_2MUL, EW_ADD_COLVEC, EW_RELU, EW_RELU_BWD = 12, 13, 14, 15, 16
 
 
 def _p(t):
@@ -197,6 +197,22 @@ class LeakyFn(torch.autograd.Function):
         return ew(EW_LEAKY_BWD, _c(g), a)
 
 
+class ReluFn(torch.autograd.Function):
+    """nn.ReLU between the MaskedLinear layers of a standalone MADE (made.py:43)."""
+
+    @staticmethod
+    def forward(ctx, a):
+        a = _c(a)
+        ctx.save_for_backward(a)
+        return ew(EW_RELU, a)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        return ew(EW_RELU_BWD, _c(g), a)
+
+
 class SampleZ0Fn(torch.autograd.Function):
     """q0_mean + exp(q0_log_var / 2) * eps (mnf_linear.py:61-64)."""
 
@@ -335,6 +351,9 @@ class KlRowsFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------------
 def rnvp_flow(flow, z, mask):
     """RNVP.forward (rnvp.py:26-40) -> (z_out, log_det[R])."""
+    from .._program import check_leaky
+
+    check_leaky(flow.net)
     y = MulFn.apply(z, mask)
     lins = flow.net.linears()
     for i, lin in enumerate(lins):

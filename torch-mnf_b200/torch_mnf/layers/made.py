@@ -20,10 +20,17 @@ class MaskedLinear(nn.Linear):
         self.mask.copy_(torch.from_numpy(np.ascontiguousarray(mask)).to(self.mask.device, torch.bool))
 
     def forward(self, x):
-        raise RuntimeError(
-            "MaskedLinear is a parameter container in the B200 build; MADE runs inside the "
-            "fused MAF/IAF kernels (flows.MAF / flows.IAF)"
-        )
+        """x @ (W.T * mask) + b (made.py:22-23) on the exact-fp32 GEMM kernel (mnf_gemm_f32); differentiable through
+        the hand-written dgrad / wgrad GEMMs when grad is enabled.  Inside MAF / IAF the whole MADE runs in the fused
+        flow kernels instead (mask folded into the packed weights)."""
+        from .. import _lib
+        from . import _train
+
+        lead = x.shape[:-1]
+        x2 = _lib.require_cuda_f32(x, "input").reshape(-1, self.in_features)
+        w = self.weight * self.mask.to(self.weight.dtype).T  # [out, in]; folding the mask is O(params), not O(batch)
+        out = _train.LinearFn.apply(x2, w, self.bias)
+        return out.reshape(*lead, self.out_features)
 
 
 class MADE(nn.Sequential):
@@ -47,6 +54,16 @@ class MADE(nn.Sequential):
         self.seed = 0
         self.m = {}
         self.update_masks()
+
+    def forward(self, x):
+        """MaskedLinear / ReLU chain (made.py:43-57 builds it as an nn.Sequential); the ReLUs run in the library's
+        elementwise kernel rather than ATen so that a standalone MADE(x) stays on the CUDA path end to end."""
+        from . import _train
+
+        h = x
+        for m in self:
+            h = m(h) if isinstance(m, MaskedLinear) else _train.ReluFn.apply(h)
+        return h
 
     def update_masks(self):
         if self.m and self.num_masks == 1:
@@ -125,7 +142,11 @@ class MadeStackPlan:
 
     def build(self, device):
         ts = self._tensors()
-        key = (str(device), tuple(t._version for t in ts), ts[0].data_ptr())
+        from .._program import param_epoch
+
+        # versions catch in-place updates, the data pointers of EVERY tensor catch re-assigned storage, the epoch
+        # catches CUDA-graph replays of an optimizer step (torch_mnf.graphs); the list is re-read from the modules
+        key = (str(device), tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts), param_epoch())
         if key == self.key:
             return
         structs, keep, self.max_hidden = [], [], 32

@@ -6,6 +6,7 @@ import torch
 from torch import nn
 
 from .. import _lib, flows
+from .._program import state_without_caches
 from . import _mnf_ops as ops
 from . import _train
 
@@ -15,6 +16,8 @@ class MNFConv2d(nn.Module):
     scales the output channels of the mean path; out = conv(x, W_mean*z) + sqrt(conv(x^2,
     exp(W_log_var)) + exp(b_log_var)) * eps, computed as one implicit-GEMM CUDA kernel.
     ``b_mean`` is a fixed zero tensor and not part of the state_dict, as in the reference."""
+
+    __getstate__ = state_without_caches  # copy.deepcopy / pickle drop cached device scratch
 
     def __init__(self, n_in: int, n_out: int, kernel_size: int, n_flows_q: int = 2, n_flows_r: int = 2,
                  h_sizes: Sequence[int] = (50,)) -> None:
@@ -38,6 +41,9 @@ class MNFConv2d(nn.Module):
         dev = self.W_mean.device
         if dev.type != "cuda":
             raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
+        if _train.needs_grad(self):  # differentiable, like the reference's (mnf_conv.py:80-88 under autograd)
+            z, ld = _train.sample_z(self, -1, _train._tape(noise, dev), self.n_out)
+            return z, ld.squeeze()
         noise = noise if isinstance(noise, ops.Noise) else ops.Noise(noise, dev)
         # z is ONE draw shared by the whole call (mnf_conv.py:80-88): it must not depend on which shard of the
         # rows this rank owns, so it is drawn at row offset 0 whatever the caller's offset is

@@ -5,6 +5,7 @@ import torch
 from torch import nn
 
 from .. import _lib, flows
+from .._program import state_without_caches
 from . import _mnf_ops as ops
 from . import _train
 
@@ -22,6 +23,8 @@ class MNFLinear(nn.Module):
 
     #: "auto" (TF32 tensor cores for large aligned shapes, exact fp32 otherwise), "fp32" or "tf32"
     precision = "auto"
+
+    __getstate__ = state_without_caches  # copy.deepcopy / pickle drop cached device scratch
 
     def __init__(self, n_in, n_out, n_flows_q=2, n_flows_r=2, h_sizes=(50,)):
         super().__init__()
@@ -46,6 +49,9 @@ class MNFLinear(nn.Module):
         dev = self.W_mean.device
         if dev.type != "cuda":
             raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
+        if _train.needs_grad(self):  # differentiable, like the reference's (mnf_linear.py:58-64 under autograd)
+            z, ld = _train.sample_z(self, batch_size, _train._tape(noise, dev), self.n_in)
+            return z, ld.squeeze()
         noise = self._noise(noise, dev, row_offset)
         z = ops.sample_z0(self.q0_mean, self.q0_log_var, batch_size, noise)
         ld, _ = ops.rnvp_stack_inplace(list(self.flow_q.flows), z, noise)
