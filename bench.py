@@ -12,6 +12,11 @@ overlapped with the next chunk's kernel.
     python bench.py --impl reference --steps 3 --warmup 1      # CPU oracle port on host cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the meaning of every key.
+
+The headline keys describe config 2.  The same line carries `configs`: BASELINE configs 1, 3, 4, 5 (and config 2 under
+strong scaling when N > 1), each measured in this process with its own value / unit / ms / roofline / cpu_baseline /
+e2e, so that every named configuration -- and the second named metric, MNF-LeNet MC predictive samples/s -- is on the
+driver's clock.  `--workload cfg2` prints the headline alone, `--workload cfg4` the MNF-LeNet line alone.
 """
 
 from __future__ import annotations
@@ -35,7 +40,7 @@ N_POINTS = 1 << 24
 K_BINS, BOUND, N_H = 8, 3, 16
 BYTES_PER_POINT = 12  # 8 B point in + 4 B log-prob out (z is not materialised in log-prob mode)
 MLP_FMA_PER_POINT = 3 * 2 * (16 + 256 + 256 + 16 * 23)  # 5376 fused multiply-adds in the conditioners
-NCU_TRAFFIC_BYTES_PER_STEP = 1895.2e6  # dram read+write summed over the 6 segment launches of one step at 2^24 points (ncu --set full, r01)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # written by tools/ncu_traffic.py from an `ncu --set full` capture
 METRIC = "flow log-prob points/s"
 WORKLOAD = "cfg2: [ActNormFlow, Glow, NSF_CL(K=8,B=3,n_h=16)] x3, 2-D points, batch 2^24 per GPU"
 
@@ -51,6 +56,53 @@ def specs():
 def make_points(n, seed=0):
     g = torch.Generator().manual_seed(seed)
     return 1.5 * torch.randn(n, 2, generator=g)
+
+
+def traffic_for(workload, units):
+    """DRAM bytes per step of `workload` scaled to `units` work items, from the committed ncu capture summary
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum summed over the step's launches), or
+    None when no capture exists for it."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            w = json.load(f)["workloads"][workload]
+        return float(w["dram_bytes"]) * units / float(w["units"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def kernels_of(fn):
+    """{launch site: launches} of the library's own tally (mnf_launch_stats) while fn() runs."""
+    from torch_mnf import _lib
+
+    _lib.launch_stats(reset=True)
+    fn()
+    return _lib.launch_stats()
+
+
+def timed_ms(fn, steps, warmup, dev, world=1):
+    """CUDA-event time per step of fn() on the current stream: warm-up, barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / steps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    return ms
 
 
 def peaks():
@@ -215,7 +267,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     affinity = pin_to_gpu_numa_node(local) if world > 1 else "unchanged (single rank)"
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     model = build_model(dev)
     n = args.points
@@ -307,11 +359,13 @@ def run_ours(args):
 
     # ---- kernel-only duration (same launches, no collective) for the roofline ----
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    _lib.launch_stats(reset=True)
     for a, b in kev:
         a.record()
         model.log_prob(x, out=gathered.view(-1)[:n])
         b.record()
     torch.cuda.synchronize(dev)
+    k_sites = {k: v // len(kev) for k, v in _lib.launch_stats().items()}  # launch sites per step, from the library's tally
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
 
     # ---- end to end through the module API with HOST buffers (pinned), copies inside ----
@@ -376,10 +430,9 @@ def run_ours(args):
     # sanity: the e2e path produced finite log-probs equal to the resident path
     chk = torch.allclose(out_host[:4096], gathered.view(-1)[:4096].cpu(), rtol=1e-6, atol=1e-6) if chunks == 1 else True
 
+    del xd, od, out_host
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     hbm_peak, peak_src, _ = peaks()
     achieved = BYTES_PER_POINT * n / (k_ms * 1e-3) / 1e9
@@ -403,8 +456,8 @@ def run_ours(args):
                 "how": f"pinned host -> {e_chunks} chunks double-buffered over 3 streams (pipelined across steps) -> NormalizingFlowModel.log_prob -> pinned host"},
         "gpu_launches": launches, "gather_verified": gather_ok,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_STEP * n / N_POINTS,
-                     "kernel": "flow_cbank_kernel<16,8> x6 segments (+ cbank_stage_kernel)",
+                     "frac": achieved / hbm_peak, "traffic": traffic_for("cfg2", n),
+                     "kernel": k_sites,
                      "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT, "peak_source": peak_src,
                      "note": "per STEP (6 segment launches): algorithmic 12 B/pt; the segmented stack moves ~113 B/pt "
                              "(ncu, profiles/r01_flow_cbank_ncu_full.md); kernel is fp32-FMA-pipe bound, not HBM "
@@ -452,24 +505,418 @@ def run_ours(args):
                                "sample": f"{ncpu} points (2^{ncpu.bit_length() - 1}), best of 2, torch CPU oracle port, {cores} threads"}
     else:
         out["cpu_baseline"] = None
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 # ---------------------------------------------------------------------------------------
-# secondary workload (not the default line): BASELINE config 4, MNF-LeNet MC prediction
+# the other BASELINE configurations (attached to the headline line as `configs`)
 # ---------------------------------------------------------------------------------------
-def run_lenet(args):
-    """MNF-LeNet Monte-Carlo predictive samples/s (BASELINE config 4).  1024 synthetic 28x28 images; every rank
-    draws `--mc-samples` samples per image per step (weak scaling: the MC-sample axis is sharded, conv z shared
-    through the common seed, per-row noise keyed by the global row), reduces them to per-image class
-    probabilities locally and all-reduces the [1024, 10] sums -- the raw samples never cross NVLink."""
+def _tf32_peak():
+    """TF32 dense peak = half the measured bf16 peak (MEASURED_PEAKS.json sustained figure: these kernels are timed
+    inside a long step)."""
+    d = peaks()[2]
+    return float(d.get("bf16_tflops_sustained", 1400.0)) / 2, ("MEASURED_PEAKS.json bf16_tflops_sustained / 2" if d else "fallback 1400 / 2")
+
+
+def cfg_strong(args, dev, world, rank, model):
+    """Config 2 as BASELINE words it: ONE batch of 2^24 points sharded over the N GPUs (strong scaling), log-probs
+    gathered on every rank through the fused peer-memory stores."""
+    import torch.distributed as dist
+    from torch_mnf.distributed import PeerGather
+
+    n_tot = N_POINTS
+    n = n_tot // world
+    x = make_points(n, seed=300 + rank).to(dev)
+    try:
+        peer = PeerGather(n, dev)
+        gather_out = peer.gather_out(use_multicast=not args.no_multicast)
+        how = "fused peer-memory stores (" + ("NVLS multicast" if gather_out.multicast_ptr else "per-peer st.global") + "), 2 barriers"
+
+        def step():
+            peer.barrier()
+            model.log_prob(x, out=peer.local_slice(), gather=gather_out)
+            peer.barrier()
+    except Exception as e:  # noqa: BLE001
+        buf = torch.empty(world * n, device=dev)
+        how = f"NCCL all_gather ({type(e).__name__}: no peer memory)"
+
+        def step():
+            model.log_prob(x, out=buf[rank * n:(rank + 1) * n])
+            dist.all_gather_into_tensor(buf, buf[rank * n:(rank + 1) * n])
+    ms = timed_ms(step, args.steps, 3, dev, world)
+    return {"metric": METRIC, "value": n_tot / (ms * 1e-3), "unit": "points/s", "ms_per_step": ms, "scaling": "strong",
+            "n_gpus": world, "steps": args.steps, "warmup": 3,
+            "config": {"workload": f"cfg2 stack, ONE batch of 2^24 points sharded over {world} GPUs ({n} points each)",
+                       "collective": how, "l2": f"{8 * n / 1e6:.0f} MB of points per GPU per step"
+                       + ("" if 8 * n > 126e6 else " (fits the 126 MB L2: steps re-read the same resident shard)")}}
+
+
+def cfg1(args, dev):
+    """BASELINE config 1: RNVP x9 (AffineHalfFlow) on 2-D half-moons, batch 4096, log_prob (inverse + log-det + base
+    density) and forward, per call.  Launch-latency-bound: 80 KB of traffic per call."""
+    from tests.helpers import golden_sd, golden_spec, load_flow_model, load_golden, t
+    from torch_mnf import _lib
+
+    g = load_golden("rnvp9_moons")  # the reference's own trained weights (tests/test_flows.py training loop)
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd, device=dev, return_intermediates=False)
+    try:
+        from sklearn.datasets import make_moons
+
+        x_host = torch.from_numpy(make_moons(4096, noise=0.05, random_state=0)[0]).float()  # data.py:21-24
+        data = "make_moons(4096, noise=0.05, random_state=0)"
+    except Exception:  # noqa: BLE001
+        x_host = t(g, "inv/x").repeat(40, 1)[:4096].contiguous()
+        data = "golden half-moon points tiled to 4096"
+    x_pin = x_host.pin_memory()
+    out_pin = torch.empty(4096).pin_memory()
+    x = x_host.to(dev)
+    lp = torch.empty(4096, device=dev)
+    K = 200
+    sites = kernels_of(lambda: model.log_prob(x, out=lp))
+    ms = timed_ms(lambda: model.log_prob(x, out=lp), K, 20, dev)
+    ms_fwd = timed_ms(lambda: model.forward(x), K, 20, dev)
+    xd = torch.empty_like(x)
+
+    def e2e():
+        xd.copy_(x_pin, non_blocking=True)
+        model.log_prob(xd, out=lp)
+        out_pin.copy_(lp, non_blocking=True)
+
+    e_ms = timed_ms(e2e, K, 20, dev)
+    fast = None
+    if hasattr(model, "frozen_log_prob"):
+        call = model.frozen_log_prob(4096)
+        ms_fast = timed_ms(lambda: call(x, lp), K, 20, dev)
+        fast = {"us_per_call": ms_fast * 1e3, "value": 4096 / (ms_fast * 1e-3),
+                "how": "NormalizingFlowModel.frozen_log_prob: C-level cached handle (no program lookup, allocation or marshalling per call)"}
+    hbm_peak, peak_src, _ = peaks()
+    res = {"metric": METRIC, "value": 4096 / (ms * 1e-3), "unit": "points/s", "us_per_call": ms * 1e3, "ms_per_step": ms,
+           "forward_us_per_call": ms_fwd * 1e3, "steps": K, "warmup": 20, "dtype": "f32",
+           "config": {"workload": "cfg1: RNVP x9 (AffineHalfFlow, h=24x3) on 2-D half-moons, batch 4096, log_prob per call",
+                      "data": data, "l2": "32 KB per call: resident in L2 by construction of this configuration (latency-bound)"},
+           "gpu_launches_per_call": sum(sites.values()), "kernels": sites,
+           "roofline": {"bound": "hbm", "achieved": 12 * 4096 / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 12 * 4096 / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic_for("cfg1", 4096), "peak_source": peak_src,
+                        "note": "49 KB of algorithmic traffic per call: the call is launch- and latency-bound (SURVEY 8d), "
+                                "the HBM fraction is reported for completeness only; us_per_call is the figure of merit"},
+           "e2e": {"value": 4096 / (e_ms * 1e-3), "unit": "points/s", "us_per_call": e_ms * 1e3, "h2d_bytes_per_step": 8 * 4096,
+                   "d2h_bytes_per_step": 4 * 4096}}
+    if fast:
+        res["cached_handle"] = fast
+    if not args.no_cpu:
+        from oracle import flows_cpu
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        best = float("inf")
+        for _ in range(20):
+            t0 = time.perf_counter()
+            flows_cpu.log_prob(sd, specs, x_host)
+            best = min(best, time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": 4096 / best, "unit": "points/s", "cores": cores, "kind": "port",
+                               "sample": "the full 4096-point call, best of 20", "us_per_call": best * 1e6}
+    return res
+
+
+def cfg3(args, dev):
+    """BASELINE config 3: MAF x9 (MADE 64-24-24-24-128) on 64-dim Gaussian data, batch 2^20, density evaluation."""
+    from tests.helpers import golden_sd, golden_spec, load_flow_model, load_golden
+
+    g = load_golden("maf9_d64")
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd, device=dev, return_intermediates=False)
+    n = 1 << 20
+    x_pin = torch.randn(n, 64, generator=torch.Generator().manual_seed(0)).pin_memory()
+    x = x_pin.to(dev)
+    steps = max(3, min(args.steps, 10))
+    res = {}
+    rows = []
+    for prec in ("auto", "fp32"):
+        for f in model.flows:
+            f.precision = prec
+        sites = kernels_of(lambda: model.inverse(x))
+        ms = timed_ms(lambda: model.inverse(x), steps, 3, dev)
+        rows.append((prec, ms, sites))
+    for f in model.flows:
+        f.precision = "auto"
+    prec, ms, sites = rows[0]
+    lp_pin = torch.empty(n).pin_memory()
+    xd = torch.empty_like(x)
+
+    def e2e():
+        xd.copy_(x_pin, non_blocking=True)
+        lp_pin.copy_(model.log_prob(xd), non_blocking=True)
+
+    e_ms = timed_ms(e2e, steps, 2, dev)
+    hbm_peak, peak_src, _ = peaks()
+    tf32_peak, tf32_src = _tf32_peak()
+    flops_row = 9 * 2 * (64 * 24 + 24 * 24 + 24 * 24 + 24 * 128)  # 103 680 dense flops per row (SURVEY 8d)
+    tflops = flops_row * n / (ms * 1e-3) / 1e12
+    on_tc = any("made_fused" in k or "tf32_gemm" in k for k in sites)
+    res = {"metric": METRIC, "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps, "warmup": 3,
+           "dtype": "tf32 tensor cores (MADE GEMMs, 2e-3 class), fp32 elsewhere" if on_tc else "f32",
+           "config": {"workload": "cfg3: MAF x9 (MADE 64-24-24-24-128), 64-dim Gaussian data, batch 2^20, density (inverse: z and log_det stored)",
+                      "l2": "268 MB of rows per step, larger than the 126 MB L2"},
+           "gpu_launches_per_step": sum(sites.values()), "kernels": sites,
+           "roofline": {"bound": "hbm", "achieved": 516 * n / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 516 * n / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic_for("cfg3", n), "peak_source": peak_src,
+                        "bytes_per_row": 516},
+           "tensor_pipe": {"dense_tflops": tflops, "peak": tf32_peak, "frac": tflops / tf32_peak, "peak_source": tf32_src,
+                           "flops_per_row": flops_row, "note": "dense-equivalent MADE flops (masks ~50% zero) against the TF32 peak"},
+           "exact_fp32_path": {"ms_per_step": rows[1][1], "value": n / (rows[1][1] * 1e-3), "kernels": rows[1][2]},
+           "e2e": {"value": n / (e_ms * 1e-3), "unit": "rows/s", "ms_per_step": e_ms, "h2d_bytes_per_step": 256 * n,
+                   "d2h_bytes_per_step": 4 * n, "how": "pinned host rows -> device -> NormalizingFlowModel.log_prob -> pinned host log-probs"}}
+    if not args.no_cpu:
+        from oracle import flows_cpu
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        xc = x_pin[: 1 << 16]
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            flows_cpu.stack(sd, specs, xc, True)
+            best = min(best, time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": (1 << 16) / best, "unit": "rows/s", "cores": cores, "kind": "port",
+                               "sample": "2^16 rows of the 2^20-row batch, best of 2"}
+    return res
+
+
+def cfg4(args, dev, world, rank, total_samples=500, per_gpu_samples=None):
+    """BASELINE config 4: MNF-LeNet Monte-Carlo predictive samples/s.  1024 synthetic 28x28 images x 500 MC samples per
+    image; the MC-sample axis is sharded over the ranks (strong scaling: 500 samples in total), conv z shared through
+    the common seed, per-row noise keyed by the global row; ranks reduce their samples to per-image class
+    probabilities and all-reduce the [1024, 10] sums -- the raw samples never cross NVLink.
+    per_gpu_samples: weak-scaling form (`--workload cfg4 --mc-samples S`)."""
     import torch.distributed as dist
     from tests.helpers import golden_sd, load_golden
     from torch_mnf import _lib
-    from torch_mnf.distributed import reduce_mc_probs
+    from torch_mnf.distributed import shard_range
     from torch_mnf.models import MNFLeNet
+
+    net = MNFLeNet()
+    net.load_state_dict(golden_sd(load_golden("mnf_lenet")))  # the briefly trained fixture (tests/golden)
+    net.to(dev)
+    n_img, chunk = 1024, 25
+    if per_gpu_samples is not None:
+        s_lo, s_hi = rank * per_gpu_samples, (rank + 1) * per_gpu_samples
+        total_s = per_gpu_samples * world
+    else:
+        s_lo, s_hi = shard_range(total_samples, world, rank)
+        total_s = total_samples
+    imgs_host = torch.rand(n_img, 1, 28, 28, generator=torch.Generator().manual_seed(0)).pin_memory()
+    imgs = imgs_host.to(dev)
+    probs_host = torch.empty(n_img, 10).pin_memory()
+    counter = [0]
+
+    def step(from_host=False):
+        counter[0] += 1
+        x = imgs_host.to(dev, non_blocking=True) if from_host else imgs
+        sums = torch.zeros(n_img, 10, device=dev)
+        for c in range(s_lo, s_hi, chunk):
+            s_here = min(chunk, s_hi - c)
+            lp = net(x, n_samples=s_here, seed=1000 + counter[0] * 131, row_offset=c * n_img)
+            sums += lp.exp().view(s_here, n_img, 10).sum(0)
+        if world > 1:
+            dist.all_reduce(sums)
+        probs = sums / total_s
+        if from_host:
+            probs_host.copy_(probs, non_blocking=True)
+        return probs
+
+    steps = max(2, min(args.steps, 5))
+    sites = kernels_of(step)
+    l0 = _lib.lib().mnf_launch_count()
+    ms = timed_ms(step, steps, 3, dev, world)
+    launches = (_lib.lib().mnf_launch_count() - l0) // (steps + 3)
+    e_ms = timed_ms(lambda: step(True), steps, 1, dev, world)
+    if rank != 0:
+        return None
+    total = n_img * total_s
+    flops = 8.2e6 * total  # SURVEY 8d: ~8.2 MFLOP per sample (dense count, conv1 per sample)
+    tf32_peak, tf32_src = _tf32_peak()
+    ach = flops / (ms * 1e-3) / 1e12 / world
+    res = {"metric": "MNF-LeNet MC predictive samples/s", "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+           "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak" if per_gpu_samples is not None else "strong", "vs_baseline": None,
+           "dtype": "tf32 tensor cores (conv2, fc1) / f32", "data": "synthetic",
+           "config": {"workload": f"cfg4: MNF-LeNet (696,950 params), 1024 images x {total_s} MC samples per image in total",
+                      "parallelism": f"MC samples sharded over {world} GPU(s) ({s_hi - s_lo} on rank 0); all_reduce of [1024,10] probability sums",
+                      "l2": "activations (46 KB/sample before the pool of conv1, 11.5 KB/sample after it) far exceed L2"},
+           "gpu_launches_per_step": launches, "kernels": sites,
+           "e2e": {"value": total / (e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": n_img * 784 * 4,
+                   "d2h_bytes_per_step": n_img * 40, "ms_per_step": e_ms},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                        "traffic": traffic_for("cfg4", total / world), "peak_source": tf32_src,
+                        "note": "dense-equivalent 8.2 MFLOP/sample per GPU against the TF32 peak; the pipeline is co-bound by "
+                                "operand generation in shared memory (implicit-GEMM conv2) and Philox noise (15.6 k normals/sample)"},
+           "normals_per_s": 15630 * total / (ms * 1e-3),
+           "cpu_baseline": None}
+    if world == 1 and not args.no_cpu:
+        # the reference's CPU path (oracle port: same ATen ops) on a bounded sample: 8 images x 250 MC samples
+        from oracle import mnf_cpu
+        from oracle.noise import FreshNoise
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        xc = imgs_host[:8].repeat(250, 1, 1, 1)
+        best = float("inf")
+        with torch.no_grad():
+            for _ in range(3):
+                t_0 = time.perf_counter()
+                mnf_cpu.lenet_forward(sd_cpu, xc, FreshNoise())
+                best = min(best, time.perf_counter() - t_0)
+        res["cpu_baseline"] = {"value": xc.size(0) / best, "unit": "samples/s", "cores": cores, "kind": "port",
+                               "sample": "8 images x 250 MC samples (2000 rows), best of 3"}
+    return res
+
+
+def cfg5(args, dev, world, rank):
+    """BASELINE config 5: MNFLinear(4096, 4096), 64 input rows x 8192 MC samples + one kl_div() per step; the MC-sample
+    axis is sharded over the ranks (strong scaling), MC mean and second moment [64, 4096] all-reduced -- never the raw
+    [R, 4096] outputs."""
+    import torch.distributed as dist
+    from torch_mnf import _lib
+    from torch_mnf.distributed import shard_range
+    from torch_mnf.layers import MNFLinear
+    from torch_mnf.layers import _train
+    from torch_mnf.layers._mnf_ops import Noise
+
+    torch.manual_seed(0)
+    layer = MNFLinear(4096, 4096).to(dev)
+    x_pin = torch.randn(64, 4096, generator=torch.Generator().manual_seed(0)).pin_memory()
+    x64 = x_pin.to(dev)
+    S_tot = args.cfg5_samples
+    s_lo, s_hi = shard_range(S_tot, world, rank)
+    S = s_hi - s_lo
+    R = 64 * S
+    stats_pin = torch.empty(2, 64 * 4096).pin_memory()
+    counter = [0]
+
+    def step(e2e=False):
+        counter[0] += 1
+        x = x_pin.to(dev, non_blocking=True) if e2e else x64
+        y = layer.forward_mc(x, S, noise=Noise(None, dev, s_lo * 64, seed=17 + counter[0]))
+        kl = layer.kl_div()
+        if e2e or world > 1:
+            flat = y.view(S, 64 * 4096)
+            m1, m2 = _train.colsum(flat), _train.colsum(flat, flat)  # MC sums of y and y^2 over the sample axis
+            st = torch.stack([m1, m2])
+            if world > 1:
+                dist.all_reduce(st)
+            if e2e:
+                stats_pin.copy_(st / S_tot, non_blocking=True)
+        return kl
+
+    steps = max(2, min(args.steps, 3))
+    sites = kernels_of(step)
+    ms = timed_ms(step, steps, 2, dev, world)
+    fwd_ms = timed_ms(lambda: layer.forward_mc(x64, S, noise=Noise(None, dev, s_lo * 64, seed=5)), steps, 1, dev, world)
+    kl_ms = timed_ms(lambda: layer.kl_div(), 20, 3, dev, world)
+    e_ms = timed_ms(lambda: step(True), steps, 1, dev, world)
+    if rank != 0:
+        return None
+    R_tot = 64 * S_tot
+    h = 64  # conditioner width padded to one 64-wide tile
+    executed = 2.0 * R * 4096 * 4096 + 2.0 * 64 * 4096 * 4096 + 2 * (2.0 * R * 4096 * h + 2.0 * R * h * 8192)
+    tf32_peak, tf32_src = _tf32_peak()
+    ach = executed / (fwd_ms * 1e-3) / 1e12
+    hbm_peak, _, _ = peaks()
+    res = {"metric": "MNFLinear MC rows/s (forward over all MC rows + one kl_div per step)", "value": R_tot / (ms * 1e-3),
+           "unit": "rows/s", "n_gpus": world, "steps": steps, "warmup": 2, "ms_per_step": ms,
+           "scaling": "strong", "dtype": "tf32 tensor cores (2e-3 class), fp32 accumulate",
+           "config": {"workload": f"cfg5: MNFLinear(4096,4096), 64 rows x {S_tot} MC samples = {R_tot} rows, 2+2 RNVP flows (h=50), + kl_div()",
+                      "parallelism": f"MC samples sharded over {world} GPU(s); all_reduce of the [2, 64, 4096] MC moment sums",
+                      "l2": f"{R * 4096 * 4 / 1e9:.1f} GB of outputs per GPU per step, far larger than L2"},
+           "forward_ms": fwd_ms, "forward_rows_per_s": R_tot / (fwd_ms * 1e-3), "kl_div_ms": kl_ms,
+           "gpu_launches_per_step": sum(sites.values()), "kernels": sites,
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                        "traffic": traffic_for("cfg5", R), "peak_source": tf32_src,
+                        "note": "EXECUTED flops of forward per GPU (mean GEMM per row, variance GEMM once per distinct input row, "
+                                "RNVP q-flow GEMMs with the conditioner padded to 64) over the forward time, against the TF32 peak"},
+           "kl_div_roofline": {"bound": "hbm", "achieved": 2 * 4096 * 4096 * 4 / (kl_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": 2 * 4096 * 4096 * 4 / (kl_ms * 1e-3) / 1e9 / hbm_peak,
+                               "note": "one read of W_mean and W_log_var (134 MB), eps_w from Philox; whole kl_div() call"},
+           "e2e": {"value": R_tot / (e_ms * 1e-3), "unit": "rows/s", "ms_per_step": e_ms, "h2d_bytes_per_step": 64 * 4096 * 4,
+                   "d2h_bytes_per_step": 2 * 64 * 4096 * 4,
+                   "how": "pinned host x[64,4096] -> forward_mc -> MC mean / second moment over the samples (library kernel) -> pinned host"},
+           "cpu_baseline": None}
+    if world == 1 and not args.no_cpu:
+        from oracle import mnf_cpu
+        from oracle.noise import FreshNoise
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd5 = {k: v.detach().cpu() for k, v in layer.state_dict().items()}
+        xc = x_pin.repeat(16, 1)  # 1024 rows
+        best = float("inf")
+        with torch.no_grad():
+            for _ in range(2):
+                t0 = time.perf_counter()
+                mnf_cpu.linear_forward(sd5, xc, FreshNoise())
+                best = min(best, time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            mnf_cpu.linear_kl_div(sd5, FreshNoise())
+            kl_cpu = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": xc.size(0) / best, "unit": "rows/s", "cores": cores, "kind": "port",
+                               "sample": "1024 rows (64 x 16 MC samples) of the forward, best of 2; kl_div once",
+                               "kl_div_ms": kl_cpu * 1e3}
+    return res
+
+
+def run_all(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    t_start = time.time()
+    out = run_ours(args)
+    if args.workload == "all":
+        extra = {}
+
+        def attempt(name, fn):
+            # a failing secondary configuration must never cost the headline line; every rank takes the same path
+            t0 = time.time()
+            try:
+                r = fn()
+            except Exception as e:  # noqa: BLE001
+                r = {"error": f"{type(e).__name__}: {e}"[:400]}
+                torch.cuda.synchronize(dev)
+            if isinstance(r, dict):
+                r["wall_s"] = round(time.time() - t0, 2)
+            extra[name] = r
+            torch.cuda.empty_cache()
+
+        if world > 1:
+            attempt("cfg2_strong", lambda: cfg_strong(args, dev, world, rank, build_model(dev)))
+            for name in ("cfg1", "cfg3"):
+                extra[name] = {"skipped": "single-GPU configuration (BASELINE names no multi-GPU form); measured at N=1"}
+        else:
+            attempt("cfg1", lambda: cfg1(args, dev))
+            attempt("cfg3", lambda: cfg3(args, dev))
+        attempt("cfg4", lambda: cfg4(args, dev, world, rank))
+        attempt("cfg5", lambda: cfg5(args, dev, world, rank))
+        if out is not None:
+            out["configs"] = extra
+            out["wall_s"] = round(time.time() - t_start, 2)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_lenet(args):
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -478,101 +925,10 @@ def run_lenet(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    net = MNFLeNet()
-    net.load_state_dict(golden_sd(load_golden("mnf_lenet")))  # the briefly trained fixture (tests/golden)
-    net.to(dev)
-    n_img, S, chunk = 1024, args.mc_samples, 32
-    imgs_host = torch.rand(n_img, 1, 28, 28, generator=torch.Generator().manual_seed(0)).pin_memory()
-    imgs = imgs_host.to(dev)
-    probs_host = torch.empty(n_img, 10).pin_memory()
-
-    def step(step_idx, from_host=False):
-        x = imgs_host.to(dev, non_blocking=True) if from_host else imgs
-        sums = torch.zeros(n_img, 10, device=dev)
-        for c in range(0, S, chunk):
-            s_here = min(chunk, S - c)
-            lp = net(x, n_samples=s_here, seed=1000 + step_idx * 131 + c, row_offset=(rank * S + c) * n_img)
-            sums += lp.exp().view(s_here, n_img, 10).sum(0)
-        if world > 1:
-            dist.all_reduce(sums)
-        probs = sums / (S * world)
-        if from_host:
-            probs_host.copy_(probs, non_blocking=True)
-        return probs
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local)
+    res = cfg4(args, dev, world, rank, per_gpu_samples=args.mc_samples)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    barrier()
-    l0 = _lib.lib().mnf_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    a.record()
-    for i in range(args.steps):
-        probs = step(100 + i)
-    b.record()
-    barrier()
-    t1 = time.time()
-    launches = _lib.lib().mnf_launch_count() - l0
-    ms = a.elapsed_time(b) / args.steps
-    a.record()
-    for i in range(args.steps):
-        step(200 + i, from_host=True)
-    b.record()
-    barrier()
-    e_ms = a.elapsed_time(b) / args.steps
-    if world > 1:
-        tt = torch.tensor([ms, e_ms], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e_ms = float(tt[0]), float(tt[1])
-    if rank == 0:
-        clocks = sampler.stop(t0, t1)
-        total = world * n_img * S
-        flops = 8.2e6 * total  # ~8.2 MFLOP per sample (dense count, conv1 per sample)
-        out = {
-            "metric": "MNF-LeNet MC predictive samples/s", "value": total / (ms * 1e-3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 tensor cores (conv2, fc1) / f32",
-            "data": "synthetic",
-            "config": {"workload": f"cfg4: MNF-LeNet (696,950 params), 1024 images x {S} MC samples per GPU per step",
-                       "parallelism": f"MC samples sharded over {world} GPU(s); all_reduce of [1024,10] probability sums",
-                       "l2": "activations (46 KB/sample before the pool of conv1, 11.5 KB/sample after it) far exceed L2"},
-            "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": total / (e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": n_img * 784 * 4,
-                    "d2h_bytes_per_step": n_img * 40, "ms_per_step": e_ms},
-            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": peaks()[2].get("bf16_tflops_sustained", 1400.0) / 2,
-                         "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / world / (peaks()[2].get("bf16_tflops_sustained", 1400.0) / 2),
-                         "traffic": None, "note": "dense-equivalent 8.2 MFLOP/sample against the TF32 peak (= half the measured bf16 "
-                                                  "sustained peak); the pipeline is bound by operand generation in shared memory (implicit-GEMM conv2) and Philox noise, not by the tensor pipe"},
-            "cpu_baseline": None,
-        }
-        if world == 1 and not args.no_cpu:
-            # the reference's CPU path (oracle port: same ATen ops) on a bounded sample: 8 images x 250 MC samples
-            from oracle import mnf_cpu
-            from oracle.noise import FreshNoise
-
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            xc = imgs_host[:8].repeat(250, 1, 1, 1)
-            best = float("inf")
-            with torch.no_grad():
-                for _ in range(3):
-                    t_0 = time.perf_counter()
-                    mnf_cpu.lenet_forward(sd_cpu, xc, FreshNoise())
-                    best = min(best, time.perf_counter() - t_0)
-            out["cpu_baseline"] = {"value": xc.size(0) / best, "unit": "samples/s", "cores": cores, "kind": "port",
-                                   "sample": "8 images x 250 MC samples (2000 rows), best of 3"}
-        print(json.dumps(out))
+        sampler = None  # clocks are sampled on the headline line; this line is a secondary entry point
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
@@ -585,14 +941,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per GPU (default 2^24)")
     ap.add_argument("--chunks", type=int, default=4, help="all-gather chunks per step when N>1")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks per step of the host-to-host (e2e) pipeline")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1 result gather: fused peer-memory stores (default) or NCCL all-gather")
     ap.add_argument("--no-multicast", action="store_true", help="peer gather: per-peer stores even if NVLS multicast exists")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
-                    help="cfg2 (default, the headline flow log-prob line) or cfg4 (MNF-LeNet MC prediction)")
-    ap.add_argument("--mc-samples", type=int, default=64, help="cfg4: MC samples per image per GPU per step")
+    ap.add_argument("--workload", default="all", choices=["all", "cfg2", "cfg4"],
+                    help="all (default): the cfg2 headline line carrying every other configuration under `configs`; "
+                         "cfg2: the headline alone; cfg4: the MNF-LeNet MC prediction line alone (weak scaling)")
+    ap.add_argument("--mc-samples", type=int, default=64, help="--workload cfg4: MC samples per image per GPU per step")
+    ap.add_argument("--cfg5-samples", type=int, default=8192, help="cfg5: MC samples (x 64 input rows) in total")
     args = ap.parse_args()
     torch.set_grad_enabled(False)  # the workload is density evaluation / prediction, not training
     if args.impl == "reference":
@@ -600,7 +958,7 @@ def main():
     elif args.workload == "cfg4":
         run_lenet(args)
     else:
-        run_ours(args)
+        run_all(args)
 
 
 if __name__ == "__main__":

@@ -40,6 +40,11 @@ int mnf_abi_version(void);
 const char *mnf_last_error(void);
 /* Kernels launched by this library in this process so far (diagnostics; bench.py's gpu_launches). */
 uint64_t mnf_launch_count(void);
+/* Per-launch-site tally since the last reset, written as "site=count;site=count;..." (sites are the kernel names the
+ * library launches); returns the length needed.  Diagnostics only: bench.py uses it to NAME the kernels of a timed region
+ * from what actually ran instead of from a literal. */
+int64_t mnf_launch_stats(char *buf, int64_t size);
+void mnf_launch_stats_reset(void);
 /* Fills SM count, max opt-in shared memory per block, compute capability major/minor of
  * the current device.  Any pointer may be NULL. */
 int mnf_device_info(int *sm_count, int *smem_optin, int *cc_major, int *cc_minor);
@@ -303,6 +308,18 @@ int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, cons
 int mnf_conv_noise_relu_pool(const float *mean, const float *sd, int64_t n_unique, const float *eps,
                              uint64_t seed, uint32_t noise_stream, uint64_t row_offset, float *out,
                              int64_t n_rows, int channels, int out_h, int out_w, void *stream);
+/* Per-sample conv-z variants (the MC predict option of SURVEY 8f-4: every Monte-Carlo sample draws its own z, as
+ * S separate reference calls would, mnf_conv.py:80-88).  z scales OUTPUT channels (mnf_conv.py:73), so the moments
+ * are evaluated once with unit z and row r's mean is scaled by z_rows[r / rows_per_z, c] in the noise / pool pass.
+ * mnf_conv2d_forward_tc_z takes exactly one of z ([c_out], folded into the packed weights) and z_rows. */
+int mnf_conv_noise_relu_pool_z(const float *mean, const float *sd, int64_t n_unique, const float *eps,
+                               uint64_t seed, uint32_t noise_stream, uint64_t row_offset, float *out,
+                               int64_t n_rows, int channels, int out_h, int out_w, const float *z_rows,
+                               int64_t rows_per_z, void *stream);
+int mnf_conv2d_forward_tc_z(const float *x, const float *z, const float *z_rows, int64_t rows_per_z,
+                            const float *W_mean, const float *W_log_var, const float *b_log_var, const float *eps,
+                            uint64_t seed, uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_imgs,
+                            int c_in, int height, int width, int c_out, int ksize, float *workspace, void *stream);
 int64_t mnf_conv_tc_workspace(int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize);
 int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, const float *W_log_var,
                           const float *b_log_var, const float *eps, uint64_t seed, uint32_t noise_stream,

@@ -29,8 +29,12 @@ int fail(int code, const char *fmt, ...);
 // process-wide count of kernel launches made by this library (mnf_launch_count(); bench.py reports it)
 unsigned long long &launch_counter();
 
+// per-launch-site tally behind mnf_launch_stats() (diagnostics: which kernels a timed region really ran)
+void note_launch(const char *what);
+
 inline int launch_status(const char *what) {
     ++launch_counter();
+    note_launch(what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "%s launch failed: %s", what, cudaGetErrorString(e));
     return 0;

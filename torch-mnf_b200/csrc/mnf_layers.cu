@@ -224,7 +224,7 @@ struct MnfConvProb {
         a[1] = xv * xv;
     }
     __device__ void load_b(int n, int k, float (&v)[2]) const {
-        v[0] = Wm[(size_t)n * K + k] * z[n];
+        v[0] = Wm[(size_t)n * K + k] * (z ? z[n] : 1.f);  // z == NULL: unit scale (per-sample z applied later)
         v[1] = expf(Wlv[(size_t)n * K + k]);
     }
     __device__ void epilogue4(int m0, int n, const float (&acc)[2][4], float (&)[4]) const {
@@ -261,8 +261,12 @@ struct MnfConvProb {
 // out[r, c, py, px] = max over the 2x2 window of relu(mean[b] + sd[b] * eps[r]),  b = r % n_unique:
 // the noise / ReLU / MaxPool2d(2) tail of an MNFConv2d whose mean and variance do not depend on the sample
 // (z is shared by the whole call, mnf_conv.py:72, so under MC replication they are per-IMAGE quantities).
+// zs (optional): per-sample channel scales [n_z, C] -- the per-sample conv-z option of the MC predict entry point
+// (SURVEY 8f-4): z scales OUTPUT channels (mnf_conv.py:73), so with mean evaluated for z = 1 row r's mean is
+// zs[r / rows_per_z, c] * mean.
 __global__ void conv_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd, int n_unique,
-                                       NoiseSrc eps, float *__restrict__ out, long long n_rows, int C, int OH, int OW) {
+                                       NoiseSrc eps, float *__restrict__ out, long long n_rows, int C, int OH, int OW,
+                                       const float *__restrict__ zs, long long rows_per_z) {
     // one thread = two horizontally adjacent pooled pixels = a 2 x 4 patch of the un-pooled map, so that each
     // Philox block (4 consecutive elements) is generated once and fully used.  Needs OW % 4 == 0 (host checks).
     const int PH = OH >> 1, PW = OW >> 1, PW2 = PW >> 1;
@@ -276,9 +280,11 @@ __global__ void conv_noise_pool_kernel(const float *__restrict__ mean, const flo
         const long long le = ((r * C + c) * OH + 2 * py) * OW + 4 * px2;  // index in the un-pooled [R, C, OH, OW]
         const long long ge = le + (long long)eps.row_offset * C * OH * OW;
         float best0 = 0.f, best1 = 0.f;  // ReLU floor
+        const float zc = zs ? zs[(r / rows_per_z) * C + c] : 1.f;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {
-            const float4 m4 = *reinterpret_cast<const float4 *>(mean + ub + dy * OW);
+            float4 m4 = *reinterpret_cast<const float4 *>(mean + ub + dy * OW);
+            m4.x *= zc, m4.y *= zc, m4.z *= zc, m4.w *= zc;
             const float4 s4 = *reinterpret_cast<const float4 *>(sd + ub + dy * OW);
             float4 n4;
             if (eps.ptr) {
@@ -352,7 +358,7 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ Wm, const flo
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Np * Kp; e += gridDim.x * blockDim.x) {
         const int n = e / Kp, k = e % Kp;
         const bool in = n < N && k < K;
-        Bm[e] = in ? rn(Wm[(size_t)n * K + k] * z[n]) : 0.f;
+        Bm[e] = in ? rn(Wm[(size_t)n * K + k] * (z ? z[n] : 1.f)) : 0.f;  // z == NULL: unit scale (per-sample z applied later)
         Bv[e] = in ? rn(expf(Wlv[(size_t)n * K + k])) : 0.f;
         if (k == 0) bvar_p[n] = n < N ? blv[n] : 0.f;
     }
@@ -432,7 +438,7 @@ extern "C" {
 int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, const float *W_log_var,
                        const float *b_log_var, float *mean_out, float *sd_out, int64_t n_imgs, int c_in, int height,
                        int width, int c_out, int ksize, void *stream) {
-    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && mean_out && sd_out, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(x && W_mean && W_log_var && b_log_var && mean_out && sd_out, MNF_E_ARG, "NULL pointer");  // z may be NULL (= 1)
     const int OH = height - ksize + 1, OW = width - ksize + 1;
     MNF_REQUIRE(n_imgs >= 0 && OH >= 1 && OW >= 1, MNF_E_SHAPE, "bad shape");
     const long long M = (long long)n_imgs * OH * OW;
@@ -452,7 +458,15 @@ int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, cons
 int mnf_conv_noise_relu_pool(const float *mean, const float *sd, int64_t n_unique, const float *eps, uint64_t seed,
                              uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_rows, int channels,
                              int out_h, int out_w, void *stream) {
+    return mnf_conv_noise_relu_pool_z(mean, sd, n_unique, eps, seed, noise_stream, row_offset, out, n_rows, channels, out_h,
+                                      out_w, nullptr, 1, stream);
+}
+
+int mnf_conv_noise_relu_pool_z(const float *mean, const float *sd, int64_t n_unique, const float *eps, uint64_t seed,
+                               uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_rows, int channels,
+                               int out_h, int out_w, const float *z_rows, int64_t rows_per_z, void *stream) {
     MNF_REQUIRE(mean && sd && out, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(rows_per_z >= 1, MNF_E_ARG, "rows_per_z must be positive");
     MNF_REQUIRE(n_rows >= 0 && n_unique >= 1 && out_h % 2 == 0 && out_w % 4 == 0, MNF_E_SHAPE,
                 "conv output %dx%d: height must be even and width a multiple of 4", out_h, out_w);
     MNF_REQUIRE(((uintptr_t)mean % 16) == 0 && ((uintptr_t)sd % 16) == 0 && (!eps || ((uintptr_t)eps % 16) == 0) &&
@@ -463,7 +477,8 @@ int mnf_conv_noise_relu_pool(const float *mean, const float *sd, int64_t n_uniqu
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     conv_noise_pool_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        mean, sd, (int)n_unique, NoiseSrc{eps, seed, noise_stream, row_offset}, out, n_rows, channels, out_h, out_w);
+        mean, sd, (int)n_unique, NoiseSrc{eps, seed, noise_stream, row_offset}, out, n_rows, channels, out_h, out_w, z_rows,
+        rows_per_z);
     return launch_status("conv_noise_pool_kernel");
 }
 
@@ -472,7 +487,7 @@ int mnf_conv_tc_stage(const float *x, const float *z, const float *W_mean, const
                       const float *b_log_var, float *a_mean, float *a_var, float *Bm, float *Bv, float *bvar_p,
                       int64_t n_imgs, int c_in, int height, int width, int c_out, int ksize, int Np, int Kp,
                       void *stream) {
-    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(x && W_mean && W_log_var && b_log_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
     MNF_REQUIRE((a_mean == nullptr) == (a_var == nullptr), MNF_E_ARG, "a_mean and a_var must both be given or both be NULL");
     const int OH = height - ksize + 1, OW = width - ksize + 1, K = c_in * ksize * ksize;
     MNF_REQUIRE(OH >= 2 && OW >= 2 && OH % 2 == 0 && OW % 2 == 0 && Kp % 4 == 0 && Kp >= K && Np >= c_out, MNF_E_SHAPE,

@@ -728,7 +728,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
 __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd,
                                             const float *__restrict__ eps, uint64_t seed, uint32_t noise_stream,
                                             uint64_t row_offset, float *__restrict__ out, long long n_imgs, int C, int Np,
-                                            int OH, int OW) {
+                                            int OH, int OW, const float *__restrict__ zs, long long rows_per_z) {
     const int PH = OH >> 1, PW = OW >> 1, GX = OW >> 2;
     const long long total = n_imgs * PH * GX * C;
     const Philox rng(seed);
@@ -740,6 +740,7 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
         const int py = (int)(t % PH);
         const long long img = t / PH;
         float best0 = 0.f, best1 = 0.f;  // ReLU folded into the max
+        const float zc = zs ? zs[(img / rows_per_z) * C + n] : 1.f;  // per-sample conv z (mean was evaluated for z = 1)
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int oy = 2 * py + r;
@@ -757,7 +758,7 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
             for (int u = 0; u < 4; ++u) {
                 const long long w = (img * PH + py) * PW + 2 * gx + (u >> 1);
                 const size_t e = (size_t)(4 * w + 2 * r + (u & 1)) * Np + n;
-                const float v = fmaf(sd[e], nz[u], mean[e]);
+                const float v = fmaf(sd[e], nz[u], zc * mean[e]);
                 if (u < 2) best0 = fmaxf(best0, v);
                 else best1 = fmaxf(best1, v);
             }
@@ -1211,7 +1212,20 @@ int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, c
                           const float *b_log_var, const float *eps, uint64_t seed, uint32_t noise_stream,
                           uint64_t row_offset, float *out, int64_t n_imgs, int c_in, int height, int width, int c_out,
                           int ksize, float *workspace, void *stream) {
-    MNF_REQUIRE(x && z && W_mean && W_log_var && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(z, MNF_E_ARG, "NULL pointer");
+    return mnf_conv2d_forward_tc_z(x, z, nullptr, 1, W_mean, W_log_var, b_log_var, eps, seed, noise_stream, row_offset, out,
+                                   n_imgs, c_in, height, width, c_out, ksize, workspace, stream);
+}
+
+// Same with an optional per-sample z: z_rows [ceil(n_imgs / rows_per_z), c_out], image r uses row r / rows_per_z
+// (z must then be NULL: the weights are packed with unit scale and the scale is applied in the noise / pool pass).
+int mnf_conv2d_forward_tc_z(const float *x, const float *z, const float *z_rows, int64_t rows_per_z, const float *W_mean,
+                            const float *W_log_var, const float *b_log_var, const float *eps, uint64_t seed,
+                            uint32_t noise_stream, uint64_t row_offset, float *out, int64_t n_imgs, int c_in, int height,
+                            int width, int c_out, int ksize, float *workspace, void *stream) {
+    MNF_REQUIRE(x && W_mean && W_log_var && b_log_var && out && workspace, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE((z != nullptr) != (z_rows != nullptr), MNF_E_ARG, "exactly one of z and z_rows must be given");
+    MNF_REQUIRE(rows_per_z >= 1, MNF_E_ARG, "rows_per_z must be positive");
     const int OH = height - ksize + 1, OW = width - ksize + 1;
     MNF_REQUIRE(OH >= 2 && OW >= 2 && OH % 2 == 0 && OW % 2 == 0, MNF_E_SHAPE, "output %dx%d must be even for the pool", OH, OW);
     MNF_REQUIRE(c_out <= tc::MAX_BN, MNF_E_SHAPE, "c_out=%d exceeds one column tile", c_out);
@@ -1233,7 +1247,7 @@ int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, c
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
         tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sdp, eps, seed, noise_stream, row_offset, out,
-                                                                       n_imgs, c_out, Np, OH, OW);
+                                                                       n_imgs, c_out, Np, OH, OW, z_rows, rows_per_z);
         return launch_status("conv_rows_noise_pool_kernel");
     }
     float *a_mean = workspace, *a_var = a_mean + (size_t)M * Kp, *sd = a_var + (size_t)M * Kp, *Bm = sd + (size_t)M * Np,
@@ -1256,9 +1270,10 @@ int mnf_conv2d_forward_tc(const float *x, const float *z, const float *W_mean, c
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
         tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sd, eps, seed, noise_stream, row_offset, out,
-                                                                       n_imgs, c_out, Np, OH, OW);
+                                                                       n_imgs, c_out, Np, OH, OW, z_rows, rows_per_z);
         return launch_status("conv_rows_noise_pool_kernel");
     }
+    MNF_REQUIRE(z_rows == nullptr, MNF_E_SHAPE, "per-sample conv z needs an output width that is a multiple of 4");
     em.mode = 5, em.sd = sd, em.sd_rows = 1, em.eps = eps, em.seed = seed, em.noise_stream = noise_stream;
     em.row_offset = row_offset, em.out = out, em.conv_c = c_out, em.conv_oh = OH, em.conv_ow = OW;
     return tc::launch(a_mean, Bm, (int)M, Np, Kp, em, st);

@@ -58,6 +58,8 @@ _SIGS = {
     "mnf_last_error": (C.c_char_p, []),
     "mnf_launch_count": (C.c_uint64, []),
     "mnf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+    "mnf_launch_stats": (C.c_int64, [C.c_char_p, C.c_int64]),
+    "mnf_launch_stats_reset": (None, []),
     "mnf_flow_stack_run": (
         C.c_int,
         [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p,
@@ -114,6 +116,21 @@ def lib():
             )
         _lib = handle
     return _lib
+
+
+def launch_stats(reset: bool = False) -> dict:
+    """{launch site (kernel name): launches since the last reset} from the library's own tally."""
+    h = lib()
+    buf = C.create_string_buffer(8192)
+    h.mnf_launch_stats(buf, 8192)
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.rsplit("=", 1)
+            out[k] = int(v)
+    if reset:
+        h.mnf_launch_stats_reset()
+    return out
 
 
 def check(rc: int, what: str) -> None:

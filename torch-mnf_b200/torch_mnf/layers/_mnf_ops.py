@@ -55,6 +55,10 @@ _lib.register({
                                    _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "mnf_conv2d_moments": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp]),
     "mnf_conv_noise_relu_pool": (_int, [_vp, _vp, _i64, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _vp]),
+    "mnf_conv_noise_relu_pool_z": (_int, [_vp, _vp, _i64, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _vp, _i64,
+                                          _vp]),
+    "mnf_conv2d_forward_tc_z": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int,
+                                       _int, _int, _int, _vp, _vp]),
     "mnf_conv_tc_workspace": (_i64, [_i64, _int, _int, _int, _int, _int]),
     "mnf_conv2d_forward_tc": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _int,
                                      _int, _vp, _vp]),
@@ -311,20 +315,22 @@ def linear_forward(layer, x, z, noise: Noise, x_rows=None, relu=False, precision
 
 
 @torch.no_grad()
-def conv_forward(layer, x, z, noise: Noise, n_imgs=None, relu_pool=False):
+def conv_forward(layer, x, z, noise: Noise, n_imgs=None, relu_pool=False, drawn=None, out=None):
+    """drawn = (eps or None, stream id, row offset): use this noise instead of drawing (a slice of a larger draw)."""
     dev = x.device
     x_imgs, c_in, H, W = x.shape
     R = n_imgs or x_imgs
     c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
     OH, OW = H - ks + 1, W - ks + 1
-    eps, sid = noise.normal((R, c_out, OH, OW))
+    eps, sid, row_offset = drawn if drawn is not None else (*noise.normal((R, c_out, OH, OW)), noise.row_offset)
     shape = (R, c_out, OH // 2, OW // 2) if relu_pool else (R, c_out, OH, OW)
-    out = torch.empty(shape, device=dev, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(shape, device=dev, dtype=torch.float32)
     args = [_param(t, dev, n) for t, n in ((layer.W_mean, "W_mean"), (layer.W_log_var, "W_log_var"),
                                            (layer.b_log_var, "b_log_var"))]
     with torch.cuda.device(dev):
         rc = _lib.lib().mnf_conv2d_forward(x.data_ptr(), x_imgs, z.data_ptr(), *(a.data_ptr() for a in args), _p(eps),
-                                           noise.seed, sid, noise.row_offset, out.data_ptr(), R, c_in, H, W, c_out, ks,
+                                           noise.seed, sid, row_offset, out.data_ptr(), R, c_in, H, W, c_out, ks,
                                            int(relu_pool), _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv2d_forward")
     _lib.launch_count += 1
@@ -337,9 +343,24 @@ def _conv_args(layer, dev):
 
 
 @torch.no_grad()
-def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows):
+def conv_sample_z_rows(layer, n_z, noise: Noise, z_offset=0):
+    """n_z independent draws of MNFConv2d.sample_z (mnf_conv.py:80-88), one per Monte-Carlo sample: [n_z, n_out].
+    Draw order: normal[n_z, n_out], then one Bernoulli[n_z, n_out] per q-flow.  Philox draws are keyed by the global
+    sample index z_offset + i, so a sharded prediction sees the z rows a single-device call would."""
+    keep, noise.row_offset = noise.row_offset, int(z_offset)
+    try:
+        z = sample_z0(layer.q0_mean, layer.q0_log_var, n_z, noise)
+        rnvp_stack_inplace(list(layer.flow_q.flows), z, noise)
+    finally:
+        noise.row_offset = keep
+    return z
+
+
+@torch.no_grad()
+def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows, z_rows=None, rows_per_z=1):
     """maxpool2(relu(MNFConv2d(x.repeat(...)))) for n_rows = len(x) * S rows: mean and variance are evaluated once
-    per distinct image (z is shared by the call), only the noise / ReLU / pool tail runs per sample."""
+    per distinct image (z is shared by the call), only the noise / ReLU / pool tail runs per sample.
+    z_rows [n_z, c_out] (with z = None): per-sample z, row r scaled by z_rows[r // rows_per_z] (SURVEY 8f-4)."""
     dev = x.device
     B, c_in, H, W = x.shape
     c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
@@ -349,21 +370,24 @@ def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows):
     args = _conv_args(layer, dev)
     lib = _lib.lib()
     with torch.cuda.device(dev):
-        rc = lib.mnf_conv2d_moments(x.data_ptr(), z.data_ptr(), *(a.data_ptr() for a in args), mean.data_ptr(),
+        rc = lib.mnf_conv2d_moments(x.data_ptr(), _p(z), *(a.data_ptr() for a in args), mean.data_ptr(),
                                     sd.data_ptr(), B, c_in, H, W, c_out, ks, _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv2d_moments")
     eps, sid = noise.normal((n_rows, c_out, OH, OW))
     out = torch.empty((n_rows, c_out, OH // 2, OW // 2), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        rc = lib.mnf_conv_noise_relu_pool(mean.data_ptr(), sd.data_ptr(), B, _p(eps), noise.seed, sid, noise.row_offset,
-                                          out.data_ptr(), n_rows, c_out, OH, OW, _lib.stream_ptr(dev))
+        rc = lib.mnf_conv_noise_relu_pool_z(mean.data_ptr(), sd.data_ptr(), B, _p(eps), noise.seed, sid, noise.row_offset,
+                                            out.data_ptr(), n_rows, c_out, OH, OW, _p(z_rows), rows_per_z,
+                                            _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv_noise_relu_pool")
+    _lib.launch_count += 2
     return out
 
 
 @torch.no_grad()
-def conv_forward_tc(layer, x, z, noise: Noise):
-    """maxpool2(relu(MNFConv2d(x))) through im2col + TF32 tensor-core GEMMs."""
+def conv_forward_tc(layer, x, z, noise: Noise, z_rows=None, rows_per_z=1):
+    """maxpool2(relu(MNFConv2d(x))) on the TF32 tensor cores (implicit GEMM, or im2col + GEMMs for other geometries).
+    z_rows [n_z, c_out] (with z = None): per-sample z, image r scaled by z_rows[r // rows_per_z]."""
     dev = x.device
     R, c_in, H, W = x.shape
     c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
@@ -374,10 +398,11 @@ def conv_forward_tc(layer, x, z, noise: Noise):
     ws = torch.empty(lib.mnf_conv_tc_workspace(R, c_in, H, W, c_out, ks), device=dev, dtype=torch.float32)
     args = _conv_args(layer, dev)
     with torch.cuda.device(dev):
-        rc = lib.mnf_conv2d_forward_tc(x.data_ptr(), z.data_ptr(), *(a.data_ptr() for a in args), _p(eps), noise.seed, sid,
-                                       noise.row_offset, out.data_ptr(), R, c_in, H, W, c_out, ks, ws.data_ptr(),
-                                       _lib.stream_ptr(dev))
+        rc = lib.mnf_conv2d_forward_tc_z(x.data_ptr(), _p(z), _p(z_rows), rows_per_z, *(a.data_ptr() for a in args),
+                                         _p(eps), noise.seed, sid, noise.row_offset, out.data_ptr(), R, c_in, H, W, c_out,
+                                         ks, ws.data_ptr(), _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv2d_forward_tc")
+    _lib.launch_count += 3
     return out
 
 

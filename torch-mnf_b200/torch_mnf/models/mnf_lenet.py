@@ -36,8 +36,15 @@ class MNFLeNet(nn.Sequential):
     precision = "auto"
     TC_MIN_ROWS = 512
 
-    def forward(self, x, noise=None, n_samples: int = 1, row_offset: int = 0, seed=None):
+    def forward(self, x, noise=None, n_samples: int = 1, row_offset: int = 0, seed=None,
+                per_sample_conv_z: bool = False):
+        """per_sample_conv_z: every Monte-Carlo sample draws its own z for the two conv layers -- what
+        ``n_samples`` separate reference calls would do (mnf_conv.py:80-88 draws one z per CALL) -- instead of sharing
+        one z across the whole replicated batch as ``model(x.repeat(n_samples, 1, 1, 1))`` does.  Draw order in this
+        mode, per conv layer: normal[S, n_out], one Bernoulli[S, n_out] per q-flow, normal[R, n_out, OH, OW]."""
         x = _lib.require_cuda_f32(x, "input")
+        if per_sample_conv_z and not _train.needs_grad(self, x):
+            return self._forward_per_sample_z(x, noise, n_samples, row_offset, seed)
         if _train.needs_grad(self, x):  # training: every layer takes its differentiable path, one shared tape
             tape = _train._tape(noise, x.device)
             h = x.repeat(n_samples, 1, 1, 1) if n_samples > 1 else x
@@ -55,6 +62,34 @@ class MNFLeNet(nn.Sequential):
         else:
             h = self[0].forward(x, nz, relu_pool=True, n_imgs=R)
             h = self[3].forward(h, nz, relu_pool=True)
+        h = h.view(R, -1)
+        prec = "fp32" if self.precision == "fp32" else None
+        h = self[7].forward(h, nz, relu=True, precision=prec)
+        h = self[9].forward(h, nz, precision=prec)
+        return torch.log_softmax(h, dim=-1)
+
+    def _forward_per_sample_z(self, x, noise, S, row_offset, seed):
+        B = x.size(0)
+        R = B * S
+        if row_offset % B:
+            raise ValueError("per-sample conv z: row_offset must be a multiple of the image count (whole samples per shard)")
+        nz = ops.Noise(noise, x.device, row_offset, seed=seed)
+        s0 = row_offset // B  # global index of this shard's first Monte-Carlo sample
+        # conv1: moments once per image with unit z (exact fp32), z[s, c] scales the mean in the noise / pool pass
+        z1 = ops.conv_sample_z_rows(self[0], S, nz, s0)
+        h = ops.conv_mc_relu_pool(self[0], x, None, nz, R, z_rows=z1, rows_per_z=B)
+        z2 = ops.conv_sample_z_rows(self[3], S, nz, s0)
+        if self.precision != "fp32":
+            h = ops.conv_forward_tc(self[3], h, None, nz, z_rows=z2, rows_per_z=B)
+        else:  # exact fp32: one launch per sample, each with its own z and its slice of the noise draw
+            c_out = self[3].n_out
+            eps, sid = nz.normal((R, c_out, 8, 8))
+            out = torch.empty((R, c_out, 4, 4), device=x.device, dtype=torch.float32)
+            for s in range(S):
+                ops.conv_forward(self[3], h[s * B:(s + 1) * B], z2[s], nz, relu_pool=True,
+                                 drawn=(None if eps is None else eps[s * B:(s + 1) * B], sid, nz.row_offset + s * B),
+                                 out=out[s * B:(s + 1) * B])
+            h = out
         h = h.view(R, -1)
         prec = "fp32" if self.precision == "fp32" else None
         h = self[7].forward(h, nz, relu=True, precision=prec)
