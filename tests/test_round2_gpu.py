@@ -110,8 +110,9 @@ def test_masked_linear_and_made_forward_standalone():
 
     cpu_params = [p.detach().clone().requires_grad_(True) for p in made.parameters()]
     xc = x.clone().requires_grad_(True)
-    ref = ref_fn(xc, cpu_params)
-    ref.square().sum().backward()
+    with torch.enable_grad():
+        ref = ref_fn(xc, cpu_params)
+        ref.square().sum().backward()
     made.cuda()
     with torch.no_grad():
         y = made(x.cuda())
