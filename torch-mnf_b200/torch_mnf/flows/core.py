@@ -52,26 +52,31 @@ class NormalizingFlow(nn.Module):
 
         return len(self.flows) > 0 and all(isinstance(f, RNVP) for f in self.flows)
 
-    def _maf_density_stack(self, v: Tensor, inverse: bool):
-        """Stacks made only of MAF (inverse) / IAF (forward) flows in their one-pass direction take the
-        tensor-core MADE chain when eligible (flows/maf.py::_use_tc)."""
-        from .maf import IAF, MAF, _use_tc
+    def _maf_density_stack(self, v: Tensor, inverse: bool, log_prob_only: bool = False, out=None):
+        """Stacks made only of MAF (inverse) / IAF (forward) flows in their one-pass direction take a tensor-core
+        path when eligible (flows/maf.py::_tc_mode): the fused persistent tcgen05 kernel for dim-64 stacks, the
+        per-layer TF32 GEMM chain otherwise.  -> (outputs list, log_det, log_prob or None) or None."""
+        from .maf import IAF, MAF, density_stack
 
         flows = list(self.flows)
         if not flows or not all(isinstance(f, MAF) for f in flows):
             return None
-        if any(isinstance(f, IAF) != (not inverse) for f in flows) or not _use_tc(flows, v):
+        if any(isinstance(f, IAF) != (not inverse) for f in flows):
             return None
-        from ..layers.made import MadeStackPlan, made_density
-
         order = flows[::-1] if inverse else flows
-        plan = self.__dict__.get("_tc_plan")
-        if plan is None or plan[0] != inverse:
-            plan = (inverse, MadeStackPlan(order))
-            self.__dict__["_tc_plan"] = plan
-        z, ld, inter = made_density(plan[1], v, want_inter=self.return_intermediates)
+        got = density_stack(order, v, self.__dict__, want_inter=self.return_intermediates and not log_prob_only,
+                            want_z=not log_prob_only, want_log_prob=log_prob_only,
+                            log_prob_out=out if (out is not None and out.is_contiguous()) else None)
+        if got is None:
+            return None
+        z, ld, inter, lp = got
+        if log_prob_only:
+            if out is not None and lp is not out:
+                out.copy_(lp)
+                lp = out
+            return None, ld, lp
         outs = [v] + (list(inter.unbind(0)) if inter is not None else [z])
-        return outs, ld
+        return outs, ld, None
 
     def _data_dependent_init(self, v: Tensor, inverse: bool) -> None:
         """ActNorm initialises itself from the first batch IT sees, i.e. the output of the flows that run before
@@ -181,6 +186,10 @@ class NormalizingFlowModel(NormalizingFlow):
         if self._base_is_std(x.size(-1)) and 0 < len(self.flows) <= _lib.MAX_OPS and not (
             torch.is_grad_enabled() and self._program().needs_grad(x)
         ):
+            if gather is None:
+                got = self._maf_density_stack(x, True, log_prob_only=True, out=out)
+                if got is not None:
+                    return got[2]
             self._data_dependent_init(x, True)
             return self._program().run(x, inverse=True, log_prob_only=True, log_prob_out=out, gather=gather)[3]
         if self._base_is_std(x.size(-1)) and len(self.flows):  # training: one differentiable pass

@@ -43,13 +43,8 @@ class MAF(Flow):
 
     def _density(self, v):
         """One-pass direction (MAF.inverse / IAF.forward)."""
-        if _use_tc([self], v):
-            from ..layers.made import MadeStackPlan, made_density
-
-            plan = self.__dict__.setdefault("_tc_plan", MadeStackPlan([self]))
-            z, ld, _ = made_density(plan, v)
-            return z, ld
-        return None
+        got = density_stack([self], v, self.__dict__, want_inter=False)
+        return None if got is None else (got[0], got[1])
 
     def inverse(self, x):
         out = self._density(x) if self._sequential_on_forward else None
@@ -66,19 +61,54 @@ class IAF(MAF):
     _sequential_on_forward = False
 
 
-def _use_tc(flows, v) -> bool:
-    """Tensor-core density path?  All flows must be eligible MAFs with the same precision policy."""
-    from ..layers.made import TC_MIN_ELEMS, made_tc_eligible
+def _tc_mode(flows, v):
+    """Which density path a stack of MAF flows takes in its one-pass direction: None = the exact-fp32 flow program,
+    "fused" = the single persistent tcgen05 kernel (dim 64, hidden <= 31: csrc/made_fused.cu), "chain" = one TF32 GEMM
+    per layer (any other eligible shape).  Both tensor-core paths are in the 2e-3 tolerance class BASELINE.json states
+    for the MADE GEMMs; ``precision = "fp32"`` on the flows keeps the exact path."""
+    from ..layers.made import FUSED_MAX_FLOWS, TC_MIN_ELEMS, made_fused_eligible, made_tc_eligible
 
     if not flows or not all(isinstance(f, MAF) and made_tc_eligible(f) for f in flows):
-        return False
+        return None
     if torch.is_grad_enabled() and (v.requires_grad or any(p.requires_grad for f in flows for p in f.parameters())):
-        return False  # training goes through the differentiable program (mnf_flow_stack_backward)
+        return None  # training goes through the differentiable program (mnf_flow_stack_backward)
     prec = {f.precision for f in flows}
-    if prec == {"fp32"}:
-        return False
+    if "fp32" in prec or not v.is_cuda:
+        return None
+    fused = (len(flows) <= FUSED_MAX_FLOWS and all(made_fused_eligible(f) for f in flows)
+             and len({len(f.net.hidden_sizes) for f in flows}) == 1)
     if prec == {"tf32"}:
-        return True
-    if all(f.dim == 64 and list(getattr(f.net, "hidden_sizes", [])) == [24, 24, 24] for f in flows):
-        return False  # the exact-fp32 constant-bank MADE kernel (made_fast.cu) beats the TF32 GEMM chain here
-    return "fp32" not in prec and v.is_cuda and v.numel() >= TC_MIN_ELEMS
+        return "fused" if fused else "chain"
+    if v.numel() < TC_MIN_ELEMS:
+        return None
+    return "fused" if fused else "chain"
+
+
+def _use_tc(flows, v) -> bool:
+    return _tc_mode(flows, v) is not None
+
+
+def density_stack(flows, v, cache, want_inter, want_z=True, want_log_prob=False, log_prob_out=None):
+    """Runs `flows` (execution order) in their one-pass direction on a tensor-core path if one applies.
+    -> (z or None, log_det, intermediates or None, log_prob or None), or None when the exact program should run.
+    `cache`: the owning module's __dict__ (packed plans are kept there, dropped by __getstate__)."""
+    mode = _tc_mode(flows, v)
+    if mode is None:
+        return None
+    from ..layers import made as M
+
+    entry = cache.get("_tc_plan")
+    ids = tuple(id(f) for f in flows)
+    if entry is None or entry[0] != (mode, ids):
+        plans = ((M.FusedMadePlan(flows, True), M.FusedMadePlan(flows, False)) if mode == "fused"
+                 else M.MadeStackPlan(flows))
+        entry = ((mode, ids), plans)
+        cache["_tc_plan"] = entry
+    if mode == "fused":
+        return M.made_density_fused(entry[1], v, want_inter=want_inter, want_z=want_z, want_log_prob=want_log_prob,
+                                    log_prob_out=log_prob_out)
+    z, ld, inter = M.made_density(entry[1], v, want_inter=want_inter)
+    lp = None
+    if want_log_prob:
+        lp = ld - 0.5 * z.square().sum(1) - 0.5 * z.size(1) * 1.8378770664093453
+    return z, ld, inter, lp

@@ -107,6 +107,9 @@ _lib.register({
     "mnf_made_workspace": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "mnf_made_density_tc": (C.c_int, [C.POINTER(MadeLayer), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "mnf_made_fused_image_floats": (C.c_int64, [C.c_int]),
+    "mnf_made_density_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 })
 
 
@@ -201,3 +204,147 @@ def made_density(plan: MadeStackPlan, x, want_inter=False):
                                      ws.data_ptr(), _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_made_density_tc")
     return z, ld, inter
+
+
+# ---------------------------------------------------------------------------------------
+# fused tcgen05 kernel for stacks of dim-64 MAF flows (mnf_made_density_fused, csrc/made_fused.cu)
+# ---------------------------------------------------------------------------------------
+FUSED_DIM, FUSED_HP, FUSED_MAX_FLOWS = 64, 32, 16
+VARIANT = 0  # 0 = library default; 10 * tiles in flight + threads per row (21, 31, 22, 32) for tuning / tests
+
+
+def made_fused_eligible(flow) -> bool:
+    net = flow.net
+    if not isinstance(net, MADE) or flow.dim != FUSED_DIM or net.n_out != 2 * FUSED_DIM:
+        return False
+    hs = list(net.hidden_sizes)
+    return 1 <= len(hs) <= MADE_MAX_HIDDEN and all(1 <= h <= FUSED_HP - 1 for h in hs)
+
+
+def _swizzled_image(W):
+    """[N, K] (K = 32 or 64) -> flat K-major, 128-byte-swizzled shared-memory image (see include/mnf_b200.h)."""
+    N, K = W.shape
+    n = torch.arange(N, device=W.device)[:, None]
+    k = torch.arange(K, device=W.device)[None, :]
+    kb, kk = k // 32, k % 32
+    off = kb * (N * 32) + (n // 8) * 256 + (n % 8) * 32 + (((kk // 4) ^ (n % 8)) * 4) + kk % 4
+    img = torch.empty(N * K, device=W.device, dtype=torch.float32)
+    img[off.reshape(-1)] = _round_tf32(W).reshape(-1)
+    return img
+
+
+class FusedMadePlan:
+    """Packed weight images of a stack of dim-64 MAF flows for mnf_made_density_fused, in execution order.
+    chained=True: one launch runs the whole stack, the parity flips folded into the following flows' weights;
+    chained=False: one launch per flow (every flow starts on an un-reversed row) -- used when the per-flow outputs
+    are wanted (core.py:20-25 returns every intermediate)."""
+
+    def __init__(self, flows, chained=True):
+        self.flows, self.chained, self.key = list(flows), chained, None
+
+    def _tensors(self):
+        return [t for f in self.flows for t in (*f.net.parameters(), *f.net.buffers())]
+
+    def build(self, device):
+        from .._program import param_epoch
+
+        ts = self._tensors()
+        key = (str(device), tuple(t._version for t in ts), tuple(t.data_ptr() for t in ts), param_epoch())
+        if key == self.key:
+            return
+        D, HP = FUSED_DIM, FUSED_HP
+        nh = {len(f.net.hidden_sizes) for f in self.flows}
+        if len(nh) != 1:
+            raise ValueError("fused MADE kernel needs the same number of hidden layers in every flow")
+        self.n_hidden = nh.pop()
+        imgs, b1s, self.reversed_after = [], [], []
+        rev = False
+        flip = torch.arange(D - 1, -1, -1, device=device)
+        with torch.no_grad():
+            for f in self.flows:
+                if not self.chained:
+                    rev = False
+                lin = [m for m in f.net if isinstance(m, MaskedLinear)]
+                ws = [(m.weight * m.mask.to(m.weight.dtype).T).to(device, torch.float32) for m in lin]
+                bs = [m.bias.to(device, torch.float32) for m in lin]
+                h = [w.size(0) for w in ws[:-1]]
+                w1 = torch.zeros(HP, D, device=device)
+                w1[: h[0]] = ws[0][:, flip] if rev else ws[0]
+                b1 = torch.zeros(HP, device=device)
+                b1[: h[0]] = bs[0]
+                parts = [_swizzled_image(w1)]
+                for l in range(1, len(h)):
+                    wp = torch.zeros(HP, HP, device=device)
+                    wp[: h[l], : h[l - 1]] = ws[l]
+                    wp[: h[l], HP - 1] = bs[l]
+                    wp[HP - 1, HP - 1] = 1.0  # keeps the constant-one column alive
+                    parts.append(_swizzled_image(wp))
+                wo, bo = ws[-1], bs[-1]  # rows: s_0..s_{D-1}, t_0..t_{D-1} (maf.py:57)
+                s_rows, t_rows, s_b, t_b = wo[:D], wo[D:], bo[:D], bo[D:]
+                if rev:
+                    s_rows, t_rows, s_b, t_b = s_rows[flip], t_rows[flip], s_b[flip], t_b[flip]
+                wop = torch.zeros(2 * D, HP, device=device)
+                wop[0::2, : h[-1]], wop[1::2, : h[-1]] = s_rows, t_rows
+                wop[0::2, HP - 1], wop[1::2, HP - 1] = s_b, t_b
+                parts.append(_swizzled_image(wop))
+                imgs.append(torch.cat(parts))
+                b1s.append(b1)
+                rev ^= bool(f.parity)  # maf.py:60: z.flip(dims=[1]) after the transform
+                self.reversed_after.append(rev)
+        self.images = torch.stack(imgs).contiguous()
+        self.b1 = torch.stack(b1s).contiguous()
+        expect = _lib.lib().mnf_made_fused_image_floats(self.n_hidden)
+        if self.images.size(1) != expect:
+            raise RuntimeError(f"weight image has {self.images.size(1)} floats, the library expects {expect}")
+        self.key = key
+
+
+@torch.no_grad()
+def made_density_fused(plans, x, want_inter=False, want_z=True, want_log_prob=False, log_prob_out=None):
+    """Density direction of a dim-64 MAF stack through the fused tcgen05 kernel.
+    plans = (chained plan, per-flow plan).  -> (z or None, log_det, intermediates or None, log_prob or None)."""
+    x = _lib.require_cuda_f32(x, "input")
+    dev = x.device
+    B, D = x.shape
+    lib = _lib.lib()
+    stream = _lib.stream_ptr(dev)
+    ld = torch.empty(B, device=dev, dtype=torch.float32)
+
+    def launch(plan, lo, hi, src, dst, ld_out, lp_out, rev_before):
+        # flows [lo, hi) of the plan; rev_before: orientation the packer assumed at flow lo (chained plans only)
+        rc = lib.mnf_made_density_fused(plan.images[lo:hi].data_ptr(), plan.b1[lo:hi].data_ptr(), hi - lo, plan.n_hidden,
+                                        int(plan.reversed_after[hi - 1]), src.data_ptr(), _lib.ptr(dst), _lib.ptr(ld_out),
+                                        _lib.ptr(lp_out), B, D, VARIANT, stream)
+        _lib.check(rc, "mnf_made_density_fused")
+        _lib.launch_count += 1
+
+    with _lib.on_device(dev):
+        if want_inter:
+            plan = plans[1]
+            plan.build(dev)
+            n = len(plan.flows)
+            inter = torch.empty((n, B, D), device=dev, dtype=torch.float32)
+            tmp = torch.empty(B, device=dev, dtype=torch.float32)
+            src = x
+            for i in range(n):
+                launch(plan, i, i + 1, src, inter[i], ld if i == 0 else tmp, None, False)
+                if i:
+                    ld += tmp
+                src = inter[i]
+            lp = None
+            if want_log_prob:
+                zf = inter[-1]
+                lp = ld - 0.5 * zf.square().sum(1) - 0.5 * D * 1.8378770664093453
+            return inter[-1], ld, inter, lp
+        plan = plans[0]
+        plan.build(dev)
+        n = len(plan.flows)
+        if n <= FUSED_MAX_FLOWS:
+            z = torch.empty_like(x) if want_z else None
+            lp = None
+            if want_log_prob:
+                lp = log_prob_out if log_prob_out is not None else torch.empty(B, device=dev, dtype=torch.float32)
+            launch(plan, 0, n, x, z, ld, lp, False)
+            return z, ld, None, lp
+    # longer stacks: chunks of <= 16 flows, each chunk packed as its own chained plan (orientation restarts per chunk)
+    raise NotImplementedError(f"fused MADE kernel: stacks of more than {FUSED_MAX_FLOWS} flows are not packed yet")
