@@ -286,7 +286,7 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
  * reach HBM; traffic is the algorithmic 516 B/row.  Hidden widths <= 31 (column 31 of every padded hidden layer is a
  * constant one that carries the next layer's bias), 1..4 hidden layers, <= 16 flows per call.
  *   weight_images: per flow, mnf_made_fused_image_floats(n_hidden) floats: W1 [32, 64] | hidden [32, 32] x (n_hidden-1) |
- *     W_out [128, 32] (rows interleaved s_0, t_0, s_1, ...), each TF32-rounded and laid out as the K-major, 128-byte-swizzled
+ *     W_out [128, 32] (rows interleaved s_0, t_0, s_1, ...; the s rows and their biases pre-multiplied by log2(e)), each TF32-rounded and laid out as the K-major, 128-byte-swizzled
  *     shared-memory image the UMMA descriptor reads (K-blocks of 32 floats; element (n, k) of a block at float offset
  *     (n/8)*256 + (n%8)*32 + (((k/4) ^ (n%8))*4) + k%4), so that one bulk copy per flow stages it.  The parity flips of
  *     maf.py:60 are folded in by the packer: a flow that runs on a reversed row has its input columns and output pairs

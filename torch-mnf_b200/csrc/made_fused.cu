@@ -7,9 +7,9 @@
 // One CTA per SM, 512 threads:
 //   warp 0      weight producer: one cp.async.bulk per flow brings the flow's four pre-swizzled weight matrices (32 KB,
 //               packed once per parameter version by the host) into a 2-slot shared-memory ring
-//   warp 1      MMA issuer: one thread issues every tcgen05.mma.kind::tf32 (M128; N32 for the hidden layers, N128 for
-//               the (s, t) output layer) round-robin over the tiles in flight; tcgen05.commit publishes accumulators
-//   warp 2      TMEM allocator (512 columns; a tile's four layers alias the same 128 columns)
+//   warps 1-3   MMA issuers, one per tile in flight: one thread each issues its tile's tcgen05.mma.kind::tf32 (M128; N32 for
+//               the hidden layers, N128 for the (s, t) output layer); tcgen05.commit publishes the accumulator
+//   warp 2      also the TMEM allocator (512 columns; a tile's four layers alias the same 128 columns)
 //   warps 4-15  three epilogue groups of 128 threads, one 128-row tile in flight each.  A thread owns one row: its 64
 //               exact fp32 coordinates stay in REGISTERS across all flows.  Per layer it reads its accumulator row
 //               with tcgen05.ld, applies bias / ReLU, rounds to TF32 and writes the row into the 128-byte-swizzled
@@ -18,6 +18,8 @@
 // The tile arrives by TMA (two 128 x 32 boxes) and the result leaves by TMA store; HBM traffic is the algorithmic
 // 516 B/row.  The parity flips (maf.py:60) are folded into the packed weights (a reversed flow has its input columns and
 // output pairs permuted), so nothing is permuted on chip; only the final store may reverse the row.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace mnf {
@@ -53,7 +55,7 @@ struct Layout {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 constexpr uint32_t IDESC_H = tf32_instr_desc(BM, HP), IDESC_O = tf32_instr_desc(BM, 2 * D);
-constexpr float LOG2E = 1.4426950408889634f, HALF_LOG_2PI = 0.9189385332046727f;
+constexpr float LN2 = 0.6931471805599453f, HALF_LOG_2PI = 0.9189385332046727f;
 
 struct Params {
     const float *wimg;  // [n_flows][flow_floats] pre-swizzled weight images (device)
@@ -62,6 +64,7 @@ struct Params {
     float *log_prob;    // [n_rows] or NULL: log_det + standard-normal log-density of the result
     long long n_rows;
     int n_flows, n_hidden, final_reversed, store_z;
+    int debug;  // timing experiments only (MNF_MADE_DEBUG): 1 = no proxy fence, 2 = no operand stores, 4 = no MMAs, 8 = no epilogue math
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -71,6 +74,23 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 }
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// round-to-nearest TF32 for an operand the tensor core will truncate: adding half a TF32 ulp to the bit pattern and
+// letting the MMA drop the low 13 bits is cvt.rna (ties away from zero) in ONE integer add; the cvt instruction itself
+// expands to four (it also handles inf / nan, which cannot survive a flow anyway)
+__device__ __forceinline__ float rnt(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of re-issuing try_wait in a tight loop:
+// the 24 epilogue warps of a CTA spend most of their time here and their spinning competes for issue slots
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
 }
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -121,7 +141,7 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(w_full(s), 1);
-            mbar_init(w_empty(s), 1);
+            mbar_init(w_empty(s), T);  // one arrival per issuer
         }
         for (int t = 0; t < T; ++t) {
             mbar_init(in_full(t), 1);
@@ -153,47 +173,52 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     bulk_load(base + OFF_W + ws * WSLOT, p.wimg + (size_t)f * (flow_bytes / 4), flow_bytes, w_full(ws));
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ---------------- MMA issuer ----------------
-            uint32_t wcount = 0, a_ph = 0;  // bit t of a_ph: phase of a_ready[t]
+        } else if (warp >= 1 && warp <= T && lane == 0) {
+            // ---------------- MMA issuers: one per tile slot, so the tiles' layer chains run independently ----------------
+            // (a single issuer walking the tiles round-robin kept them in lockstep: its per-tile wake-up / descriptor /
+            // commit latency was paid T times per layer and the MMA time never overlapped the epilogues)
+            const int t = warp - 1;
+            const uint32_t d = tmem_base + (uint32_t)(t * 128);
+            const uint64_t az = make_smem_desc(base + t * Z_BYTES), ah = make_smem_desc(base + OFF_H + t * H_BYTES);
+            uint32_t wcount = 0, a_ph = 0;
 #pragma unroll 1
-            for (int j0 = 0; j0 < my_tiles; j0 += T) {
-                const int n_active = my_tiles - j0 < T ? my_tiles - j0 : T;
+            const int iters = (my_tiles + T - 1) / T;
+            for (int i = 0; i < iters; ++i) {              // every issuer walks the same (iteration, flow) sequence ...
+                const bool active = i * T + t < my_tiles;  // ... idle ones only keep the weight-ring counts right
 #pragma unroll 1
                 for (int f = 0; f < F; ++f, ++wcount) {
                     const int ws = wcount & 1;
+                    if (!active) {
+                        mbar_wait(w_full(ws), (wcount >> 1) & 1u);
+                        mbar_arrive(w_empty(ws));
+                        continue;
+                    }
                     mbar_wait(w_full(ws), (wcount >> 1) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t wb = base + OFF_W + ws * WSLOT;
+                    const uint64_t b1d = make_smem_desc(wb);
 #pragma unroll 1
                     for (int l = 0; l <= NH; ++l) {
-#pragma unroll 1
-                        for (int t = 0; t < n_active; ++t) {
-                            mbar_wait(a_ready(t), (a_ph >> t) & 1u);
-                            a_ph ^= 1u << t;
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t d = tmem_base + (uint32_t)(t * 128);
-                            if (l == 0) {
-                                const uint64_t a0 = make_smem_desc(base + t * Z_BYTES), b0 = make_smem_desc(wb);
+                        mbar_wait_parked(a_ready(t), a_ph);
+                        a_ph ^= 1u;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (p.debug & 4) {
+                        } else if (l == 0) {
 #pragma unroll
-                                for (int k = 0; k < D / UMMA_K; ++k) {
-                                    // k-block kb = k / 4 (16 KB apart in A, 4 KB in B), 32 B per k-step inside the swizzle atom
-                                    const uint64_t ao = (uint64_t)((k >> 2) * (ZBLK >> 4) + 2 * (k & 3));
-                                    const uint64_t bo = (uint64_t)((k >> 2) * ((HP * 128) >> 4) + 2 * (k & 3));
-                                    umma_tf32(d, a0 + ao, b0 + bo, k != 0, IDESC_H);
-                                }
-                            } else {
-                                const uint64_t a0 = make_smem_desc(base + OFF_H + t * H_BYTES);
-                                const uint64_t b0 = make_smem_desc(wb + W1_BYTES + (uint32_t)(l - 1) * WH_BYTES);
-                                const uint32_t idesc = l == NH ? IDESC_O : IDESC_H;
-#pragma unroll
-                                for (int k = 0; k < HP / UMMA_K; ++k)
-                                    umma_tf32(d, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), k != 0, idesc);
+                            for (int k = 0; k < D / UMMA_K; ++k) {
+                                // k-block kb = k / 4 (16 KB apart in A, 4 KB in B), 32 B per k-step inside the swizzle atom
+                                const uint64_t ao = (uint64_t)((k >> 2) * (ZBLK >> 4) + 2 * (k & 3));
+                                const uint64_t bo = (uint64_t)((k >> 2) * ((HP * 128) >> 4) + 2 * (k & 3));
+                                umma_tf32(d, az + ao, b1d + bo, k != 0, IDESC_H);
                             }
-                            umma_commit(acc_ready(t));
+                        } else {
+                            const uint64_t b0 = b1d + (uint64_t)((W1_BYTES + (uint32_t)(l - 1) * WH_BYTES) >> 4);
+                            const uint32_t idesc = l == NH ? IDESC_O : IDESC_H;
+#pragma unroll
+                            for (int k = 0; k < HP / UMMA_K; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), k != 0, idesc);
                         }
+                        umma_commit(acc_ready(t));
                     }
-                    umma_commit(w_empty(ws));  // every MMA that read this weight slot has completed when this fires
+                    umma_commit(w_empty(ws));  // this issuer's reads of the weight slot have completed when this fires
                 }
             }
         }
@@ -218,7 +243,7 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             return zrow + (uint32_t)(cc >> 3) * ZBLK + (((uint32_t)(cc & 7) ^ swz) << 4);
         };
         auto publish = [&]() {  // operand rows written: make them visible to the tensor core, one arrival per warp
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (!(p.debug & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready(slot));
@@ -233,14 +258,14 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll 1
         for (; tile < n_tiles; tile += T * (int)gridDim.x) {
             float z[DPT];
-            mbar_wait(in_full(slot), in_phase);
+            mbar_wait_parked(in_full(slot), in_phase);
             in_phase ^= 1u;
 #pragma unroll
             for (int i = 0; i < ZC; ++i) {
                 const uint32_t a = zaddr(i);
                 const float4 v = lds128(a);
                 z[4 * i] = v.x, z[4 * i + 1] = v.y, z[4 * i + 2] = v.z, z[4 * i + 3] = v.w;
-                sts128(a, rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+                sts128(a, rnt(v.x), rnt(v.y), rnt(v.z), rnt(v.w));
             }
             publish();
             float ld4[4] = {0.f, 0.f, 0.f, 0.f};  // four partial sums: the additions must not form one dependent chain
@@ -248,7 +273,7 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             for (int f = 0; f < F; ++f) {
 #pragma unroll 1
                 for (int l = 0; l < NH; ++l) {
-                    mbar_wait(acc_ready(slot), acc_phase);
+                    mbar_wait_parked(acc_ready(slot), acc_phase);
                     acc_phase ^= 1u;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -256,23 +281,31 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         const int col0 = 16 * (part * (2 / S) + g);
                         uint32_t r[16];
                         tmem_ld16(trow + (uint32_t)col0, r);
-                        const float4 *bb = reinterpret_cast<const float4 *>(sb1 + f * HP + col0);
+                        if (p.debug & 8) {
+                        } else if (l == 0) {
+                            const float4 *bb = reinterpret_cast<const float4 *>(sb1 + f * HP + col0);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (l == 0) b = bb[c];
-                            const float h0 = rn_tf32(fmaxf(__uint_as_float(r[4 * c]) + b.x, 0.f));
-                            const float h1 = rn_tf32(fmaxf(__uint_as_float(r[4 * c + 1]) + b.y, 0.f));
-                            const float h2 = rn_tf32(fmaxf(__uint_as_float(r[4 * c + 2]) + b.z, 0.f));
-                            float h3 = rn_tf32(fmaxf(__uint_as_float(r[4 * c + 3]) + b.w, 0.f));
-                            if (l == 0 && col0 + 4 * c + 3 == HP - 1) h3 = 1.f;  // the constant-one column that carries the later biases
-                            sts128(hrow + (((uint32_t)(col0 / 4 + c) ^ swz) << 4), h0, h1, h2, h3);
+                            for (int c = 0; c < 4; ++c) {
+                                const float4 b = bb[c];
+                                const float h0 = rnt(fmaxf(__uint_as_float(r[4 * c]) + b.x, 0.f));
+                                const float h1 = rnt(fmaxf(__uint_as_float(r[4 * c + 1]) + b.y, 0.f));
+                                const float h2 = rnt(fmaxf(__uint_as_float(r[4 * c + 2]) + b.z, 0.f));
+                                float h3 = rnt(fmaxf(__uint_as_float(r[4 * c + 3]) + b.w, 0.f));
+                                if (col0 + 4 * c + 3 == HP - 1) h3 = 1.f;  // the constant-one column that carries the later biases
+                                sts128(hrow + (((uint32_t)(col0 / 4 + c) ^ swz) << 4), h0, h1, h2, h3);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                sts128(hrow + (((uint32_t)(col0 / 4 + c) ^ swz) << 4), rnt(fmaxf(__uint_as_float(r[4 * c]), 0.f)),
+                                       rnt(fmaxf(__uint_as_float(r[4 * c + 1]), 0.f)), rnt(fmaxf(__uint_as_float(r[4 * c + 2]), 0.f)),
+                                       rnt(fmaxf(__uint_as_float(r[4 * c + 3]), 0.f)));
                         }
                     }
                     publish();
                 }
                 // output layer: 128 accumulator columns = 64 (s, t) pairs; z_i = x_i exp(s_i) + t_i (maf.py:58), log_det += sum s (maf.py:61)
-                mbar_wait(acc_ready(slot), acc_phase);
+                mbar_wait_parked(acc_ready(slot), acc_phase);
                 acc_phase ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool last = f == F - 1;
@@ -280,17 +313,18 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 for (int g = 0; g < 8 / S; ++g) {  // 16 accumulator columns = 8 (s, t) pairs = 8 dims per load
                     uint32_t r[16];
                     tmem_ld16(trow + (uint32_t)(part * (128 / S) + g * 16), r);
+                    if (p.debug & 8) continue;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const float sv = __uint_as_float(r[2 * u]), tv = __uint_as_float(r[2 * u + 1]);
-                        z[8 * g + u] = fmaf(z[8 * g + u], ex2(sv * LOG2E), tv);
+                        z[8 * g + u] = fmaf(z[8 * g + u], ex2(sv), tv);  // the packer scaled the s rows by log2(e)
                         ld4[u & 3] += sv;
                     }
                     if (!last) {
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             const int i = 2 * g + c;
-                            sts128(zaddr(i), rn_tf32(z[4 * i]), rn_tf32(z[4 * i + 1]), rn_tf32(z[4 * i + 2]), rn_tf32(z[4 * i + 3]));
+                            sts128(zaddr(i), rnt(z[4 * i]), rnt(z[4 * i + 1]), rnt(z[4 * i + 2]), rnt(z[4 * i + 3]));
                         }
                     }
                 }
@@ -298,7 +332,7 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 else asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
             // ---- results ----
-            float ld = (ld4[0] + ld4[1]) + (ld4[2] + ld4[3]), ss = 0.f;
+            float ld = ((ld4[0] + ld4[1]) + (ld4[2] + ld4[3])) * LN2, ss = 0.f;  // the accumulators hold s * log2(e)
             if (p.log_prob) {
 #pragma unroll
                 for (int i = 0; i < DPT; ++i) ss = fmaf(z[i], z[i], ss);
@@ -393,7 +427,9 @@ int mnf_made_density_fused(const float *wimg, const float *b1, int n_flows, int 
     if (rc) return rc;
     rc = tc::make_map(&mz, z ? z : x, (int)n_rows, dim, tc::BM);
     if (rc) return rc;
-    madef::Params p{wimg, b1, log_det, log_prob, (long long)n_rows, n_flows, n_hidden, final_reversed, z ? 1 : 0};
+    const char *dbg = getenv("MNF_MADE_DEBUG");
+    madef::Params p{wimg, b1, log_det, log_prob, (long long)n_rows, n_flows, n_hidden, final_reversed, z ? 1 : 0,
+                    dbg ? atoi(dbg) : 0};
     const long long n_tiles = (n_rows + tc::BM - 1) / tc::BM;
     const unsigned grid = (unsigned)(n_tiles < dp->sm_count ? n_tiles : dp->sm_count);
     cudaStream_t st = (cudaStream_t)stream;

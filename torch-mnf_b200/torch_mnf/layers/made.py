@@ -210,6 +210,7 @@ def made_density(plan: MadeStackPlan, x, want_inter=False):
 # fused tcgen05 kernel for stacks of dim-64 MAF flows (mnf_made_density_fused, csrc/made_fused.cu)
 # ---------------------------------------------------------------------------------------
 FUSED_DIM, FUSED_HP, FUSED_MAX_FLOWS = 64, 32, 16
+LOG2E = 1.4426950408889634
 VARIANT = 0  # 0 = library default; 10 * tiles in flight + threads per row (21, 31, 22, 32) for tuning / tests
 
 
@@ -284,8 +285,9 @@ class FusedMadePlan:
                 if rev:
                     s_rows, t_rows, s_b, t_b = s_rows[flip], t_rows[flip], s_b[flip], t_b[flip]
                 wop = torch.zeros(2 * D, HP, device=device)
-                wop[0::2, : h[-1]], wop[1::2, : h[-1]] = s_rows, t_rows
-                wop[0::2, HP - 1], wop[1::2, HP - 1] = s_b, t_b
+                # the s rows carry log2(e): the kernel evaluates exp(s) as ex2(s') and rescales the log-det sum by ln 2
+                wop[0::2, : h[-1]], wop[1::2, : h[-1]] = s_rows * LOG2E, t_rows
+                wop[0::2, HP - 1], wop[1::2, HP - 1] = s_b * LOG2E, t_b
                 parts.append(_swizzled_image(wop))
                 imgs.append(torch.cat(parts))
                 b1s.append(b1)
