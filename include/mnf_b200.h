@@ -281,22 +281,25 @@ int mnf_made_density_tc(const mnf_made_layer *layers_host, int n_flows, const fl
                         float *log_det, float *intermediates /* optional [n_flows, n_rows, dim] */,
                         int64_t n_rows, int dim, float *workspace, void *stream);
 /* The same direction for a whole stack of dim-64 MAF flows as ONE persistent tcgen05 kernel (csrc/made_fused.cu): a
- * 128-row tile arrives by TMA, every thread of an epilogue group keeps one row's 64 exact coordinates in registers
- * across ALL flows, the hidden activations travel TMEM -> registers -> shared memory (the next MMA's operand) and never
- * reach HBM; traffic is the algorithmic 516 B/row.  Hidden widths <= 31 (column 31 of every padded hidden layer is a
- * constant one that carries the next layer's bias), 1..4 hidden layers, <= 16 flows per call.
- *   weight_images: per flow, mnf_made_fused_image_floats(n_hidden) floats: W1 [32, 64] | hidden [32, 32] x (n_hidden-1) |
- *     W_out [128, 32] (rows interleaved s_0, t_0, s_1, ...; the s rows and their biases pre-multiplied by log2(e)), each TF32-rounded and laid out as the K-major, 128-byte-swizzled
- *     shared-memory image the UMMA descriptor reads (K-blocks of 32 floats; element (n, k) of a block at float offset
- *     (n/8)*256 + (n%8)*32 + (((k/4) ^ (n%8))*4) + k%4), so that one bulk copy per flow stages it.  The parity flips of
- *     maf.py:60 are folded in by the packer: a flow that runs on a reversed row has its input columns and output pairs
- *     permuted; final_reversed says whether the last flow leaves the row reversed (the final store undoes it).
+ * 128-row tile arrives by TMA, every thread of an epilogue group keeps (half of) one row's exact fp32 coordinates in
+ * registers across ALL flows, the hidden activations travel TMEM -> registers -> shared memory (the next MMA's operand)
+ * and never reach HBM; traffic is the algorithmic 516 B/row.  Hidden widths <= 31 (column 31 of every padded hidden layer
+ * is a constant one that carries the next layer's bias), 1..4 hidden layers, <= 16 flows per call.  MMA operands are
+ * fp16 (kind::f16, fp32 accumulation): the 11-bit significand of TF32 at half the shared-memory traffic, which is what
+ * bounds the kernel; operands saturate at +-65504, the running point stays exact fp32.
+ *   weight_images: per flow, mnf_made_fused_image_bytes(n_hidden) bytes of fp16: W1 [32, 64] | hidden [32, 32] x
+ *     (n_hidden-1) | W_out [128, 32] (rows interleaved s_0, t_0, s_1, ...; the s rows and their biases pre-multiplied
+ *     by log2(e)), every matrix stored as rows of 128 bytes (K padded to 64 with zeros) in the K-major, 128-byte-swizzled
+ *     shared-memory image the UMMA descriptor reads: element (n, k) at fp16 offset (n/8)*512 + (n%8)*64 + (((k/8) ^
+ *     (n%8))*8) + k%8, so that one bulk copy per flow stages it.  The parity flips of maf.py:60 are folded in by the
+ *     packer: a flow that runs on a reversed row has its input columns and output pairs permuted; final_reversed says
+ *     whether the last flow leaves the row reversed (the final store undoes it).
  *   b1: [n_flows, 32] first-layer biases (exact fp32, added in the epilogue).
  *   z / log_det / log_prob: any may be NULL; log_prob = log_det + standard-normal log-density of z.
- *   variant: 0 = default, or 10 * (tiles in flight per CTA) + (threads per row): 21, 31, 22, 32 (tuning / tests).
+ *   variant: 0 = default, or 10 * (tiles in flight per CTA) + (threads per row): 21, 31, 41, 32 (tuning / tests).
  * Tolerance class: tensor-core GEMM (2e-3). */
-int64_t mnf_made_fused_image_floats(int n_hidden);
-int mnf_made_density_fused(const float *weight_images, const float *b1, int n_flows, int n_hidden, int final_reversed,
+int64_t mnf_made_fused_image_bytes(int n_hidden);
+int mnf_made_density_fused(const void *weight_images, const float *b1, int n_flows, int n_hidden, int final_reversed,
                            const float *x, float *z, float *log_det, float *log_prob, int64_t n_rows, int dim,
                            int variant, void *stream);
 /* 1 if (A, W, M, N, K) can take the tensor-core path (alignment / shape), else 0.  Host-only. */

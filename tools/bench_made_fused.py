@@ -29,7 +29,7 @@ def t_ms(fn, iters=10, warm=3):
 
 
 out = {}
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [32, 22, 31, 21]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [41, 32, 31, 21]
 for tiles in variants:
     made.VARIANT = tiles
     ms = t_ms(lambda: model.inverse(x))

@@ -4,20 +4,28 @@
 // Shape class: dim 64, hidden widths <= 31 (padded to 32; column 31 is a constant one that carries the biases), 1..4
 // hidden layers, up to 16 flows -- BASELINE config 3 is 9 x MADE(64-24-24-24-128).
 //
-// One CTA per SM, 512 threads:
-//   warp 0      weight producer: one cp.async.bulk per flow brings the flow's four pre-swizzled weight matrices (32 KB,
-//               packed once per parameter version by the host) into a 2-slot shared-memory ring
-//   warps 1-3   MMA issuers, one per tile in flight: one thread each issues its tile's tcgen05.mma.kind::tf32 (M128; N32 for
-//               the hidden layers, N128 for the (s, t) output layer); tcgen05.commit publishes the accumulator
-//   warp 2      also the TMEM allocator (512 columns; a tile's four layers alias the same 128 columns)
-//   warps 4-15  three epilogue groups of 128 threads, one 128-row tile in flight each.  A thread owns one row: its 64
-//               exact fp32 coordinates stay in REGISTERS across all flows.  Per layer it reads its accumulator row
-//               with tcgen05.ld, applies bias / ReLU, rounds to TF32 and writes the row into the 128-byte-swizzled
-//               K-major operand tile of the next MMA (fence.proxy.async + mbarrier); after the output layer it applies
-//               z_i = x_i exp(s_i) + t_i, adds s_i to its log-det and restages tf32(z) for the next flow.
-// The tile arrives by TMA (two 128 x 32 boxes) and the result leaves by TMA store; HBM traffic is the algorithmic
-// 516 B/row.  The parity flips (maf.py:60) are folded into the packed weights (a reversed flow has its input columns and
-// output pairs permuted), so nothing is permuted on chip; only the final store may reverse the row.
+// Operand precision: fp16 (tcgen05.mma.kind::f16, fp32 accumulation in TMEM).  fp16 has the 11-bit significand of TF32,
+// i.e. the same 2e-3 tolerance class BASELINE.json states for the MADE GEMMs, at half the bytes: the kernel is bound by
+// shared-memory bandwidth (operand tiles written by the epilogue threads and read by the tensor core), and the TF32
+// version of this kernel measured 1.8x slower (profiles/r02_made_fused_history.md).  Operands are converted with
+// round-to-nearest and saturate at +-65504; the running point z itself stays in exact fp32 registers.
+//
+// One CTA per SM, T tiles of 128 rows in flight, S threads per row:
+//   warps 0..T-1   MMA issuers, one per tile: a single thread issues the tile's MMAs (M128; N32 for the hidden layers,
+//                  N128 for the (s, t) output layer) and commits the accumulator to an mbarrier.  Separate issuers keep
+//                  the tiles' layer chains independent, so one tile's MMAs overlap the other tiles' epilogues.  Issuer 0
+//                  also streams the weights: one cp.async.bulk per flow brings the flow's pre-swizzled fp16 matrices
+//                  (packed once per parameter version by the host) into a 2-slot shared-memory ring.
+//   warp 2         also the TMEM allocator (512 columns; a tile's layers alias the same 128 columns)
+//   warps 4..      T epilogue groups of S x 128 threads.  A thread owns (1/S of) one row: the exact fp32 coordinates stay
+//                  in REGISTERS across all flows.  Per layer it reads its accumulator columns with tcgen05.ld, applies
+//                  bias / ReLU, converts to fp16 and writes them into the 128-byte-swizzled K-major operand tile of the
+//                  next MMA (fence.proxy.async + mbarrier); after the output layer it applies z_i = x_i exp(s_i) + t_i,
+//                  adds s_i to its log-det and restages fp16(z) for the next flow.
+// A tile arrives by TMA (two 128 x 32 fp32 boxes) and leaves by TMA store from the same 32 KB region, which holds the
+// operand tiles in between; HBM traffic is the algorithmic 516 B/row.  The parity flips (maf.py:60) are folded into the
+// packed weights (a reversed flow has its input columns and output pairs permuted), so nothing is permuted on chip; only
+// the final store may reverse the row.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -27,44 +35,49 @@ namespace madef {
 using namespace tc;
 
 constexpr int D = 64, HP = 32, MAX_FLOWS = 16, MAX_HIDDEN = 4;
-constexpr uint32_t ZBLK = BM * 32 * 4;          // one K-block of the point tile: 128 rows x 128 B
-constexpr uint32_t Z_BYTES = 2 * ZBLK;          // 128 x 64 fp32
-constexpr uint32_t H_BYTES = BM * HP * 4;       // 128 x 32 hidden activations
-constexpr uint32_t W1_BYTES = HP * D * 4;       // [32, 64] as two K-blocks of [32 x 32]
-constexpr uint32_t WH_BYTES = HP * HP * 4;      // [32, 32]
-constexpr uint32_t WO_BYTES = 2 * D * HP * 4;   // [128, 32], rows interleaved (s_0, t_0, s_1, t_1, ...)
+constexpr uint32_t ZBLK = BM * 32 * 4;      // one fp32 K-block of the staged tile: 128 rows x 128 B
+constexpr uint32_t TILE_BYTES = 2 * ZBLK;   // per tile slot: fp32 staging [128 x 64]; later fp16 z [128 x 64] | fp16 h [128 x 32 (+32 pad)]
+constexpr uint32_t OPER_H = ZBLK;           // offset of the hidden-activation operand inside the slot
+constexpr uint32_t W1_BYTES = HP * 128;     // [32 rows x 64 fp16]
+constexpr uint32_t WH_BYTES = HP * 128;     // [32 rows x 32 fp16, rows padded to 128 B]
+constexpr uint32_t WO_BYTES = 2 * D * 128;  // [128 rows x 32 fp16, padded], rows interleaved (s_0, t_0, s_1, t_1, ...)
 constexpr uint32_t WSLOT = W1_BYTES + (MAX_HIDDEN - 1) * WH_BYTES + WO_BYTES;
 // T = tiles in flight per CTA (one epilogue group each), S = threads per row (the S warps with the same warp % 4 split a
 // row's columns).  Register split between the 4 control warps and the epilogue warps (setmaxnreg; 0 = leave as compiled):
-//   T S  threads  control / epilogue registers
-//   2 1    384       56 / 224
-//   3 1    512       56 / 152
-//   2 2    640       40 / 104   (the CTA is launched with 640 x 96 registers: 128 x 56 freed = 512 x 14 -> +8)
-//   3 2    896       -- / 72 (uniform)
+//   T S  threads  launch regs  control / epilogue registers
+//   2 1    384       168            56 / 224
+//   3 1    512       128            56 / 152
+//   4 1    640        96            32 / 112
+//   3 2    896        72            -- / 72 (uniform)
 template <int T, int S>
 struct Layout {
     static constexpr int THREADS = 128 + T * S * 128;
-    static constexpr int REG_CTRL = (S == 1) ? 56 : (T == 2 ? 40 : 0);
-    static constexpr int REG_EPI = (S == 1) ? (T == 2 ? 224 : 152) : (T == 2 ? 104 : 0);
+    static constexpr int REG_CTRL = (S == 2) ? 0 : (T == 4 ? 32 : 56);
+    static constexpr int REG_EPI = (S == 2) ? 0 : (T == 2 ? 224 : (T == 3 ? 152 : 112));
     // registers the CTA holds at launch (per-thread count rounded down to a multiple of 8) must cover the split
     static constexpr int REG_LAUNCH = (65536 / THREADS) / 8 * 8;
     static_assert(REG_EPI == 0 || 128 * REG_CTRL + (THREADS - 128) * REG_EPI <= THREADS * REG_LAUNCH, "setmaxnreg split exceeds the CTA's registers");
-    static constexpr uint32_t OFF_H = T * Z_BYTES, OFF_W = OFF_H + T * H_BYTES, OFF_B1 = OFF_W + 2 * WSLOT,
-                              OFF_RED = OFF_B1 + MAX_FLOWS * HP * 4, OFF_BAR = OFF_RED + T * 256 * 4,
-                              SMEM_BYTES = OFF_BAR + 256 + 1024;
+    static_assert(T <= 4, "one issuer warp per tile slot");
+    static constexpr uint32_t OFF_W = T * TILE_BYTES, OFF_B1 = OFF_W + 2 * WSLOT, OFF_RED = OFF_B1 + MAX_FLOWS * HP * 4,
+                              OFF_BAR = OFF_RED + T * 256 * 4, SMEM_BYTES = OFF_BAR + 256 + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
-constexpr uint32_t IDESC_H = tf32_instr_desc(BM, HP), IDESC_O = tf32_instr_desc(BM, 2 * D);
+// tcgen05 instruction descriptor, kind::f16: D = F32 (1 << 4), A = B = F16 (format 0), both K-major
+__host__ __device__ constexpr uint32_t f16_instr_desc(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+constexpr uint32_t IDESC_H = f16_instr_desc(BM, HP), IDESC_O = f16_instr_desc(BM, 2 * D);
+constexpr int UK = 16;  // K per kind::f16 MMA (32 bytes)
 constexpr float LN2 = 0.6931471805599453f, HALF_LOG_2PI = 0.9189385332046727f;
 
 struct Params {
-    const float *wimg;  // [n_flows][flow_floats] pre-swizzled weight images (device)
+    const void *wimg;   // [n_flows][flow_bytes] pre-swizzled fp16 weight images (device)
     const float *b1;    // [n_flows][32] first-layer biases (device)
     float *log_det;     // [n_rows] or NULL
     float *log_prob;    // [n_rows] or NULL: log_det + standard-normal log-density of the result
     long long n_rows;
     int n_flows, n_hidden, final_reversed, store_z;
-    int debug;  // timing experiments only (MNF_MADE_DEBUG): 1 = no proxy fence, 2 = no operand stores, 4 = no MMAs, 8 = no epilogue math
+    int debug;  // timing experiments only (MNF_MADE_DEBUG): 1 = no proxy fence, 4 = no MMAs, 8 = no epilogue math
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -75,12 +88,17 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-// round-to-nearest TF32 for an operand the tensor core will truncate: adding half a TF32 ulp to the bit pattern and
-// letting the MMA drop the low 13 bits is cvt.rna (ties away from zero) in ONE integer add; the cvt instruction itself
-// expands to four (it also handles inf / nan, which cannot survive a flow anyway)
-__device__ __forceinline__ float rnt(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// two fp32 -> packed fp16 (round to nearest, saturating at +-65504); `lo` lands at the lower address
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of re-issuing try_wait in a tight loop:
-// the 24 epilogue warps of a CTA spend most of their time here and their spinning competes for issue slots
+// the epilogue warps of a CTA spend most of their time here and their spinning competes for issue slots
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -92,12 +110,30 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
         ::"r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -113,7 +149,7 @@ __global__ void __launch_bounds__(Layout<T, S>::THREADS, 1)
 made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z, const Params p) {
     using L = Layout<T, S>;
     constexpr int THREADS = L::THREADS;
-    constexpr uint32_t OFF_H = L::OFF_H, OFF_W = L::OFF_W, OFF_B1 = L::OFF_B1, OFF_BAR = L::OFF_BAR, OFF_RED = L::OFF_RED;
+    constexpr uint32_t OFF_W = L::OFF_W, OFF_B1 = L::OFF_B1, OFF_BAR = L::OFF_BAR, OFF_RED = L::OFF_RED;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + OFF_BAR;
@@ -130,8 +166,9 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int F = p.n_flows, NH = p.n_hidden;
     const uint32_t flow_bytes = W1_BYTES + (uint32_t)(NH - 1) * WH_BYTES + WO_BYTES;
     const int n_tiles = (int)((p.n_rows + BM - 1) / BM);
-    // this CTA owns tiles blockIdx.x + j * gridDim.x, j < my_tiles; epilogue group t takes j = t, t + T, ...
+    // this CTA owns tiles blockIdx.x + j * gridDim.x, j < my_tiles; tile slot t takes j = t, t + T, ...
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int iters = (my_tiles + T - 1) / T;
 
     for (int i = threadIdx.x; i < F * HP; i += THREADS) sb1[i] = p.b1[i];
     if (warp == 0 && lane == 0) {
@@ -160,100 +197,100 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp < 4) {
-        // control warps hand most of their registers to the epilogue groups (a thread there keeps a 64-wide row resident)
+        // control warps hand most of their registers to the epilogue groups (a thread there keeps its row resident)
         if constexpr (L::REG_CTRL != 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(L::REG_CTRL));
-        if (warp == 0 && lane == 0) {
-            // ---------------- weight producer ----------------
-            uint32_t wcount = 0;
-            for (int j0 = 0; j0 < my_tiles; j0 += T) {
-                for (int f = 0; f < F; ++f, ++wcount) {
-                    const int ws = wcount & 1;
-                    mbar_wait(w_empty(ws), ((wcount >> 1) & 1u) ^ 1u);
-                    mbar_expect_tx(w_full(ws), flow_bytes);
-                    bulk_load(base + OFF_W + ws * WSLOT, p.wimg + (size_t)f * (flow_bytes / 4), flow_bytes, w_full(ws));
-                }
-            }
-        } else if (warp >= 1 && warp <= T && lane == 0) {
-            // ---------------- MMA issuers: one per tile slot, so the tiles' layer chains run independently ----------------
-            // (a single issuer walking the tiles round-robin kept them in lockstep: its per-tile wake-up / descriptor /
-            // commit latency was paid T times per layer and the MMA time never overlapped the epilogues)
-            const int t = warp - 1;
+        if (warp < T && lane == 0) {
+            // ---------------- MMA issuer of tile slot `t` (issuer 0 also streams the weights) ----------------
+            const int t = warp;
             const uint32_t d = tmem_base + (uint32_t)(t * 128);
-            const uint64_t az = make_smem_desc(base + t * Z_BYTES), ah = make_smem_desc(base + OFF_H + t * H_BYTES);
-            uint32_t wcount = 0, a_ph = 0;
+            const uint64_t az = make_smem_desc(base + t * TILE_BYTES), ah = make_smem_desc(base + t * TILE_BYTES + OPER_H);
+            const uint32_t total = (uint32_t)(iters * F);  // every issuer walks the same sequence of (iteration, flow) steps
+            uint32_t loaded = 0, a_ph = 0;                 // weight images requested so far (issuer 0)
+            auto load_weights = [&](uint32_t n) {          // image of step n into ring slot n & 1
+                const int ws = n & 1;
+                mbar_expect_tx(w_full(ws), flow_bytes);
+                bulk_load(base + OFF_W + ws * WSLOT, (const uint8_t *)p.wimg + (size_t)(n % F) * flow_bytes, flow_bytes, w_full(ws));
+            };
 #pragma unroll 1
-            const int iters = (my_tiles + T - 1) / T;
-            for (int i = 0; i < iters; ++i) {              // every issuer walks the same (iteration, flow) sequence ...
-                const bool active = i * T + t < my_tiles;  // ... idle ones only keep the weight-ring counts right
-#pragma unroll 1
-                for (int f = 0; f < F; ++f, ++wcount) {
-                    const int ws = wcount & 1;
-                    if (!active) {
-                        mbar_wait(w_full(ws), (wcount >> 1) & 1u);
-                        mbar_arrive(w_empty(ws));
-                        continue;
+            for (uint32_t n = 0; n < total; ++n) {
+                const int ws = n & 1;
+                const bool active = (int)(n / F) * T + t < my_tiles;  // idle issuers only keep the weight-ring counts right
+                if (t == 0) {
+                    // step n's image must be on its way before this thread blocks on it; step n + 1 is prefetched as soon as
+                    // its slot has been released by every issuer (they finished step n - 1)
+                    while (loaded <= n) {
+                        mbar_wait(w_empty(loaded & 1), ((loaded >> 1) & 1u) ^ 1u);
+                        load_weights(loaded++);
                     }
-                    mbar_wait(w_full(ws), (wcount >> 1) & 1u);
-                    const uint32_t wb = base + OFF_W + ws * WSLOT;
-                    const uint64_t b1d = make_smem_desc(wb);
-#pragma unroll 1
-                    for (int l = 0; l <= NH; ++l) {
-                        mbar_wait_parked(a_ready(t), a_ph);
-                        a_ph ^= 1u;
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (p.debug & 4) {
-                        } else if (l == 0) {
-#pragma unroll
-                            for (int k = 0; k < D / UMMA_K; ++k) {
-                                // k-block kb = k / 4 (16 KB apart in A, 4 KB in B), 32 B per k-step inside the swizzle atom
-                                const uint64_t ao = (uint64_t)((k >> 2) * (ZBLK >> 4) + 2 * (k & 3));
-                                const uint64_t bo = (uint64_t)((k >> 2) * ((HP * 128) >> 4) + 2 * (k & 3));
-                                umma_tf32(d, az + ao, b1d + bo, k != 0, IDESC_H);
-                            }
-                        } else {
-                            const uint64_t b0 = b1d + (uint64_t)((W1_BYTES + (uint32_t)(l - 1) * WH_BYTES) >> 4);
-                            const uint32_t idesc = l == NH ? IDESC_O : IDESC_H;
-#pragma unroll
-                            for (int k = 0; k < HP / UMMA_K; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), k != 0, idesc);
-                        }
-                        umma_commit(acc_ready(t));
-                    }
-                    umma_commit(w_empty(ws));  // this issuer's reads of the weight slot have completed when this fires
+                    if (loaded == n + 1 && loaded < total && mbar_test(w_empty(loaded & 1), ((loaded >> 1) & 1u) ^ 1u))
+                        load_weights(loaded++);
                 }
+                mbar_wait(w_full(ws), (n >> 1) & 1u);
+                if (!active) {
+                    mbar_arrive(w_empty(ws));
+                    continue;
+                }
+                const uint64_t b1d = make_smem_desc(base + OFF_W + ws * WSLOT);
+#pragma unroll 1
+                for (int l = 0; l <= NH; ++l) {
+                    mbar_wait_parked(a_ready(t), a_ph);
+                    a_ph ^= 1u;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (p.debug & 4) {
+                    } else if (l == 0) {
+#pragma unroll
+                        for (int k = 0; k < D / UK; ++k)  // 32 bytes per k-step inside the 128-byte swizzle atom
+                            umma_f16(d, az + (uint64_t)(2 * k), b1d + (uint64_t)(2 * k), k != 0, IDESC_H);
+                    } else {
+                        const uint64_t b0 = b1d + (uint64_t)((W1_BYTES + (uint32_t)(l - 1) * WH_BYTES) >> 4);
+                        const uint32_t idesc = l == NH ? IDESC_O : IDESC_H;
+#pragma unroll
+                        for (int k = 0; k < HP / UK; ++k) umma_f16(d, ah + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), k != 0, idesc);
+                    }
+                    umma_commit(acc_ready(t));
+                    if (t == 0 && loaded == n + 1 && loaded < total && mbar_test(w_empty(loaded & 1), ((loaded >> 1) & 1u) ^ 1u))
+                        load_weights(loaded++);  // another chance to prefetch the next flow's weights
+                }
+                umma_commit(w_empty(ws));  // this issuer's reads of the weight slot have completed when this fires
             }
         }
     } else {
-        if constexpr (Layout<T, S>::REG_EPI != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Layout<T, S>::REG_EPI));
+        if constexpr (L::REG_EPI != 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(L::REG_EPI));
         // ---------------- epilogue groups: one tile in flight per group, S threads per row ----------------
         // a warp may only touch TMEM lanes [32 * (warp % 4), +32): the S warps with the same warp % 4 share those rows and
         // split their columns -- thread `part` owns dims [part * D / S, (part + 1) * D / S) of row q * 32 + lane
-        constexpr int WPS = 4 * S;            // warps per group
-        constexpr int ZC = 16 / S;            // 16-byte chunks of the point row per thread
-        constexpr int DPT = D / S;            // dims per thread
+        constexpr int WPS = 4 * S;  // warps per group
+        constexpr int ZC = 16 / S;  // 16-byte fp32 chunks of the staged row per thread
+        constexpr int DPT = D / S;  // dims per thread
         const int w = (warp - 4) % WPS, slot = (warp - 4) / WPS, q = w & 3, part = w >> 2, row = q * 32 + lane;
         const bool leader = (w == 0 && lane == 0);
         const uint32_t swz = (uint32_t)(row & 7);
-        const uint32_t zrow = base + slot * Z_BYTES + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-        const uint32_t hrow = base + OFF_H + slot * H_BYTES + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t zrow = base + slot * TILE_BYTES + rowoff;  // fp32 staging row (K-block 0; K-block 1 at + ZBLK) = fp16 z row
+        const uint32_t hrow = zrow + OPER_H;                      // fp16 hidden row (first 64 of its 128 bytes)
         const uint32_t trow = tmem_base + (uint32_t)(slot * 128) + ((uint32_t)(q * 32) << 16);
         float *red = reinterpret_cast<float *>(smem_raw + (base + OFF_RED - smem_u32(smem_raw))) + slot * 256;
-        // address of the thread's i-th chunk of the point row (chunks ZC * part + i; 8 chunks per 16 KB K-block)
-        auto zaddr = [&](int i) {
-            const int cc = ZC * part + i;
-            return zrow + (uint32_t)(cc >> 3) * ZBLK + (((uint32_t)(cc & 7) ^ swz) << 4);
-        };
+        // fp32 staging: address of 16-byte chunk cc of the row (8 chunks per 16 KB K-block)
+        auto saddr = [&](int cc) { return zrow + (uint32_t)(cc >> 3) * ZBLK + (((uint32_t)(cc & 7) ^ swz) << 4); };
         auto publish = [&]() {  // operand rows written: make them visible to the tensor core, one arrival per warp
             if (!(p.debug & 1)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready(slot));
         };
+        // fp16 z operand: 8 dims per 16-byte chunk; the thread's dims [DPT * part, +DPT) are chunks (DPT / 8) * part + i
+        auto stage_z = [&](const float(&z)[DPT]) {
+#pragma unroll
+            for (int i = 0; i < DPT / 8; ++i)
+                sts128u(zrow + (((uint32_t)((DPT / 8) * part + i) ^ swz) << 4), pack_h2(z[8 * i], z[8 * i + 1]),
+                        pack_h2(z[8 * i + 2], z[8 * i + 3]), pack_h2(z[8 * i + 4], z[8 * i + 5]), pack_h2(z[8 * i + 6], z[8 * i + 7]));
+        };
         uint32_t in_phase = 0, acc_phase = 0;
         int tile = (int)blockIdx.x + slot * (int)gridDim.x;
         if (leader && tile < n_tiles) {
-            mbar_expect_tx(in_full(slot), Z_BYTES);
-            tma_load_2d(base + slot * Z_BYTES, &map_x, in_full(slot), 0, tile * BM);
-            tma_load_2d(base + slot * Z_BYTES + ZBLK, &map_x, in_full(slot), 32, tile * BM);
+            mbar_expect_tx(in_full(slot), TILE_BYTES);
+            tma_load_2d(base + slot * TILE_BYTES, &map_x, in_full(slot), 0, tile * BM);
+            tma_load_2d(base + slot * TILE_BYTES + ZBLK, &map_x, in_full(slot), 32, tile * BM);
         }
 #pragma unroll 1
         for (; tile < n_tiles; tile += T * (int)gridDim.x) {
@@ -262,11 +299,12 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             in_phase ^= 1u;
 #pragma unroll
             for (int i = 0; i < ZC; ++i) {
-                const uint32_t a = zaddr(i);
-                const float4 v = lds128(a);
+                const float4 v = lds128(saddr(ZC * part + i));
                 z[4 * i] = v.x, z[4 * i + 1] = v.y, z[4 * i + 2] = v.z, z[4 * i + 3] = v.w;
-                sts128(a, rnt(v.x), rnt(v.y), rnt(v.z), rnt(v.w));
             }
+            // the fp16 operand rows overwrite the staged fp32 rows: with two threads per row the partner must have read first
+            if constexpr (S == 2) asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(WPS * 32) : "memory");
+            stage_z(z);
             publish();
             float ld4[4] = {0.f, 0.f, 0.f, 0.f};  // four partial sums: the additions must not form one dependent chain
 #pragma unroll 1
@@ -277,30 +315,29 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     acc_phase ^= 1u;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int g = 0; g < 2 / S; ++g) {  // 16 hidden columns per load: bias (first layer), ReLU, TF32 rounding, operand store
+                    for (int g = 0; g < 2 / S; ++g) {  // 16 hidden columns per load: bias (first layer), ReLU, fp16, operand store
                         const int col0 = 16 * (part * (2 / S) + g);
                         uint32_t r[16];
                         tmem_ld16(trow + (uint32_t)col0, r);
-                        if (p.debug & 8) {
-                        } else if (l == 0) {
+                        if (p.debug & 8) continue;
+                        float h[16];
+                        if (l == 0) {
                             const float4 *bb = reinterpret_cast<const float4 *>(sb1 + f * HP + col0);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 const float4 b = bb[c];
-                                const float h0 = rnt(fmaxf(__uint_as_float(r[4 * c]) + b.x, 0.f));
-                                const float h1 = rnt(fmaxf(__uint_as_float(r[4 * c + 1]) + b.y, 0.f));
-                                const float h2 = rnt(fmaxf(__uint_as_float(r[4 * c + 2]) + b.z, 0.f));
-                                float h3 = rnt(fmaxf(__uint_as_float(r[4 * c + 3]) + b.w, 0.f));
-                                if (col0 + 4 * c + 3 == HP - 1) h3 = 1.f;  // the constant-one column that carries the later biases
-                                sts128(hrow + (((uint32_t)(col0 / 4 + c) ^ swz) << 4), h0, h1, h2, h3);
+                                h[4 * c] = fmaxf(__uint_as_float(r[4 * c]) + b.x, 0.f), h[4 * c + 1] = fmaxf(__uint_as_float(r[4 * c + 1]) + b.y, 0.f);
+                                h[4 * c + 2] = fmaxf(__uint_as_float(r[4 * c + 2]) + b.z, 0.f), h[4 * c + 3] = fmaxf(__uint_as_float(r[4 * c + 3]) + b.w, 0.f);
                             }
+                            if (col0 + 15 == HP - 1) h[15] = 1.f;  // the constant-one column that carries the later layers' biases
                         } else {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                sts128(hrow + (((uint32_t)(col0 / 4 + c) ^ swz) << 4), rnt(fmaxf(__uint_as_float(r[4 * c]), 0.f)),
-                                       rnt(fmaxf(__uint_as_float(r[4 * c + 1]), 0.f)), rnt(fmaxf(__uint_as_float(r[4 * c + 2]), 0.f)),
-                                       rnt(fmaxf(__uint_as_float(r[4 * c + 3]), 0.f)));
+                            for (int j = 0; j < 16; ++j) h[j] = fmaxf(__uint_as_float(r[j]), 0.f);
                         }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)  // 8 fp16 per 16-byte chunk
+                            sts128u(hrow + (((uint32_t)(col0 / 8 + c) ^ swz) << 4), pack_h2(h[8 * c], h[8 * c + 1]), pack_h2(h[8 * c + 2], h[8 * c + 3]),
+                                    pack_h2(h[8 * c + 4], h[8 * c + 5]), pack_h2(h[8 * c + 6], h[8 * c + 7]));
                     }
                     publish();
                 }
@@ -320,16 +357,13 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                         z[8 * g + u] = fmaf(z[8 * g + u], ex2(sv), tv);  // the packer scaled the s rows by log2(e)
                         ld4[u & 3] += sv;
                     }
-                    if (!last) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int i = 2 * g + c;
-                            sts128(zaddr(i), rnt(z[4 * i]), rnt(z[4 * i + 1]), rnt(z[4 * i + 2]), rnt(z[4 * i + 3]));
-                        }
-                    }
                 }
-                if (!last) publish();
-                else asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (!last) {
+                    stage_z(z);
+                    publish();
+                } else {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                }
             }
             // ---- results ----
             float ld = ((ld4[0] + ld4[1]) + (ld4[2] + ld4[3])) * LN2, ss = 0.f;  // the accumulators hold s * log2(e)
@@ -348,34 +382,31 @@ made_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 if (p.log_prob) p.log_prob[grow] = ld - 0.5f * ss - (float)D * HALF_LOG_2PI;
             }
             if (p.store_z) {
+                // exact fp32 row back into the staging layout (the operand tiles are dead: the last MMA has completed)
                 if (p.final_reversed) {  // physical position j holds logical dim 63 - j: chunk cc goes to chunk 15 - cc, reversed
 #pragma unroll
-                    for (int i = 0; i < ZC; ++i) {
-                        const int cc = 15 - (ZC * part + i);
-                        sts128(zrow + (uint32_t)(cc >> 3) * ZBLK + (((uint32_t)(cc & 7) ^ swz) << 4), z[4 * i + 3], z[4 * i + 2],
-                               z[4 * i + 1], z[4 * i]);
-                    }
+                    for (int i = 0; i < ZC; ++i) sts128(saddr(15 - (ZC * part + i)), z[4 * i + 3], z[4 * i + 2], z[4 * i + 1], z[4 * i]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < ZC; ++i) sts128(zaddr(i), z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                    for (int i = 0; i < ZC; ++i) sts128(saddr(ZC * part + i), z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(WPS * 32) : "memory");
                 if (leader) {
-                    tma_store_2d(&map_z, base + slot * Z_BYTES, 0, tile * BM);
-                    tma_store_2d(&map_z, base + slot * Z_BYTES + ZBLK, 32, tile * BM);
+                    tma_store_2d(&map_z, base + slot * TILE_BYTES, 0, tile * BM);
+                    tma_store_2d(&map_z, base + slot * TILE_BYTES + ZBLK, 32, tile * BM);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile buffer may be overwritten
                 }
             } else if constexpr (S == 2) {
-                // no store: the partner may still be reading `red` / nothing else is shared; the next tile's load must only
-                // wait for this group's last operand reads, which completed before the output accumulator was published
+                // the partner's last operand stores to this slot are ordered before the next TMA load by this barrier
+                asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(WPS * 32) : "memory");
             }
             const int next = tile + T * (int)gridDim.x;
             if (leader && next < n_tiles) {
-                mbar_expect_tx(in_full(slot), Z_BYTES);
-                tma_load_2d(base + slot * Z_BYTES, &map_x, in_full(slot), 0, next * BM);
-                tma_load_2d(base + slot * Z_BYTES + ZBLK, &map_x, in_full(slot), 32, next * BM);
+                mbar_expect_tx(in_full(slot), TILE_BYTES);
+                tma_load_2d(base + slot * TILE_BYTES, &map_x, in_full(slot), 0, next * BM);
+                tma_load_2d(base + slot * TILE_BYTES + ZBLK, &map_x, in_full(slot), 32, next * BM);
             }
         }
         if (leader && p.store_z) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
@@ -403,12 +434,12 @@ static int launch_fused(const CUtensorMap &mx, const CUtensorMap &mz, const made
 
 extern "C" {
 
-int64_t mnf_made_fused_image_floats(int n_hidden) {
+int64_t mnf_made_fused_image_bytes(int n_hidden) {
     if (n_hidden < 1 || n_hidden > madef::MAX_HIDDEN) return 0;
-    return (int64_t)(madef::W1_BYTES + (uint32_t)(n_hidden - 1) * madef::WH_BYTES + madef::WO_BYTES) / 4;
+    return (int64_t)(madef::W1_BYTES + (uint32_t)(n_hidden - 1) * madef::WH_BYTES + madef::WO_BYTES);
 }
 
-int mnf_made_density_fused(const float *wimg, const float *b1, int n_flows, int n_hidden, int final_reversed,
+int mnf_made_density_fused(const void *wimg, const float *b1, int n_flows, int n_hidden, int final_reversed,
                            const float *x, float *z, float *log_det, float *log_prob, int64_t n_rows, int dim,
                            int variant, void *stream) {
     MNF_REQUIRE(wimg && b1 && x && (z || log_det || log_prob), MNF_E_ARG, "NULL pointer");
@@ -436,10 +467,10 @@ int mnf_made_density_fused(const float *wimg, const float *b1, int n_flows, int 
     switch (variant) {  // 10 * tiles in flight + threads per row
         case 21: return launch_fused<2, 1>(mx, mz, p, grid, st);
         case 31: return launch_fused<3, 1>(mx, mz, p, grid, st);
-        case 22: return launch_fused<2, 2>(mx, mz, p, grid, st);
+        case 41: return launch_fused<4, 1>(mx, mz, p, grid, st);
         case 0:
         case 32: return launch_fused<3, 2>(mx, mz, p, grid, st);
-        default: return fail(MNF_E_ARG, "variant must be 0 (default), 21, 31, 22 or 32 (10 * tiles in flight + threads per row)");
+        default: return fail(MNF_E_ARG, "variant must be 0 (default), 21, 31, 41 or 32 (10 * tiles in flight + threads per row)");
     }
 }
 

@@ -107,7 +107,7 @@ _lib.register({
     "mnf_made_workspace": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "mnf_made_density_tc": (C.c_int, [C.POINTER(MadeLayer), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
-    "mnf_made_fused_image_floats": (C.c_int64, [C.c_int]),
+    "mnf_made_fused_image_bytes": (C.c_int64, [C.c_int]),
     "mnf_made_density_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
 })
@@ -211,7 +211,7 @@ def made_density(plan: MadeStackPlan, x, want_inter=False):
 # ---------------------------------------------------------------------------------------
 FUSED_DIM, FUSED_HP, FUSED_MAX_FLOWS = 64, 32, 16
 LOG2E = 1.4426950408889634
-VARIANT = 0  # 0 = library default; 10 * tiles in flight + threads per row (21, 31, 22, 32) for tuning / tests
+VARIANT = 0  # 0 = library default; 10 * tiles in flight + threads per row (21, 31, 41, 32) for tuning / tests
 
 
 def made_fused_eligible(flow) -> bool:
@@ -223,14 +223,14 @@ def made_fused_eligible(flow) -> bool:
 
 
 def _swizzled_image(W):
-    """[N, K] (K = 32 or 64) -> flat K-major, 128-byte-swizzled shared-memory image (see include/mnf_b200.h)."""
+    """[N, K] (K <= 64) -> flat fp16 image: rows of 128 bytes (K padded to 64), K-major, 128-byte swizzle
+    (see include/mnf_b200.h).  fp16 conversion rounds to nearest and saturates at +-65504."""
     N, K = W.shape
     n = torch.arange(N, device=W.device)[:, None]
     k = torch.arange(K, device=W.device)[None, :]
-    kb, kk = k // 32, k % 32
-    off = kb * (N * 32) + (n // 8) * 256 + (n % 8) * 32 + (((kk // 4) ^ (n % 8)) * 4) + kk % 4
-    img = torch.empty(N * K, device=W.device, dtype=torch.float32)
-    img[off.reshape(-1)] = _round_tf32(W).reshape(-1)
+    off = (n // 8) * 512 + (n % 8) * 64 + (((k // 8) ^ (n % 8)) * 8) + k % 8
+    img = torch.zeros(N * 64, device=W.device, dtype=torch.float16)
+    img[off.reshape(-1)] = W.clamp(-65504.0, 65504.0).to(torch.float16).reshape(-1)
     return img
 
 
@@ -295,9 +295,9 @@ class FusedMadePlan:
                 self.reversed_after.append(rev)
         self.images = torch.stack(imgs).contiguous()
         self.b1 = torch.stack(b1s).contiguous()
-        expect = _lib.lib().mnf_made_fused_image_floats(self.n_hidden)
-        if self.images.size(1) != expect:
-            raise RuntimeError(f"weight image has {self.images.size(1)} floats, the library expects {expect}")
+        expect = _lib.lib().mnf_made_fused_image_bytes(self.n_hidden)
+        if self.images.size(1) * 2 != expect:
+            raise RuntimeError(f"weight image has {self.images.size(1) * 2} bytes, the library expects {expect}")
         self.key = key
 
 
