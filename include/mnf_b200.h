@@ -255,7 +255,8 @@ int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, 
                         float *xz_out, float *workspace,
                         /* optional: draw z0 = q0_mean + sqrt(exp(q0_log_var)) * eps_z here (z is then output only) */
                         const float *q0_mean, const float *q0_log_var, const float *eps_z, uint32_t eps_stream,
-                        void *stream);
+                        /* 1: the caller consumes only xz_out; z is scratch and its final value may be left unwritten */
+                        int z_is_scratch, void *stream);
 
 /* out = A W^T (+ bias) (+ ReLU) on the tensor cores: A [M,K], W [N,K] (torch Linear layout). */
 int mnf_tc_linear(const float *A, const float *W, const float *bias, float *out, int64_t M, int N, int K,

@@ -268,7 +268,7 @@ def test_packed_parameters_follow_every_kind_of_update():
         sd["flows.5.f1.2.weight"] = sd["flows.5.f1.2.weight"] / 1.5
         model.load_state_dict(sd, assign=True)
         lp2 = model.log_prob(x)
-        torch.testing.assert_close(lp2, lp0, rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(lp2, lp0, rtol=1e-5, atol=2e-5)  # w * 1.5 / 1.5 is not bit-exact
 
 
 def test_graphed_training_replays_invalidate_packed_blobs():
@@ -316,4 +316,6 @@ def test_graphed_inference_draws_fresh_noise_per_replay():
     m = torch.stack([call(x).clone() for _ in range(200)])
     with torch.no_grad():
         eager = torch.stack([layer(x) for _ in range(200)])
-    torch.testing.assert_close(m.mean(0), eager.mean(0), rtol=0.2, atol=0.15)
+    # same distribution as eager calls: means agree within 6 standard errors of the 200-sample means
+    se = (eager.std(0) + m.std(0)) / 200**0.5
+    assert ((m.mean(0) - eager.mean(0)).abs() < 6 * se + 1e-3).all()

@@ -10,6 +10,15 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32, UMMA_K = 8, MAX_BN = 256;
 
+// 16 Bernoulli(0.5) bits for 16 consecutive elements starting at global index e0 (a multiple of 16), identical to
+// philox_bernoulli() element by element
+__device__ __forceinline__ uint32_t philox_bits16(const Philox &g, uint64_t e0, uint32_t stream) {
+    const uint4 q = g(e0 >> 7, stream);
+    const uint32_t bit = (uint32_t)e0 & 127u;
+    const uint32_t w = bit < 32 ? q.x : bit < 64 ? q.y : bit < 96 ? q.z : q.w;
+    return (w >> (bit & 31u)) & 0xFFFFu;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // The tensor core TRUNCATES fp32 operands to TF32 (drops 13 mantissa bits), which biases every product

@@ -13,6 +13,7 @@
 //            tile's MMAs through the second accumulator
 // TF32 keeps a 10-bit mantissa: products carry ~2e-4 relative error, inside the 2e-3 tolerance BASELINE.json
 // states for tensor-core GEMM outputs (the exact-fp32 path is simt_gemm_kernel in mnf_common.cuh).
+#include "rnvp_fused.cuh"
 #include "tc_common.cuh"
 
 namespace mnf {
@@ -62,15 +63,6 @@ struct Epilogue {
     // sd: [M, N] (row stride N); eps indexed like the un-pooled [R, conv_c, conv_oh, conv_ow] tensor.
     int conv_c, conv_oh, conv_ow;
 };
-
-// 16 Bernoulli(0.5) bits for 16 consecutive elements starting at global index e0 (a multiple of 16), identical to
-// philox_bernoulli() element by element
-__device__ __forceinline__ uint32_t philox_bits16(const Philox &g, uint64_t e0, uint32_t stream) {
-    const uint4 q = g(e0 >> 7, stream);
-    const uint32_t bit = (uint32_t)e0 & 127u;
-    const uint32_t w = bit < 32 ? q.x : bit < 64 ? q.y : bit < 96 ? q.z : q.w;
-    return (w >> (bit & 31u)) & 0xFFFFu;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -867,19 +859,22 @@ __global__ void rnvp_pack_kernel(const float *__restrict__ Wn, const float *__re
                                  const float *__restrict__ Wt, const float *__restrict__ bt,
                                  const float *__restrict__ Ws, const float *__restrict__ bsc, int h, int dim,
                                  float *__restrict__ Wn_p, float *__restrict__ bn_p, float *__restrict__ Wts,
-                                 float *__restrict__ bts) {
+                                 float *__restrict__ bts, int bias_column) {
+    // bias_column: column 63 of the padded conditioner output is a constant one (its packed bias is 1, its weights 0) and
+    // column 63 of Wts holds the shift / scale biases -- the form the fused output-GEMM + gate kernel consumes
     const long long n1 = (long long)RNVP_HP * dim, n2 = 2LL * dim * RNVP_HP;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n1 + n2; e += (long long)gridDim.x * blockDim.x) {
         if (e < n1) {
             const int j = (int)(e / dim), k = (int)(e % dim);
             Wn_p[e] = j < h ? rn_tf32(Wn[(size_t)j * dim + k]) : 0.f;
-            if (k == 0) bn_p[j] = j < h ? bn[j] : 0.f;
+            if (k == 0) bn_p[j] = j < h ? bn[j] : ((bias_column && j == RNVP_HP - 1) ? 1.f : 0.f);
         } else {
             const long long f = e - n1;
             const int row = (int)(f / RNVP_HP), k = (int)(f % RNVP_HP), n = row >> 1;
             const float *src = (row & 1) ? Ws : Wt;
-            Wts[f] = k < h ? rn_tf32(src[(size_t)n * h + k]) : 0.f;
-            if (k == 0) bts[row] = (row & 1) ? bsc[n] : bt[n];
+            const float bias = (row & 1) ? bsc[n] : bt[n];
+            Wts[f] = k < h ? rn_tf32(src[(size_t)n * h + k]) : ((bias_column && k == RNVP_HP - 1) ? rn_tf32(bias) : 0.f);
+            if (k == 0) bts[row] = bias;
         }
     }
 }
@@ -919,6 +914,47 @@ __global__ void z0_mask_kernel(const float *__restrict__ q0_mean, const float *_
         *reinterpret_cast<float4 *>(z + e0) = make_float4(zv[0], zv[1], zv[2], zv[3]);
         *reinterpret_cast<float4 *>(mz + e0) =
             make_float4(rn_tf32(m4[0] * zv[0]), rn_tf32(m4[1] * zv[1]), rn_tf32(m4[2] * zv[2]), rn_tf32(m4[3] * zv[3]));
+    }
+}
+
+// Philox-only form of z0_mask_kernel for dim % 128 == 0 (BASELINE config 5: 268 M normals per 65 536 rows, ALU-bound).
+// A warp owns spans of 4096 consecutive elements: one Philox block yields the Bernoulli bits of 128 elements, so lane L
+// draws the mask block of the span's L-th 128-element group once and hands it round by shuffle (the general kernel drew
+// one block per float4: 32x the calls); q0_mean and the standard deviation exp(q0_log_var / 2) come from a shared-memory
+// table; accesses are 512 contiguous bytes per warp instruction.  Draw numbering identical to the general kernel.
+__global__ void __launch_bounds__(256)
+z0_mask_philox_kernel(const float *__restrict__ q0_mean, const float *__restrict__ q0_log_var, float *__restrict__ z,
+                      float *__restrict__ mz, long long n_rows, int dim, uint64_t seed, uint32_t eps_stream,
+                      uint32_t mask_stream, uint64_t row_offset) {
+    extern __shared__ float tab[];  // [dim] mean | [dim] std
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) tab[i] = q0_mean[i], tab[dim + i] = sqrtf(expf(q0_log_var[i]));
+    __syncthreads();
+    const Philox rng(seed);
+    const long long total = n_rows * dim, n_spans = (total + 4095) >> 12;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const uint64_t gbase = (uint64_t)row_offset * dim;  // a multiple of 128: the groups line up with Philox mask blocks
+    for (long long span = warp_id; span < n_spans; span += n_warps) {
+        const long long s0 = span << 12;
+        const uint4 mb = rng((gbase + (uint64_t)s0 + 128ull * lane) >> 7, mask_stream);  // mask bits of the span's group `lane`
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t wx = __shfl_sync(0xffffffffu, mb.x, i), wy = __shfl_sync(0xffffffffu, mb.y, i),
+                           wz = __shfl_sync(0xffffffffu, mb.z, i), ww = __shfl_sync(0xffffffffu, mb.w, i);
+            const long long e0 = s0 + 128 * i + 4 * lane;
+            if (e0 >= total) break;
+            const uint32_t word = lane < 8 ? wx : (lane < 16 ? wy : (lane < 24 ? wz : ww));
+            const uint32_t bits = (word >> ((4 * lane) & 31)) & 0xFu;
+            const uint4 q = rng((gbase + (uint64_t)e0) >> 2, eps_stream);
+            const float2 a = box_muller(q.x, q.y), b = box_muller(q.z, q.w);
+            const int d = (int)(e0 % dim);
+            const float4 mu = *reinterpret_cast<const float4 *>(tab + d), sd = *reinterpret_cast<const float4 *>(tab + dim + d);
+            const float z0 = fmaf(sd.x, a.x, mu.x), z1 = fmaf(sd.y, a.y, mu.y), z2 = fmaf(sd.z, b.x, mu.z), z3 = fmaf(sd.w, b.y, mu.w);
+            st_stream4(reinterpret_cast<float4 *>(z + e0), make_float4(z0, z1, z2, z3));
+            st_stream4(reinterpret_cast<float4 *>(mz + e0),
+                       make_float4((bits & 1u) ? rn_tf32(z0) : 0.f, (bits & 2u) ? rn_tf32(z1) : 0.f, (bits & 4u) ? rn_tf32(z2) : 0.f,
+                                   (bits & 8u) ? rn_tf32(z3) : 0.f));
+        }
     }
 }
 
@@ -1029,7 +1065,7 @@ int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, 
                         const float *const *masks_host, uint64_t seed, uint32_t first_noise_stream, uint64_t row_offset,
                         int64_t n_rows, int dim, const float *x, int64_t x_rows, float *xz_out, float *workspace,
                         const float *q0_mean, const float *q0_log_var, const float *eps_z, uint32_t eps_stream,
-                        void *stream) {
+                        int z_is_scratch, void *stream) {
     MNF_REQUIRE(flows_host && z && log_det && workspace, MNF_E_ARG, "NULL pointer");
     MNF_REQUIRE(n_flows >= 1 && n_rows >= 0 && n_rows <= 0x7fffffff - 256, MNF_E_ARG, "bad shape");
     MNF_REQUIRE(dim % 16 == 0 && dim >= 32, MNF_E_SHAPE, "tensor-core RNVP needs dim %% 16 == 0 and dim >= 32 (got %d)", dim);
@@ -1043,15 +1079,25 @@ int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, 
           *wbase = ts + 2 * (size_t)n_rows * dim;
     wbase += (16 - ((uintptr_t)wbase / 4) % 16) % 16;  // keep every packed matrix 64-byte aligned
     const size_t per_flow = (size_t)tc::RNVP_HP * dim + tc::RNVP_HP + 2ull * dim * tc::RNVP_HP + 2ull * dim;
-    MNF_CUDA(cudaMemsetAsync(log_det, 0, sizeof(float) * n_rows, st));
+    // wide dims take the fused output-GEMM + gate kernel (rnvp_fused.cu): the [R, 2 * dim] shift / scale matrix never exists
+    bool fused = true;
+    for (int f = 0; f < n_flows; ++f) fused = fused && rnvpf::eligible(dim, flows_host[f].net_sizes[0]);
+    if (!fused) MNF_CUDA(cudaMemsetAsync(log_det, 0, sizeof(float) * n_rows, st));
     for (int f = 0; f < n_flows; ++f) {
         const mnf_rnvp_flow &fl = flows_host[f];
         float *Wn_p = wbase + f * per_flow, *bn_p = Wn_p + (size_t)tc::RNVP_HP * dim, *Wts = bn_p + tc::RNVP_HP,
               *bts = Wts + 2ull * dim * tc::RNVP_HP;
         tc::rnvp_pack_kernel<<<tc::blocks_for((long long)tc::RNVP_HP * dim * 3), 256, 0, st>>>(
-            fl.net_w[0], fl.net_b[0], fl.t_w, fl.t_b, fl.s_w, fl.s_b, fl.net_sizes[0], dim, Wn_p, bn_p, Wts, bts);
+            fl.net_w[0], fl.net_b[0], fl.t_w, fl.t_b, fl.s_w, fl.s_b, fl.net_sizes[0], dim, Wn_p, bn_p, Wts, bts, fused ? 1 : 0);
     }
-    if (q0_mean && q0_log_var)  // sample z0 here (saves a pass over z): MNFLinear.sample_z, mnf_linear.py:58-62
+    const bool philox_fast = q0_mean && q0_log_var && !eps_z && !masks_host && dim % 128 == 0 && dim <= 8192;
+    if (philox_fast) {
+        const size_t smem = 2 * sizeof(float) * (size_t)dim;
+        if (smem > 48 * 1024)
+            MNF_CUDA(cudaFuncSetAttribute(tc::z0_mask_philox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::z0_mask_philox_kernel<<<148 * 4, 256, smem, st>>>(q0_mean, q0_log_var, z, mz, n_rows, dim, seed, eps_stream,
+                                                              first_noise_stream, row_offset);
+    } else if (q0_mean && q0_log_var)  // sample z0 here (saves a pass over z): MNFLinear.sample_z, mnf_linear.py:58-62
         tc::z0_mask_kernel<<<tc::blocks_for(n_rows * dim / 4), 256, 0, st>>>(q0_mean, q0_log_var, eps_z,
                                                                            masks_host ? masks_host[0] : nullptr, z, mz,
                                                                            n_rows, dim, seed, eps_stream,
@@ -1070,6 +1116,23 @@ int mnf_rnvp_forward_tc(const mnf_rnvp_flow *flows_host, int n_flows, float *z, 
         rc = tc::launch(mz, Wn_p, (int)n_rows, tc::RNVP_HP, dim, e1, st);
         if (rc) return rc;
         const bool last = f == n_flows - 1;
+        if (fused) {
+            rnvpf::Params gp{};
+            gp.z = z, gp.log_det = log_det;
+            gp.mask = masks_host ? masks_host[f] : nullptr;
+            gp.mask_next = (!last && masks_host) ? masks_host[f + 1] : nullptr;
+            gp.mz_next = last ? nullptr : mz;
+            gp.xmul = x, gp.xmul_rows = (int)(x_rows > 0 ? x_rows : 1);
+            gp.xz_out = (last && xz_out) ? xz_out : nullptr;
+            gp.n_rows = n_rows, gp.dim = dim;
+            gp.write_z = !(last && z_is_scratch && xz_out);  // a caller that only consumes x * z_final saves the last z store
+            gp.accumulate_ld = f != 0;
+            gp.seed = seed, gp.row_offset = row_offset;
+            gp.stream = first_noise_stream + (uint32_t)f, gp.next_stream = first_noise_stream + (uint32_t)f + 1;
+            rc = rnvpf::launch(y, Wts, gp, st);
+            if (rc) return rc;
+            continue;
+        }
         // [shift | scale] = y [Wt; Ws]^T + bias as a plain GEMM, then the gate as a full-occupancy streaming pass
         // (measured: the same arithmetic inside the GEMM epilogue is latency-bound on its 8 warps, 2.6-3.3 ms
         // per 65536 x 4096 flow against ~1.3 ms this way)

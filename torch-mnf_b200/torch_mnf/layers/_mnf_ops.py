@@ -52,7 +52,7 @@ _lib.register({
                                      _int, _int, _vp, _vp]),
     "mnf_rnvp_tc_workspace": (_i64, [_int, _i64, _int]),
     "mnf_rnvp_forward_tc": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64, _i64,
-                                   _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
+                                   _int, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u32, _int, _vp]),
     "mnf_conv2d_moments": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp]),
     "mnf_conv_noise_relu_pool": (_int, [_vp, _vp, _i64, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _vp]),
     "mnf_conv_noise_relu_pool_z": (_int, [_vp, _vp, _i64, _vp, _u64, _u32, _u64, _vp, _i64, _int, _int, _int, _vp, _i64,
@@ -211,7 +211,7 @@ def rnvp_tc_ok(flows, dim) -> bool:
 
 
 @torch.no_grad()
-def rnvp_stack_tc(flows, z, noise: Noise, x=None, x_rows=None, xz_out=None, q0=None, n_rows=None):
+def rnvp_stack_tc(flows, z, noise: Noise, x=None, x_rows=None, xz_out=None, q0=None, n_rows=None, z_is_scratch=False):
     """Tensor-core variant of rnvp_stack_inplace; optionally leaves tf32(x*z_final) in xz_out.  With q0 =
     (q0_mean, q0_log_var) the base sample z0 is drawn inside the call (z may be None) -- draw order as in
     MNFLinear.sample_z: normal[R, dim] first, then one Bernoulli mask per flow."""
@@ -238,7 +238,7 @@ def rnvp_stack_tc(flows, z, noise: Noise, x=None, x_rows=None, xz_out=None, q0=N
     with torch.cuda.device(dev):
         rc = lib.mnf_rnvp_forward_tc(arr, n, z.data_ptr(), ld.data_ptr(), mask_arr, noise.seed, first_sid or 0,
                                      noise.row_offset, R, dim, _p(x), x_rows or (x.size(0) if x is not None else 1),
-                                     _p(xz_out), ws.data_ptr(), _p(q0m), _p(q0v), _p(eps_z), eps_sid,
+                                     _p(xz_out), ws.data_ptr(), _p(q0m), _p(q0v), _p(eps_z), eps_sid, int(z_is_scratch),
                                      _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_rnvp_forward_tc")
     return ld, z

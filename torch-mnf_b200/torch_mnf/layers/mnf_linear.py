@@ -68,10 +68,10 @@ class MNFLinear(nn.Module):
             ok4 = self.n_in % 4 == 0 and (noise.row_offset * self.n_in) % 16 == 0
             if ok4:  # z0 drawn inside the RNVP call (one pass less over z)
                 ops.rnvp_stack_tc(flows_q, None, noise, x=x, x_rows=x.size(0), xz_out=ws,
-                                  q0=(self.q0_mean, self.q0_log_var), n_rows=n_rows)
+                                  q0=(self.q0_mean, self.q0_log_var), n_rows=n_rows, z_is_scratch=True)
             else:
                 z = ops.sample_z0(self.q0_mean, self.q0_log_var, n_rows, noise)
-                ops.rnvp_stack_tc(flows_q, z, noise, x=x, x_rows=x.size(0), xz_out=ws)
+                ops.rnvp_stack_tc(flows_q, z, noise, x=x, x_rows=x.size(0), xz_out=ws, z_is_scratch=True)
             return ops.linear_forward(self, x, None, noise, x_rows=x.size(0), relu=relu, staged_ws=ws, n_rows=n_rows)
         z, _ = self.sample_z(n_rows, noise)
         return ops.linear_forward(self, x, z, noise, x_rows=x.size(0), relu=relu, precision=precision)
