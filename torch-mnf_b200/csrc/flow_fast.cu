@@ -12,6 +12,10 @@ int stage_image_16_8(const FlowProgram &, const FastLayout &, const float *, flo
 int stage_image_24_8(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
 int stage_image_8_5(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
 
+int launch_flow_tc(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                   float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *workspace,
+                   const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
+
 // ---- host side: plan + launch ---------------------------------------------------------
 
 struct FastPlan {
@@ -62,6 +66,7 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
 // single-launch shared-memory variant for small ones
 constexpr long long kCbankMinRows = 1 << 16;
 constexpr int kNumVariants = 4;
+constexpr bool kTcDefault = false;  // flipped once measured faster at unchanged parity (profiles/r02_flow_tc.md)
 
 // ---------------------------------------------------------------------------------------------------
 // Conditioner-free stacks (AffineConstantFlow / ActNormFlow / Glow only, dim 2): the whole stack is ONE
@@ -179,8 +184,17 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     for (int k = 0; k < n_ops; ++k) has_spline |= ops[k].type == MNF_OP_NSF_CL;
     // measured (r01): the constant-bank variant wins on spline stacks (4.10 vs 5.52 ms per 2^24 points) and loses
     // slightly on pure AffineHalfFlow stacks (16.1 vs 15.0 ms), where a segment still holds two conditioners
-    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
     const bool want_gather = gather && (gather->n_peers > 0 || gather->multicast_ptr);
+    // variant 4: conditioners on the tensor cores (flow_tc.cu), one launch for the whole stack, weights in the caller's
+    // workspace.  Spline stacks of its shape class take it by default from kCbankMinRows rows up.
+    if (!(inverse & 4) && (variant == 4 || (variant < 0 && kTcDefault && has_spline && (plan_only || n_rows >= kCbankMinRows))) &&
+        (!want_gather || (inverse & 2))) {
+        const int rc = launch_flow_tc(ops, n_ops, params, x, y, log_det, base_lp, inter, n_rows, dim, inverse & 3, workspace,
+                                      gather, stream, plan_only);
+        if (rc != 1) return rc;
+    }
+    if (variant == 4) variant = -1;  // not of the tensor-core kernel's shape class: library default
+    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
     if (want_gather && (mode != 3 || !(inverse & 2) || (n_rows & 1))) return 1;  // caller reports the restriction
     bool has_net = false;
     for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;

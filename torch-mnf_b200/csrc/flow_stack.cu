@@ -12,6 +12,7 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int mode, float *workspace, const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
 int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim);
+int64_t flow_tc_workspace_floats();
 int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream);
 int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
                      float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
@@ -156,7 +157,8 @@ int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *pa
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim) {
     (void)n_ops;
     if (dim == 64) return n_rows * 64;  // MADE density stack in log-prob mode parks z here between flows
-    return 3 * (n_rows + (n_rows & 1)) * (dim == 2 ? 1 : 0);
+    // dim 2: points + log-det between the segments of the constant-bank kernel, or the weight image of the tensor-core kernel
+    return dim == 2 ? 3 * (n_rows + (n_rows & 1)) + flow_tc_workspace_floats() : 0;
 }
 
 int mnf_glow_assemble(const float *P, const float *L, const float *U, const float *S, float *out, int dim,
