@@ -459,12 +459,20 @@ def run_ours(args):
                      "frac": achieved / hbm_peak, "traffic": traffic_for("cfg2", n),
                      "kernel": k_sites,
                      "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT, "peak_source": peak_src,
-                     "note": "per STEP (6 segment launches): algorithmic 12 B/pt; the segmented stack moves ~113 B/pt "
-                             "(ncu, profiles/r01_flow_cbank_ncu_full.md); kernel is fp32-FMA-pipe bound, not HBM "
-                             "bound (DESIGN.md): see fma_pipe"},
+                     "note": ("one launch per step (flow_tc16_kernel): conditioner MLPs on tcgen05 as fp16-split 3-term products, "
+                              "weights resident in shared memory, points in registers; DRAM traffic is the algorithmic 12 B/pt. "
+                              "The kernel is instruction-issue bound (spline arithmetic + operand splitting), not HBM bound: "
+                              "profiles/r02_flow_tc.md"
+                              if any("flow_tc" in k for k in k_sites) else
+                              "per STEP (6 segment launches): algorithmic 12 B/pt; the segmented stack moves ~113 B/pt "
+                              "(ncu, profiles/r01_flow_cbank_ncu_full.md); kernel is fp32-FMA-pipe bound, not HBM "
+                              "bound (DESIGN.md): see fma_pipe")},
         "fma_pipe": {"mlp_tflops": mlp_tflops, "fp32_peak_tflops_at_sampled_clock": fp32_peak,
                      "frac_mlp_only": mlp_tflops / fp32_peak, "fma_per_point_mlp": MLP_FMA_PER_POINT,
-                     "note": "conditioner-MLP FMAs only; spline arithmetic shares the same pipe"},
+                     "note": ("conditioner-MLP multiply-adds per second against the fp32 FMA peak, for comparison with the FFMA2 "
+                              "kernel of round 1 (this kernel runs them on the tensor pipe)"
+                              if any("flow_tc" in k for k in k_sites) else
+                              "conditioner-MLP FMAs only; spline arithmetic shares the same pipe")},
     }
     if world == 1:
         # The conditioner-free part of the same stack ([ActNormFlow, Glow] x 3) is the flow workload that IS HBM-bound:

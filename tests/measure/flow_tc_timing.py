@@ -1,6 +1,6 @@
 """Timing + error statistics of the tensor-core spline kernel (variant 4) next to the constant-bank FFMA2 kernel
 (variant 3) on BASELINE config 2.  Run on a GPU box:  python tests/measure/flow_tc_timing.py [log2_rows]
-Env: MNF_FTC_T (tiles in flight, 4..7), MNF_FTC_DEBUG (1 no spline, 2 no MMAs, 4 truncating hi split)."""
+Env: MNF_FTC_V (groups * 10 + tiles per thread, + 100 = biases in the epilogue), MNF_FTC_DEBUG (1 no spline, 2 no MMAs, 4 truncating hi split)."""
 import json
 import os
 import sys
@@ -19,7 +19,7 @@ model = load_flow_model(specs, sd, device="cuda:0", return_intermediates=False)
 prog = model._program()
 n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 24)
 x = 1.5 * torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
-out = {"rows": n, "T": os.environ.get("MNF_FTC_T"), "debug": os.environ.get("MNF_FTC_DEBUG")}
+out = {"rows": n, "V": os.environ.get("MNF_FTC_V"), "debug": os.environ.get("MNF_FTC_DEBUG")}
 lp_out = torch.empty(n, device="cuda")
 for kernel in (3, 4):
     for _ in range(3):

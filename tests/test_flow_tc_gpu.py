@@ -65,3 +65,22 @@ def test_other_shapes_fall_back():
     x = torch.randn(1000, 2, generator=torch.Generator().manual_seed(1))
     y, ld, _, _ = prog.run(x.cuda(), inverse=True, kernel=4)
     close_vs_oracle((y, ld), sd, specs, x, True, "nsf_default via variant 4")
+
+
+def test_activations_outside_fp16_range_take_the_exact_path():
+    """The fp16-split operands overflow for |activation| > 65504: the kernel must notice (non-finite conditioner
+    outputs) and re-evaluate those points' conditioners in fp32.  Conditioning coordinates of 3e5 .. 1e7 with the
+    transformed coordinate inside [-B, B] exercise exactly that."""
+    specs = [{"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}] * 2
+    sd = random_flow_sd(specs, seed=5, scale=0.6)
+    prog = load_flow_model(specs, sd)._program()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4096, 2, generator=g)
+    x[::7, 0] = 3e5 * (1 + 30 * torch.rand(x[::7].size(0), generator=g))  # f1 conditions on x[:, 0]
+    x[3::11, 1] = -2e6
+    for inverse in (True, False):
+        y, ld, _, _ = prog.run(x.cuda(), inverse=inverse, kernel=4)
+        yg, ldg, _, _ = prog.run(x.cuda(), inverse=inverse, kernel="generic")
+        assert torch.isfinite(y).all() and torch.isfinite(ld).all()
+        torch.testing.assert_close(y, yg, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ld, ldg, rtol=1e-4, atol=3e-4)
