@@ -75,6 +75,43 @@ __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, f
     float m = raw[0];
 #pragma unroll
     for (int k = 1; k < Kn; ++k) m = fmaxf(m, raw[k]);
+    const float twoB = 2.f * B;
+    const float span = 1.f - kMinBin * (float)Kn;
+    if constexpr (FAST) {
+        // Same formulas with the constant factors folded (the kernels using this path are instruction-issue bound):
+        //   first softmax   e_k = 2^((raw_k - m) log2 e)                      one FFMA + MUFU.EX2 per bin
+        //   second softmax  f_k = exp(2B e_k / sum)  (its arguments lie in [0, 2B]: no maximum needs subtracting while
+        //                   exp(2B) is representable, B <= 40)                one FMUL + MUFU.EX2 per bin
+        //   knots           x_{k+1} = x_k + 2B min_bin + (2B span / sum f) f_k   one FFMA + FADD per bin
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float mneg = -m * LOG2E;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < Kn; ++k) {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(raw[k], LOG2E, mneg)));
+            sum += e[k];
+        }
+        const float inv = frcp<true>(sum);
+        const bool big = twoB > 80.f;           // uniform across the launch
+        const float sc = twoB * inv * LOG2E;     // first softmax scaled by 2B (spline_flow.py:254-255), in log2 units
+        const float off = big ? -sc : 0.f;       // its maximum element is e = 1
+        float sum2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < Kn; ++k) {
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k]) : "f"(fmaf(e[k], sc, off)));  // second softmax (spline_flow.py:95)
+            sum2 += e[k];
+        }
+        const float c1 = twoB * span * frcp<true>(sum2), c0 = twoB * kMinBin;  // spline_flow.py:96-99
+        float x = -B;
+        knots[0] = -B;
+#pragma unroll
+        for (int k = 0; k < Kn; ++k) {
+            x += fmaf(e[k], c1, c0);
+            knots[k + 1] = x;
+        }
+        knots[Kn] = B;  // spline_flow.py:101
+        return;
+    }
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < Kn; ++k) {
@@ -82,7 +119,6 @@ __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, f
         sum += e[k];
     }
     // first softmax scaled by 2B (spline_flow.py:254-255); its maximum element is 2B/sum
-    const float twoB = 2.f * B;
     const float inv = frcp<FAST>(sum);
     const float m2 = twoB * inv;  // e == 1 at the arg-max
     float sum2 = 0.f;
@@ -93,7 +129,6 @@ __device__ __forceinline__ void spline_knots(const float *raw, int K, float B, f
         sum2 += e[k];
     }
     const float inv2 = frcp<FAST>(sum2);
-    const float span = 1.f - kMinBin * (float)Kn;
     float cum = 0.f;
     knots[0] = -B;
 #pragma unroll
