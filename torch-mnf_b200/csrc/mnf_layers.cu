@@ -7,6 +7,8 @@
 // All GEMM-shaped work goes through the functor skeleton in mnf_common.cuh.
 #include <cooperative_groups.h>
 
+#include <cuda_fp16.h>
+
 #include "mnf_common.cuh"
 
 namespace mnf {
@@ -364,6 +366,21 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ Wm, const flo
     }
 }
 
+// fp16 weights of the implicit-GEMM conv (tc_gemm.cu, conv_implicit_kernel): Bm = fp16(W_mean * z),
+// Bv = fp16(exp(W_log_var) * 2^8) (scale undone by the kernel's epilogue: keeps variances down to 2.4e-7 in fp16's
+// normal range), rows padded to Np and columns to Kp with zeros; bvar_p[n] = b_log_var[n]
+__global__ void conv_pack_weights_f16_kernel(const float *__restrict__ Wm, const float *__restrict__ Wlv,
+                                             const float *__restrict__ blv, const float *__restrict__ z, int N, int K,
+                                             int Np, int Kp, __half *__restrict__ Bm, __half *__restrict__ Bv,
+                                             float *__restrict__ bvar_p) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Np * Kp; e += gridDim.x * blockDim.x) {
+        const int n = e / Kp, k = e % Kp;
+        const bool in = n < N && k < K;
+        Bm[e] = __float2half_rn(in ? Wm[(size_t)n * K + k] * (z ? z[n] : 1.f) : 0.f);  // z == NULL: unit scale (per-sample z applied later)
+        Bv[e] = __float2half_rn(in ? fminf(expf(Wlv[(size_t)n * K + k]) * 256.f, 65504.f) : 0.f);
+        if (k == 0) bvar_p[n] = n < N ? blv[n] : 0.f;
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // One RNVP flow on ONE row (kl_div runs its q / r flows with a single z, mnf_linear.py:67, :83) in one launch:
@@ -427,6 +444,92 @@ rnvp_row_kernel(const float *__restrict__ W0, const float *__restrict__ b0, int 
     }
 }
 
+
+// Direct form of the moments of a small MNFConv2d (few input taps, few output channels: MNF-LeNet's conv1 is
+// 1 x 5 x 5 -> 20): as a GEMM it is M x 20 x 25, a shape the tiled SIMT GEMM runs at 1.4 TFLOP/s.  Here a CTA owns one
+// image (staged in shared memory next to the folded weights [tap][channel]); a thread owns one output pixel and
+// keeps the 2 x NP accumulators of all channels in registers: per tap one image load, NP / 2 broadcast LDS.128 and
+// 2 NP FFMAs.
+template <int NP>
+__global__ void __launch_bounds__(256) conv_moments_direct_kernel(const float *__restrict__ x, const float *__restrict__ z,
+                                                                  const float *__restrict__ Wm, const float *__restrict__ Wlv,
+                                                                  const float *__restrict__ blv, float *__restrict__ mean_out,
+                                                                  float *__restrict__ sd_out, long long n_imgs, int C, int H,
+                                                                  int W, int ks, int N) {
+    extern __shared__ __align__(16) float sm_direct[];
+    const int K = C * ks * ks, OH = H - ks + 1, OW = W - ks + 1, img_floats = C * H * W;
+    float *wm = sm_direct;                       // [K][NP]  W_mean * z
+    float *wv = wm + K * NP;                     // [K][NP]  exp(W_log_var)
+    float *bv = wv + K * NP;                     // [NP]     exp(b_log_var)
+    int *koff = reinterpret_cast<int *>(bv + NP);  // [K]      offset of tap k inside an image
+    float *xs = reinterpret_cast<float *>(koff + ((K + 3) & ~3));
+    for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
+        const int k = i / NP, n = i % NP;
+        wm[i] = n < N ? Wm[(size_t)n * K + k] * (z ? z[n] : 1.f) : 0.f;  // z == NULL: unit scale (per-sample z applied later)
+        wv[i] = n < N ? expf(Wlv[(size_t)n * K + k]) : 0.f;
+    }
+    for (int n = threadIdx.x; n < NP; n += blockDim.x) bv[n] = n < N ? expf(blv[n]) : 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
+        koff[k] = (ci * H + ky) * W + kx;
+    }
+    for (long long img = blockIdx.x; img < n_imgs; img += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < img_floats; i += blockDim.x) xs[i] = x[(size_t)img * img_floats + i];
+        __syncthreads();
+        for (int pix = threadIdx.x; pix < OH * OW; pix += blockDim.x) {
+            const int oy = pix / OW, ox = pix % OW;
+            const float *xp = xs + oy * W + ox;
+            float am[NP], av[NP];
+#pragma unroll
+            for (int n = 0; n < NP; ++n) am[n] = 0.f, av[n] = 0.f;
+#pragma unroll 5
+            for (int k = 0; k < K; ++k) {
+                const float xv = xp[koff[k]], x2 = xv * xv;
+                const float4 *m4 = reinterpret_cast<const float4 *>(wm + k * NP), *v4 = reinterpret_cast<const float4 *>(wv + k * NP);
+#pragma unroll
+                for (int j = 0; j < NP / 4; ++j) {
+                    const float4 a = m4[j], b = v4[j];
+                    am[4 * j] = fmaf(xv, a.x, am[4 * j]), am[4 * j + 1] = fmaf(xv, a.y, am[4 * j + 1]);
+                    am[4 * j + 2] = fmaf(xv, a.z, am[4 * j + 2]), am[4 * j + 3] = fmaf(xv, a.w, am[4 * j + 3]);
+                    av[4 * j] = fmaf(x2, b.x, av[4 * j]), av[4 * j + 1] = fmaf(x2, b.y, av[4 * j + 1]);
+                    av[4 * j + 2] = fmaf(x2, b.z, av[4 * j + 2]), av[4 * j + 3] = fmaf(x2, b.w, av[4 * j + 3]);
+                }
+            }
+            const size_t o = (size_t)img * N * OH * OW + pix;
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                if (n >= N) break;
+                mean_out[o + (size_t)n * OH * OW] = am[n];
+                sd_out[o + (size_t)n * OH * OW] = sqrtf(av[n] + bv[n]);
+            }
+        }
+    }
+}
+
+template <int NP>
+static int launch_conv_moments_direct(const float *x, const float *z, const float *Wm, const float *Wlv, const float *blv,
+                                      float *mean_out, float *sd_out, long long n_imgs, int C, int H, int W, int ks, int N,
+                                      cudaStream_t st) {
+    const int K = C * ks * ks;
+    const size_t smem = sizeof(float) * ((size_t)2 * K * NP + NP + ((K + 3) & ~3) + (size_t)C * H * W);
+    if (smem > 48 * 1024)
+        MNF_CUDA(cudaFuncSetAttribute(conv_moments_direct_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const DeviceProps *dp = device_props();
+    MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
+    long long blocks = n_imgs < (long long)dp->sm_count * 8 ? n_imgs : (long long)dp->sm_count * 8;
+    conv_moments_direct_kernel<NP><<<(unsigned)blocks, 256, smem, st>>>(x, z, Wm, Wlv, blv, mean_out, sd_out, n_imgs, C, H, W, ks, N);
+    return launch_status("conv_moments_direct_kernel");
+}
+
+int conv_pack_weights_f16(const float *z, const float *W_mean, const float *W_log_var, const float *b_log_var, void *Bm,
+                          void *Bv, float *bvar_p, int K, int c_out, int Np, int Kp, void *stream) {
+    MNF_REQUIRE(W_mean && W_log_var && b_log_var && Bm && Bv && bvar_p, MNF_E_ARG, "NULL pointer");
+    conv_pack_weights_f16_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(W_mean, W_log_var, b_log_var, z, c_out, K, Np, Kp,
+                                                                     (__half *)Bm, (__half *)Bv, bvar_p);
+    return launch_status("conv_pack_weights_kernel");
+}
+
 }  // namespace mnf
 
 using namespace mnf;
@@ -444,6 +547,14 @@ int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, cons
     const long long M = (long long)n_imgs * OH * OW;
     MNF_REQUIRE(M <= 0x7fffffff - 64, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
     MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "too many filter taps");
+    if (n_imgs == 0) return 0;
+    if (c_in * ksize * ksize <= 64 && c_out <= 32 && c_in * height * width <= 4096) {  // few taps, few channels: direct form
+        if (c_out <= 20)
+            return launch_conv_moments_direct<20>(x, z, W_mean, W_log_var, b_log_var, mean_out, sd_out, n_imgs, c_in, height,
+                                                  width, ksize, c_out, (cudaStream_t)stream);
+        return launch_conv_moments_direct<32>(x, z, W_mean, W_log_var, b_log_var, mean_out, sd_out, n_imgs, c_in, height, width,
+                                              ksize, c_out, (cudaStream_t)stream);
+    }
     MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)(n_imgs > 0 ? n_imgs : 1), c_in, height, width, ksize,
                   OH, OW, W_mean, W_log_var, b_log_var, z, mean_out, NoiseSrc{nullptr, 0, 0, 0}, 0, sd_out, {}};
     for (int k = 0; k < p.K; ++k) {

@@ -17,6 +17,12 @@
 #include "tc_common.cuh"
 
 namespace mnf {
+// fp16 weights of the implicit-GEMM conv (mnf_layers.cu): Bm = fp16(W_mean * z), Bv = fp16(exp(W_log_var) * 2^8), [Np, Kp]
+int conv_pack_weights_f16(const float *z, const float *W_mean, const float *W_log_var, const float *b_log_var, void *Bm,
+                          void *Bv, float *bvar_p, int K, int c_out, int Np, int Kp, void *stream);
+}  // namespace mnf
+
+namespace mnf {
 namespace tc {
 
 constexpr uint32_t A_BYTES = BM * BK * 4;
@@ -391,8 +397,13 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 
 // =====================================================================================================================
 // Implicit-GEMM MNFConv2d (no im2col in HBM): both moments of the local reparameterisation from ONE pass over x.
-//   mean[m, n] = sum_k A[m, k] Bm[n, k]          A[m, k]  = tf32(x[img, ci, oy + ky, ox + kx])     (generated in smem)
-//   sd[m, n]   = sqrt(sum_k A2[m, k] Bv[n, k] + exp(b_log_var[n]))    A2 = tf32(x^2)
+//   mean[m, n] = sum_k A[m, k] Bm[n, k]          A[m, k]  = fp16(x[img, ci, oy + ky, ox + kx])     (generated in smem)
+//   sd[m, n]   = sqrt(sum_k A2[m, k] Bv[n, k] + exp(b_log_var[n]))    A2 = fp16(x^2)
+// Operands are fp16 (kind::f16, fp32 accumulation): the 11-bit significand of TF32 -- the 2e-3 tolerance class BASELINE.json
+// states for the MNF GEMMs -- at half the bytes.  The kernel is bound by shared memory (operand tiles written by the
+// generators and read by the tensor core: r01 ncu, 152 M wavefronts, tensor pipe 20 %); a k-block of 128-byte rows now
+// holds 64 taps instead of 32, so the generators' stores, the MMAs' reads and the MMA count per tile all halve.
+// exp(W_log_var) (~1e-4 at the prior's -9) is packed times 2^8 to stay in fp16's normal range; the epilogue undoes it.
 // rows m are pool-major (4 * window + 2 * (oy & 1) + (ox & 1)), k = (ci * ks + ky) * ks + kx padded to Kp.
 // A tile is 128 rows = IMGS whole images (128 % (OH * OW) == 0).  Roles (512 threads): warp 0 = TMA producer of the
 // two weight tiles, warp 1 = single-thread tcgen05.mma issuer (two MMAs per k-step into two 64-column TMEM
@@ -402,11 +413,28 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 // descriptor expects, then fence.proxy.async + mbarrier arrive), warps 12-15 = epilogue (tcgen05.ld -> mean, sd rows).  The materialised im2col this replaces wrote and re-read
 // 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
 // =====================================================================================================================
-constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_THREADS = 512, CONV_MAX_KP = 512;
+constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_THREADS = 512, CONV_MAX_KP = 512, CONV_BK = 64;
+constexpr float CONV_VAR_SCALE = 256.f;  // must match conv_pack_weights_f16_kernel (mnf_layers.cu)
 struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image (0 for the zero padding of K); travels as a
     int off[CONV_MAX_KP];  // kernel parameter so that the generators read it through the uniform datapath
 };
-constexpr uint32_t CONV_B_BYTES = CONV_BN * BK * 4, CONV_STAGE_BYTES = 2 * A_BYTES + 2 * CONV_B_BYTES;
+constexpr uint32_t CONV_B_BYTES = CONV_BN * CONV_BK * 2, CONV_STAGE_BYTES = 2 * A_BYTES + 2 * CONV_B_BYTES;
+static_assert(BM * CONV_BK * 2 == A_BYTES, "an fp16 k-block of 64 taps fills the same 128-byte rows as 32 fp32 values");
+// tcgen05 instruction descriptor, kind::f16: D = F32, A = B = F16, both K-major
+constexpr uint32_t conv_f16_idesc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t conv_pack_h2(float lo, float hi) {  // `lo` lands at the lower address
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -462,7 +490,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
 
     const long long M = n_imgs * RPI;
     const long long n_tiles = (n_imgs + IMGS - 1) / IMGS;
-    const int n_kblk = Kp / BK;
+    const int n_kblk = Kp / CONV_BK;
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer: the two weight tiles of every k-block ----------------
@@ -473,8 +501,8 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                 mbar_wait(empty(stage), phase ^ 1u);
                 mbar_expect_tx(full_b(stage), 2 * CONV_B_BYTES);
                 const uint32_t sb = base + stage * CONV_STAGE_BYTES + 2 * A_BYTES;
-                tma_load_2d(sb, &map_bm, full_b(stage), kb * BK, 0);
-                tma_load_2d(sb + CONV_B_BYTES, &map_bv, full_b(stage), kb * BK, 0);
+                tma_load_2d(sb, &map_bm, full_b(stage), kb * CONV_BK, 0);
+                tma_load_2d(sb + CONV_B_BYTES, &map_bv, full_b(stage), kb * CONV_BK, 0);
                 if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
             }
         }
@@ -494,9 +522,9 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                 const uint64_t a1 = make_smem_desc(sa), a2 = make_smem_desc(sa + A_BYTES);
                 const uint64_t b1 = make_smem_desc(sa + 2 * A_BYTES), b2 = make_smem_desc(sa + 2 * A_BYTES + CONV_B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_tf32(d_mean, a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), (kb | k) != 0, Cfg<CONV_BN>::kInstrDesc);
-                    umma_tf32(d_var, a2 + (uint64_t)(2 * k), b2 + (uint64_t)(2 * k), (kb | k) != 0, Cfg<CONV_BN>::kInstrDesc);
+                for (int k = 0; k < CONV_BK / 16; ++k) {  // 16 fp16 = 32 bytes per MMA inside the 128-byte swizzle atom
+                    umma_f16(d_mean, a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), (kb | k) != 0, conv_f16_idesc(BM, CONV_BN));
+                    umma_f16(d_var, a2 + (uint64_t)(2 * k), b2 + (uint64_t)(2 * k), (kb | k) != 0, conv_f16_idesc(BM, CONV_BN));
                 }
                 umma_commit(empty(stage));
                 if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
@@ -505,7 +533,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             if (++acc == CONV_ACC) acc = 0, acc_phase ^= 1u;
         }
     } else if (warp >= 4 && warp < 12) {
-        // ---------------- A generators: 256 threads, two per tile row (four 16-byte chunks of the k-block each) ----------------
+        // ---------------- A generators: 256 threads, two per tile row (four 16-byte chunks = 32 taps of the k-block each) ----------------
         const int gt = threadIdx.x - 128, ml = gt & 127, half = gt >> 7;
         const int img_l = ml / RPI, p = ml % RPI, q = p & 3, w = p >> 2;
         const int row_base = img_l * CHW + (2 * (w / PW) + (q >> 1)) * W + 2 * (w % PW) + (q & 1);
@@ -531,9 +559,9 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");  // every generator's copies of this tile have landed
             const float *xt = xs + (size_t)buf * IMGS * CHW;
-            // software pipeline: the 16 taps of the NEXT k-block are gathered into registers right after this one is
+            // software pipeline: the 32 taps of the NEXT k-block are gathered into registers right after this one is
             // published, so their shared-memory latency overlaps the wait for the stage to come back from the MMAs
-            float v[16];
+            float v[32];
             // no validity checks: the zero padding of K is done by the WEIGHT tiles (their columns >= K are zero and the
             // padded taps point at offset 0, a finite value), and rows past the last image of a half-filled tile read
             // whatever the buffer holds -- their outputs are never stored and rows do not mix in an MMA
@@ -541,9 +569,9 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             auto gather = [&](int kb) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int kk = kb * BK + 4 * (half * 4 + cc);
+                    const int kk = kb * CONV_BK + 8 * (half * 4 + cc);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) v[4 * cc + u] = xrow[taps.off[kk + u]];
+                    for (int u = 0; u < 8; ++u) v[8 * cc + u] = xrow[taps.off[kk + u]];
                 }
             };
             gather(0);
@@ -553,10 +581,12 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const int pos = ((half * 4 + cc) ^ swz) * 16;
-                    const float v0 = v[4 * cc], v1 = v[4 * cc + 1], v2 = v[4 * cc + 2], v3 = v[4 * cc + 3];
-                    *reinterpret_cast<float4 *>(sa + pos) = make_float4(rn_tf32(v0), rn_tf32(v1), rn_tf32(v2), rn_tf32(v3));
-                    *reinterpret_cast<float4 *>(sa + A_BYTES + pos) =
-                        make_float4(rn_tf32(v0 * v0), rn_tf32(v1 * v1), rn_tf32(v2 * v2), rn_tf32(v3 * v3));
+                    const float *q = v + 8 * cc;
+                    *reinterpret_cast<uint4 *>(sa + pos) =
+                        make_uint4(conv_pack_h2(q[0], q[1]), conv_pack_h2(q[2], q[3]), conv_pack_h2(q[4], q[5]), conv_pack_h2(q[6], q[7]));
+                    *reinterpret_cast<uint4 *>(sa + A_BYTES + pos) =
+                        make_uint4(conv_pack_h2(q[0] * q[0], q[1] * q[1]), conv_pack_h2(q[2] * q[2], q[3] * q[3]),
+                                   conv_pack_h2(q[4] * q[4], q[5] * q[5]), conv_pack_h2(q[6] * q[6], q[7] * q[7]));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
                 mbar_arrive(full_a(stage));
@@ -590,8 +620,10 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                                                                             __uint_as_float(rm[j + 2]), __uint_as_float(rm[j + 3]));
                         const float4 bv = *reinterpret_cast<const float4 *>(sbv + c * 32 + j);
                         *reinterpret_cast<float4 *>(srow + j) =
-                            make_float4(sqrtf(__uint_as_float(rv[j]) + bv.x), sqrtf(__uint_as_float(rv[j + 1]) + bv.y),
-                                        sqrtf(__uint_as_float(rv[j + 2]) + bv.z), sqrtf(__uint_as_float(rv[j + 3]) + bv.w));
+                            make_float4(sqrtf(fmaf(__uint_as_float(rv[j]), 1.f / CONV_VAR_SCALE, bv.x)),
+                                        sqrtf(fmaf(__uint_as_float(rv[j + 1]), 1.f / CONV_VAR_SCALE, bv.y)),
+                                        sqrtf(fmaf(__uint_as_float(rv[j + 2]), 1.f / CONV_VAR_SCALE, bv.z)),
+                                        sqrtf(fmaf(__uint_as_float(rv[j + 3]), 1.f / CONV_VAR_SCALE, bv.w)));
                     }
                 }
             }
@@ -660,14 +692,29 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
 // smem of conv_implicit_kernel for this geometry (0 = not eligible)
 static size_t conv_implicit_smem(int c_in, int height, int width, int ksize, int Kp, int Np) {
     const int OH = height - ksize + 1, OW = width - ksize + 1, RPI = OH * OW, CHW = c_in * height * width;
-    if (RPI <= 0 || BM % RPI != 0 || Np > CONV_BN || Np % 32 != 0 || CHW % 4 != 0 || Kp % BK != 0) return 0;
+    if (RPI <= 0 || BM % RPI != 0 || Np > CONV_BN || Np % 32 != 0 || CHW % 4 != 0 || Kp % CONV_BK != 0) return 0;
     if (Kp > CONV_MAX_KP) return 0;
     const size_t bytes = (size_t)CONV_STAGES * CONV_STAGE_BYTES + 1024 + 256 + sizeof(float) * CONV_BN +
                          sizeof(float) * 2 * (size_t)(BM / RPI) * CHW + 16;
     return bytes <= 227 * 1024 ? bytes : 0;
 }
 
-static int launch_conv_implicit(const float *x, const float *Bm, const float *Bv, const float *bvar_log, float *mean, float *sd,
+// fp16 weight matrix [rows, cols] (row pitch cols halves) as a TMA map of 64 x box_rows boxes, 128-byte swizzle
+static int make_map_f16(CUtensorMap *map, const void *ptr, int rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    MNF_REQUIRE(fn != nullptr, MNF_E_DEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)CONV_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MNF_REQUIRE(r == CUDA_SUCCESS, MNF_E_ARG, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rows=%d cols=%d)", (int)r, rows, cols);
+    return 0;
+}
+
+// Bm / Bv: fp16 [Np, Kp] from conv_pack_weights_f16_kernel
+static int launch_conv_implicit(const float *x, const void *Bm, const void *Bv, const float *bvar_log, float *mean, float *sd,
                                 long long n_imgs, int c_in, int height, int width, int ksize, int Kp, int Np,
                                 cudaStream_t stream) {
     const DeviceProps *dp = device_props();
@@ -677,9 +724,9 @@ static int launch_conv_implicit(const float *x, const float *Bm, const float *Bv
     MNF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)mean % 16) == 0 && ((uintptr_t)sd % 16) == 0, MNF_E_ALIGN,
                 "pointers must be 16-byte aligned");
     CUtensorMap mbm, mbv;
-    int rc = make_map(&mbm, Bm, Np, Kp, CONV_BN);
+    int rc = make_map_f16(&mbm, Bm, Np, Kp, CONV_BN);
     if (rc) return rc;
-    rc = make_map(&mbv, Bv, Np, Kp, CONV_BN);
+    rc = make_map_f16(&mbv, Bv, Np, Kp, CONV_BN);
     if (rc) return rc;
     MNF_CUDA(cudaFuncSetAttribute(conv_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int RPI = (height - ksize + 1) * (width - ksize + 1), IMGS = BM / RPI;
@@ -1160,8 +1207,9 @@ int64_t mnf_conv_tc_workspace(int64_t n_imgs, int c_in, int height, int width, i
     const int OH = height - ksize + 1, OW = width - ksize + 1;
     const int64_t Kp = (c_in * ksize * ksize + 31) / 32 * 32, Np = (c_out + 31) / 32 * 32;
     const int64_t M = n_imgs * OH * OW;
-    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, (int)Kp, (int)Np) != 0)
-        return 2 * M * Np + 2 * Np * Kp + Np + 64;  // implicit GEMM: mean, sd, packed weights -- no im2col
+    const int64_t Kp64 = (c_in * ksize * ksize + 63) / 64 * 64;
+    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, (int)Kp64, (int)Np) != 0)
+        return 2 * M * Np + 2 * Np * Kp64 + Np + 64;  // implicit GEMM: mean, sd, packed weights -- no im2col
     return 2 * M * Kp + M * Np + 2 * Np * Kp + Np + 64;
 }
 
@@ -1194,14 +1242,14 @@ int mnf_conv2d_forward_tc_z(const float *x, const float *z, const float *z_rows,
     MNF_REQUIRE(n_imgs >= 0 && M <= 0x7fffffff - 256, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
     if (n_imgs == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, Kp, Np) != 0) {
-        // implicit GEMM: x is read once, the A / A^2 tiles are generated in shared memory
-        float *mean = workspace, *sdp = mean + (size_t)M * Np, *Bm = sdp + (size_t)M * Np, *Bv = Bm + (size_t)Np * Kp,
-              *bvar_p = Bv + (size_t)Np * Kp;
-        int rc = mnf_conv_tc_stage(x, z, W_mean, W_log_var, b_log_var, nullptr, nullptr, Bm, Bv, bvar_p, n_imgs, c_in, height,
-                                   width, c_out, ksize, Np, Kp, stream);
+    const int Kp64 = (c_in * ksize * ksize + 63) / 64 * 64;
+    if (OW % 4 == 0 && tc::conv_implicit_smem(c_in, height, width, ksize, Kp64, Np) != 0) {
+        // implicit GEMM: x is read once, the fp16 A / A^2 tiles are generated in shared memory
+        float *mean = workspace, *sdp = mean + (size_t)M * Np, *Bm = sdp + (size_t)M * Np, *Bv = Bm + (size_t)Np * Kp64,
+              *bvar_p = Bv + (size_t)Np * Kp64;
+        int rc = mnf::conv_pack_weights_f16(z, W_mean, W_log_var, b_log_var, Bm, Bv, bvar_p, c_in * ksize * ksize, c_out, Np, Kp64, stream);
         if (rc) return rc;
-        rc = tc::launch_conv_implicit(x, Bm, Bv, bvar_p, mean, sdp, n_imgs, c_in, height, width, ksize, Kp, Np, st);
+        rc = tc::launch_conv_implicit(x, Bm, Bv, bvar_p, mean, sdp, n_imgs, c_in, height, width, ksize, Kp64, Np, st);
         if (rc) return rc;
         const long long total = n_imgs * (OH / 2) * (OW / 4) * c_out;
         long long blocks = (total + 255) / 256;
