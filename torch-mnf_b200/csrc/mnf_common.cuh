@@ -38,13 +38,40 @@ struct Philox {
 
 __device__ __forceinline__ float u32_to_unit(uint32_t u) { return ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
-// two standard normals from two 32-bit words
+// two standard normals from two 32-bit words (Box-Muller).  The uniforms are built in the mantissa ([1, 2) bit pattern,
+// 23 random bits: no I2F on the XU pipe), the radius uses one LG2 and one approximate SQRT -- the noise kernels are
+// bound by this arithmetic, and only the distribution matters (every kernel draws through this one definition).
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-    const float r = sqrtf(-2.f * __logf(u32_to_unit(a)));
+    const float u1 = 2.f - __uint_as_float((a >> 9) | 0x3f800000u);  // (0, 1]
+    const float u2 = __uint_as_float((b >> 9) | 0x3f800000u) - 1.f;  // [0, 1)
+    float lg, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));  // sqrt(-2 ln u1)
     float s, c;
-    __sincosf(6.283185307179586f * u32_to_unit(b), &s, &c);
+    __sincosf(6.283185307179586f * u2, &s, &c);
     return make_float2(r * c, r * s);
 }
+
+// division of a non-negative 32-bit index by a run-time constant without the integer-divide sequence
+// (n < 2^31; multiplier / shift found on the host): the noise / pool passes decode four indices per element
+struct FastDiv {
+    uint32_t d, m, s;
+    __host__ FastDiv() : d(1), m(0), s(0) {}
+    __host__ explicit FastDiv(uint32_t div) : d(div), m(0), s(0) {
+        if (div > 1) {
+            uint32_t l = 0;
+            while ((1ull << l) < div) ++l;  // ceil(log2 div)
+            const uint32_t p = 31 + l;
+            m = (uint32_t)(((1ull << p) + div - 1) / div);
+            s = p - 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, m) >> s; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
 
 // standard normal for global element index e of noise stream `stream`
 __device__ __forceinline__ float philox_normal(const Philox &g, uint64_t e, uint32_t stream) {

@@ -266,18 +266,35 @@ struct MnfConvProb {
 // zs (optional): per-sample channel scales [n_z, C] -- the per-sample conv-z option of the MC predict entry point
 // (SURVEY 8f-4): z scales OUTPUT channels (mnf_conv.py:73), so with mean evaluated for z = 1 row r's mean is
 // zs[r / rows_per_z, c] * mean.
+struct PoolDivs {  // run-time divisors of the index decode, as multiply-shift pairs
+    FastDiv pw2, ph, c;
+};
+
+template <bool IDX32>
 __global__ void conv_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd, int n_unique,
                                        NoiseSrc eps, float *__restrict__ out, long long n_rows, int C, int OH, int OW,
-                                       const float *__restrict__ zs, long long rows_per_z) {
+                                       const float *__restrict__ zs, long long rows_per_z, const PoolDivs dv) {
     // one thread = two horizontally adjacent pooled pixels = a 2 x 4 patch of the un-pooled map, so that each
     // Philox block (4 consecutive elements) is generated once and fully used.  Needs OW % 4 == 0 (host checks).
+    // IDX32: fewer than 2^31 work items -- the decode runs on 32-bit multiply-shift divisions (the 64-bit
+    // divide sequences were a third of the kernel's instructions).
     const int PH = OH >> 1, PW = OW >> 1, PW2 = PW >> 1;
     const long long total = n_rows * C * PH * PW2;
     const Philox rng(eps.seed);
     for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total;
          o += (long long)gridDim.x * blockDim.x) {
-        const int px2 = (int)(o % PW2), py = (int)((o / PW2) % PH), c = (int)((o / ((long long)PW2 * PH)) % C);
-        const long long r = o / ((long long)PW2 * PH * C);
+        int px2, py, c;
+        long long r;
+        if constexpr (IDX32) {
+            uint32_t t, a, b, cc;
+            dv.pw2.divmod((uint32_t)o, t, a);
+            dv.ph.divmod(t, t, b);
+            dv.c.divmod(t, t, cc);
+            px2 = (int)a, py = (int)b, c = (int)cc, r = (long long)t;
+        } else {
+            px2 = (int)(o % PW2), py = (int)((o / PW2) % PH), c = (int)((o / ((long long)PW2 * PH)) % C);
+            r = o / ((long long)PW2 * PH * C);
+        }
         const size_t ub = (((size_t)(r % n_unique) * C + c) * OH + 2 * py) * OW + 4 * px2;
         const long long le = ((r * C + c) * OH + 2 * py) * OW + 4 * px2;  // index in the un-pooled [R, C, OH, OW]
         const long long ge = le + (long long)eps.row_offset * C * OH * OW;
@@ -587,9 +604,15 @@ int mnf_conv_noise_relu_pool_z(const float *mean, const float *sd, int64_t n_uni
     const long long total = (long long)n_rows * channels * (out_h / 2) * (out_w / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    conv_noise_pool_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        mean, sd, (int)n_unique, NoiseSrc{eps, seed, noise_stream, row_offset}, out, n_rows, channels, out_h, out_w, z_rows,
-        rows_per_z);
+    PoolDivs dv;
+    dv.pw2 = FastDiv((uint32_t)(out_w / 4)), dv.ph = FastDiv((uint32_t)(out_h / 2)), dv.c = FastDiv((uint32_t)channels);
+    const NoiseSrc src{eps, seed, noise_stream, row_offset};
+    if (total < 0x7fffffffLL)
+        conv_noise_pool_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            mean, sd, (int)n_unique, src, out, n_rows, channels, out_h, out_w, z_rows, rows_per_z, dv);
+    else
+        conv_noise_pool_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            mean, sd, (int)n_unique, src, out, n_rows, channels, out_h, out_w, z_rows, rows_per_z, dv);
     return launch_status("conv_noise_pool_kernel");
 }
 

@@ -646,20 +646,35 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
 // consecutive ox of one row, so two calls cover the patch (the GEMM-epilogue form of this stage, mode 5, spends a
 // whole Philox call per element on 8 warps per SM and took 3x longer than this full-occupancy pass).
 // Needs OW % 4 == 0.  Channels are the fastest thread index: loads of mean / sd are contiguous across the warp.
+struct RowsPoolDivs {  // run-time divisors of the index decode, as multiply-shift pairs
+    FastDiv c, gx, ph;
+};
+template <bool IDX32>
 __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, const float *__restrict__ sd,
                                             const float *__restrict__ eps, uint64_t seed, uint32_t noise_stream,
                                             uint64_t row_offset, float *__restrict__ out, long long n_imgs, int C, int Np,
-                                            int OH, int OW, const float *__restrict__ zs, long long rows_per_z) {
+                                            int OH, int OW, const float *__restrict__ zs, long long rows_per_z,
+                                            const RowsPoolDivs dv) {
     const int PH = OH >> 1, PW = OW >> 1, GX = OW >> 2;
     const long long total = n_imgs * PH * GX * C;
     const Philox rng(seed);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(i % C);
-        long long t = i / C;
-        const int gx = (int)(t % GX);
-        t /= GX;
-        const int py = (int)(t % PH);
-        const long long img = t / PH;
+        int n, gx, py;
+        long long img;
+        if constexpr (IDX32) {  // fewer than 2^31 work items: multiply-shift divisions instead of 64-bit divides
+            uint32_t t, a, b, cc;
+            dv.c.divmod((uint32_t)i, t, a);
+            dv.gx.divmod(t, t, b);
+            dv.ph.divmod(t, t, cc);
+            n = (int)a, gx = (int)b, py = (int)cc, img = (long long)t;
+        } else {
+            n = (int)(i % C);
+            long long t = i / C;
+            gx = (int)(t % GX);
+            t /= GX;
+            py = (int)(t % PH);
+            img = t / PH;
+        }
         float best0 = 0.f, best1 = 0.f;  // ReLU folded into the max
         const float zc = zs ? zs[(img / rows_per_z) * C + n] : 1.f;  // per-sample conv z (mean was evaluated for z = 1)
 #pragma unroll
@@ -687,6 +702,20 @@ __global__ void conv_rows_noise_pool_kernel(const float *__restrict__ mean, cons
         float *o = out + ((img * C + n) * PH + py) * PW + 2 * gx;
         o[0] = best0, o[1] = best1;
     }
+}
+
+static int launch_rows_noise_pool(const float *mean, const float *sd, const float *eps, uint64_t seed, uint32_t noise_stream,
+                                  uint64_t row_offset, float *out, long long n_imgs, int C, int Np, int OH, int OW,
+                                  const float *zs, long long rows_per_z, long long total, unsigned blocks, cudaStream_t st) {
+    RowsPoolDivs dv;
+    dv.c = FastDiv((uint32_t)C), dv.gx = FastDiv((uint32_t)(OW / 4)), dv.ph = FastDiv((uint32_t)(OH / 2));
+    if (total < 0x7fffffffLL)
+        conv_rows_noise_pool_kernel<true><<<blocks, 256, 0, st>>>(mean, sd, eps, seed, noise_stream, row_offset, out, n_imgs, C, Np,
+                                                                 OH, OW, zs, rows_per_z, dv);
+    else
+        conv_rows_noise_pool_kernel<false><<<blocks, 256, 0, st>>>(mean, sd, eps, seed, noise_stream, row_offset, out, n_imgs, C, Np,
+                                                                  OH, OW, zs, rows_per_z, dv);
+    return launch_status("conv_rows_noise_pool_kernel");
 }
 
 // smem of conv_implicit_kernel for this geometry (0 = not eligible)
@@ -1254,9 +1283,8 @@ int mnf_conv2d_forward_tc_z(const float *x, const float *z, const float *z_rows,
         const long long total = n_imgs * (OH / 2) * (OW / 4) * c_out;
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sdp, eps, seed, noise_stream, row_offset, out,
-                                                                       n_imgs, c_out, Np, OH, OW, z_rows, rows_per_z);
-        return launch_status("conv_rows_noise_pool_kernel");
+        return tc::launch_rows_noise_pool(mean, sdp, eps, seed, noise_stream, row_offset, out, n_imgs, c_out, Np, OH, OW, z_rows,
+                                          rows_per_z, total, (unsigned)blocks, st);
     }
     float *a_mean = workspace, *a_var = a_mean + (size_t)M * Kp, *sd = a_var + (size_t)M * Kp, *Bm = sd + (size_t)M * Np,
           *Bv = Bm + (size_t)Np * Kp, *bvar_p = Bv + (size_t)Np * Kp;
@@ -1277,9 +1305,8 @@ int mnf_conv2d_forward_tc_z(const float *x, const float *z, const float *z_rows,
         const long long total = n_imgs * (OH / 2) * (OW / 4) * c_out;
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        tc::conv_rows_noise_pool_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, sd, eps, seed, noise_stream, row_offset, out,
-                                                                       n_imgs, c_out, Np, OH, OW, z_rows, rows_per_z);
-        return launch_status("conv_rows_noise_pool_kernel");
+        return tc::launch_rows_noise_pool(mean, sd, eps, seed, noise_stream, row_offset, out, n_imgs, c_out, Np, OH, OW, z_rows,
+                                          rows_per_z, total, (unsigned)blocks, st);
     }
     MNF_REQUIRE(z_rows == nullptr, MNF_E_SHAPE, "per-sample conv z needs an output width that is a multiple of 4");
     em.mode = 5, em.sd = sd, em.sd_rows = 1, em.eps = eps, em.seed = seed, em.noise_stream = noise_stream;
