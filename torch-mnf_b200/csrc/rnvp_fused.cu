@@ -306,12 +306,12 @@ rnvp_out_gate_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_con
     }
 }
 
-bool eligible(int dim, int h) { return dim % 64 == 0 && dim >= 64 && h >= 1 && h <= HP - 1; }
+bool eligible(int dim, int h) { return dim % CH == 0 && dim >= 64 && h >= 1 && h <= HP - 1; }
 
 int launch(const float *y, const float *Wts, const Params &p, cudaStream_t stream) {
     const DeviceProps *dp = device_props();
     MNF_REQUIRE(dp != nullptr && dp->cc_major == 10, MNF_E_DEVICE, "tcgen05 path needs an sm_100 device");
-    MNF_REQUIRE(p.dim % 64 == 0 && p.n_rows >= 1 && p.n_rows <= 0x7fffffff - 256, MNF_E_SHAPE, "bad shape for the fused RNVP gate");
+    MNF_REQUIRE(p.dim % CH == 0 && p.n_rows >= 1 && p.n_rows <= 0x7fffffff - 256, MNF_E_SHAPE, "bad shape for the fused RNVP gate");
     MNF_REQUIRE(((uintptr_t)p.z % 16) == 0 && (!p.mz_next || ((uintptr_t)p.mz_next % 16) == 0) &&
                     (!p.xz_out || ((uintptr_t)p.xz_out % 16) == 0) && (!p.xmul || ((uintptr_t)p.xmul % 16) == 0),
                 MNF_E_ALIGN, "pointers must be 16-byte aligned");
