@@ -130,6 +130,23 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
                        int flags, float *workspace, const mnf_gather_out *gather /* may be NULL */,
                        void *stream);
 
+/* A flow program bound once, for call sites that evaluate the same model over and over (BASELINE config 1: 4096
+ * points per call, where a call is latency-bound): the handle keeps a host copy of the descriptors and the device
+ * pointers of the packed parameters and of the pre-staged net image, so that a log-probability call is five arguments
+ * and no validation.  The caller owns every device buffer and must keep them alive and UNCHANGED while the handle is in
+ * use (re-create it after a parameter update); the handle itself is a small host allocation freed by
+ * mnf_flow_handle_destroy.  staged: mnf_flow_stack_stage output for these parameters or NULL; workspace:
+ * mnf_flow_stack_workspace(n_ops, max_rows, dim) floats or NULL if that is 0 (with `staged`, batches below 65536 rows
+ * need none).
+ *   mnf_flow_handle_log_prob: log_prob[r] = log|det J|(x_r) + standard-normal log-density of the result, i.e.
+ *   NormalizingFlowModel.log_prob (flows/core.py:46-49 over :27-35) for an N(0, I) base, one fused pass. */
+typedef struct mnf_flow_handle mnf_flow_handle;
+int mnf_flow_handle_create(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
+                           const float *staged, float *workspace, int64_t workspace_rows, mnf_flow_handle **out);
+void mnf_flow_handle_destroy(mnf_flow_handle *handle);
+int mnf_flow_handle_log_prob(const mnf_flow_handle *handle, const float *x, float *log_prob, int64_t n_rows,
+                             void *stream);
+
 /* Reverse-mode pass of mnf_flow_stack_run (the reference trains through torch autograd:
  * tests/test_flows.py:14-31 calls loss.backward() on -(log_det + base_log_prob)).
  *   x              [n_rows, dim]         the input the forward run saw
@@ -373,6 +390,27 @@ typedef struct mnf_kl_args {
     float *out;                       /* [5]                                                   */
 } mnf_kl_args;
 int mnf_kl_div(const mnf_kl_args *args_host, void *stream);
+
+/* The whole kl_div() of a layer (mnf_linear.py:66-90 / mnf_conv.py:90-133) in THREE launches: one thread-block cluster
+ * draws z0 = q0_mean + sqrt(exp(q0_log_var)) eps_z and runs flow_q (-> z, ld_q) and flow_r (-> zT, ld_r) on that single
+ * row, then the weight pass and the final reduction of mnf_kl_div.  Needs single-Linear RNVP conditioners of width <= 64
+ * and at most MNF_KL_MAX_FLOWS flows per stack (otherwise: mnf_sample_z0 + mnf_rnvp_forward + mnf_kl_div).
+ *   kl        as for mnf_kl_div, except that kl.z, kl.zT ([n_in] linear / [n_out] conv) and kl.ld_q, kl.ld_r ([1]) are
+ *             OUTPUT buffers of this call; kl.workspace: 2 * max(n_out, n_in*k*k) + 64 floats.
+ *   eps_z     injected z0 noise or NULL (Philox stream z_stream); masks[f]: injected Bernoulli mask of flow f or NULL
+ *             (Philox stream mask_streams[f]); flows / masks / mask_streams hold flow_q's flows first, then flow_r's. */
+#define MNF_KL_MAX_FLOWS 4
+typedef struct mnf_kl_fused_args {
+    mnf_kl_args kl;
+    const float *q0_mean;
+    const float *eps_z;
+    uint32_t z_stream;
+    int32_t n_flows_q, n_flows_r, reserved;
+    mnf_rnvp_flow flows[2 * MNF_KL_MAX_FLOWS];
+    const float *masks[2 * MNF_KL_MAX_FLOWS];
+    uint32_t mask_streams[2 * MNF_KL_MAX_FLOWS];
+} mnf_kl_fused_args;
+int mnf_kl_div_fused(const mnf_kl_fused_args *args_host, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Training path of the MNF layers.  The reference differentiates MNFLinear.forward /

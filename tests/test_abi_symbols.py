@@ -35,11 +35,12 @@ def test_binding_matches_header():
 
 def test_struct_layouts_match_header():
     from torch_mnf import _lib
-    from torch_mnf.layers._mnf_ops import KlArgs, RnvpFlow
+    from torch_mnf.layers._mnf_ops import KlArgs, KlFusedArgs, RnvpFlow
 
     assert ctypes.sizeof(_lib.FlowOp) == 4 * (5 + 7 + 2 + 2)  # mnf_flow_op: 16 32-bit words
     assert ctypes.sizeof(RnvpFlow) == 4 * 5 + 4 + 8 * (4 + 4 + 4)  # n_net, sizes[4], pad, 12 pointers
     assert ctypes.sizeof(KlArgs) == 16 + 8 * 14 + 8 + 8 + 8 * 2
+    assert ctypes.sizeof(KlFusedArgs) == ctypes.sizeof(KlArgs) + 8 + 8 + 16 + 8 * ctypes.sizeof(RnvpFlow) + 8 * 8 + 8 * 4
     assert ctypes.sizeof(_lib.GatherOut) == 4 + 4 + 8 + 8 * 8 + 8  # mnf_gather_out
 
 

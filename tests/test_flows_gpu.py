@@ -355,3 +355,24 @@ def test_conditioner_free_stack_streaming_kernel():
             torch.testing.assert_close(b.cpu(), ref_ld, rtol=1e-5, atol=1e-5)
     lp = model.log_prob(x.cuda())
     torch.testing.assert_close(lp.cpu(), flows_cpu.log_prob(sd, specs, x), rtol=1e-5, atol=5e-5)
+
+
+@pytest.mark.parametrize("name,n_rows", [("cfg1_shape", 4096), ("cfg2_shape", 777), ("cfg2_shape", 70001), ("nsf_wide_d6", 501)])
+def test_bound_log_prob_equals_module_call(name, n_rows):
+    """NormalizingFlowModel.log_prob_fn (mnf_flow_handle_*: the program bound once) returns exactly what log_prob
+    returns, for the staged small-batch kernel, the large-batch kernel and the interpreter."""
+    specs = ORACLE_CASES[name]
+    model = load_flow_model(specs, random_flow_sd(specs, seed=2, scale=0.4), return_intermediates=False)
+    dim = specs[0]["dim"]
+    x = 1.2 * torch.randn(n_rows, dim, generator=torch.Generator().manual_seed(n_rows)).cuda()
+    f = model.log_prob_fn(max_rows=n_rows)
+    want = model.log_prob(x)
+    assert torch.equal(f(x), want)
+    out = torch.empty(n_rows, device="cuda")
+    assert f(x, out) is out and torch.equal(out, want)
+    assert torch.equal(f(x[: n_rows // 2].contiguous()), model.log_prob(x[: n_rows // 2].contiguous()))
+    with pytest.raises(RuntimeError):
+        if n_rows > 65535:
+            f(torch.cat([x, x]))  # more rows than the bound workspace holds
+        else:
+            raise RuntimeError("staged small-batch programs need no workspace")

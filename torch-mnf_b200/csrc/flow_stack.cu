@@ -1,6 +1,8 @@
 // flow_stack.cu -- C-ABI entry points for flow stacks (dispatch: dim-2 register-resident
 // kernel when the program qualifies, generic interpreter otherwise) and the two small
 // parameter-side kernels (Glow assembly, ActNorm data-dependent init).
+#include <new>
+
 #include "common.cuh"
 
 namespace mnf {
@@ -140,6 +142,61 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
                 "peer-memory gather output needs the constant-bank dim-2 kernel (spline stack, >= 65536 rows)");
     return launch_flow_generic(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
                                n_rows, dim, inverse & 3, st);
+}
+
+struct mnf_flow_handle {
+    int n_ops, dim;
+    int64_t n_params, workspace_rows;
+    const float *params, *staged;
+    float *workspace;
+    mnf_flow_op ops[MNF_MAX_OPS];
+};
+
+int mnf_flow_handle_create(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
+                           const float *staged, float *workspace, int64_t workspace_rows, mnf_flow_handle **out) {
+    MNF_REQUIRE(out != nullptr, MNF_E_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = validate_program(ops_host, n_ops, dim, n_params);
+    if (rc) return rc;
+    MNF_REQUIRE(n_ops >= 1 && n_ops <= MNF_MAX_OPS, MNF_E_SHAPE, "n_ops=%d outside [1,%d]", n_ops, MNF_MAX_OPS);
+    MNF_REQUIRE(params || n_params == 0, MNF_E_ARG, "params is NULL");
+    MNF_REQUIRE(!staged || dim == 2, MNF_E_ARG, "a staged image exists for dim-2 programs only");
+    mnf_flow_handle *h = new (std::nothrow) mnf_flow_handle();
+    MNF_REQUIRE(h != nullptr, MNF_E_ARG, "out of host memory");
+    h->n_ops = n_ops, h->dim = dim, h->n_params = n_params, h->workspace_rows = workspace_rows;
+    h->params = params, h->staged = staged, h->workspace = workspace;
+    for (int k = 0; k < n_ops; ++k) h->ops[k] = ops_host[k];
+    *out = h;
+    return 0;
+}
+
+void mnf_flow_handle_destroy(mnf_flow_handle *handle) { delete handle; }
+
+int mnf_flow_handle_log_prob(const mnf_flow_handle *h, const float *x, float *log_prob, int64_t n_rows, void *stream) {
+    MNF_REQUIRE(h && x && log_prob, MNF_E_ARG, "NULL pointer");
+    MNF_REQUIRE(n_rows >= 0, MNF_E_ARG, "n_rows=%lld is negative", (long long)n_rows);
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int base = 1 | 2;  // inverse direction, log_det summed into the base log-density
+    int rc;
+    if (h->dim != 2) {
+        rc = launch_made_fast(h->ops, h->n_ops, h->params, x, nullptr, nullptr, log_prob, nullptr, n_rows, h->dim, base,
+                              n_rows <= h->workspace_rows ? h->workspace : nullptr, st, false);
+        if (rc != 1) return rc;
+    } else if (h->staged && n_rows < (1 << 16)) {  // small batches: the pre-staged shared-memory image (variant 2)
+        rc = launch_flow_fast(h->ops, h->n_ops, h->params, h->n_params, x, nullptr, nullptr, log_prob, nullptr, n_rows, 2,
+                              base | 4, -1, const_cast<float *>(h->staged), nullptr, st, false);
+        if (rc != 1) return rc;
+    } else {
+        MNF_REQUIRE(n_rows <= h->workspace_rows && h->workspace, MNF_E_ARG,
+                    "handle was created with a workspace for %lld rows, call has %lld", (long long)h->workspace_rows,
+                    (long long)n_rows);
+        rc = launch_flow_fast(h->ops, h->n_ops, h->params, h->n_params, x, nullptr, nullptr, log_prob, nullptr, n_rows, 2,
+                              base, -1, h->workspace, nullptr, st, false);
+        if (rc != 1) return rc;
+    }
+    return launch_flow_generic(h->ops, h->n_ops, h->params, h->n_params, x, nullptr, nullptr, log_prob, nullptr, n_rows,
+                               h->dim, base, st);
 }
 
 int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params) {

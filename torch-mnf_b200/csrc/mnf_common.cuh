@@ -88,6 +88,20 @@ __device__ __forceinline__ float philox_bernoulli(const Philox &g, uint64_t e, u
     return (float)((w >> (bit & 31u)) & 1u);
 }
 
+struct NoiseSrc {
+    const float *ptr;  // injected tensor or nullptr -> Philox(seed, stream) indexed by global element
+    uint64_t seed;
+    uint32_t stream;
+    uint64_t row_offset;  // global index of local row 0 (sharded runs draw the same numbers)
+};
+
+__device__ __forceinline__ float noise_normal(const NoiseSrc &s, long long local_idx, long long global_idx) {
+    return s.ptr ? s.ptr[local_idx] : philox_normal(Philox(s.seed), (uint64_t)global_idx, s.stream);
+}
+__device__ __forceinline__ float noise_bernoulli(const NoiseSrc &s, long long local_idx, long long global_idx) {
+    return s.ptr ? s.ptr[local_idx] : philox_bernoulli(Philox(s.seed), (uint64_t)global_idx, s.stream);
+}
+
 // ---------------------------------------------------------------------------------------
 // SIMT GEMM skeleton.  NACC accumulator sets share one pass over K (NACC = 2: the MNF
 // mean / variance pair shares the x tile).  Problem functor interface:

@@ -8,6 +8,8 @@
 //       act_row =       r0_c . (z*W_mean) + (r0_c . sqrt(exp(log_var))) * eps_w[row] (conv, on the
 //                 reference's view(-1, n_out) reinterpretation of the [n_out,n_in,k,k] memory)
 //   pass 2 (one CTA): kl_W, kl_b, log_q, mean(act), log_r and the final sum.
+#include <cooperative_groups.h>
+
 #include "mnf_common.cuh"
 
 namespace mnf {
@@ -25,6 +27,21 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     return red[0];
 }
 
+// three block sums with one shared-memory exchange (the weight pass ends every row with them)
+__device__ __forceinline__ void block_sum3(float &a, float &b, float &c, float *red) {
+    a = warp_sum(a), b = warp_sum(b), c = warp_sum(c);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) red[w] = a, red[32 + w] = b, red[64 + w] = c;
+    __syncthreads();
+    if (w == 0) {
+        float x = lane < nw ? red[lane] : 0.f, y = lane < nw ? red[32 + lane] : 0.f, z = lane < nw ? red[64 + lane] : 0.f;
+        x = warp_sum(x), y = warp_sum(y), z = warp_sum(z);
+        if (lane == 0) red[0] = x, red[32] = y, red[64] = z;
+    }
+    __syncthreads();
+    a = red[0], b = red[32], c = red[64];
+}
+
 struct KlRowArgs {
     const float *W_mean, *W_log_var;  // flat [rows * cols]
     const float *z;                   // multiplicative noise after flow_q
@@ -40,19 +57,22 @@ struct KlRowArgs {
 };
 
 __global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
-    __shared__ float red[32];
+    __shared__ float red[96];
     const int row = blockIdx.x;
     const size_t base = (size_t)row * a.cols;
     const Philox rng(a.seed);
     float kl = 0.f, dot_mean = 0.f, dot_noise = 0.f;
     auto element = [&](size_t f, int c, float wmean, float lv, float e) {
-        const float var = expf(lv);
+        // sd = exp(lv / 2) with one EX2, var = sd^2, and -log(var) = -lv: the pass is bound by this arithmetic and the
+        // Philox draws, not by HBM (2^-22 relative error per term against the 2e-5 tolerance of the sum)
+        float sd;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(0.7213475204444817f * lv));
+        const float var = sd * sd;
         const float zz = a.conv ? a.z[f / a.z_block] : a.z[c];
         const float wm = wmean * zz;
-        kl += -logf(var) + var + wm * wm - 1.f;  // mnf_linear.py:73 / mnf_conv.py:99 (-W_var.log())
+        kl += (var - lv) + fmaf(wm, wm, -1.f);  // mnf_linear.py:73 / mnf_conv.py:99 (-W_var.log())
         const float rc = a.r0_c[c];
         dot_mean = fmaf(rc, wm, dot_mean);
-        const float sd = sqrtf(var);
         dot_noise = fmaf(rc, a.conv ? sd : sd * e, dot_noise);  // conv: W_std row . r0_c, scaled by eps_w[row] below
     };
     if ((a.cols & 3) == 0) {
@@ -85,9 +105,7 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
             element(f, c, a.W_mean[f], a.W_log_var[f], e);
         }
     }
-    kl = block_sum(kl, red);
-    dot_mean = block_sum(dot_mean, red);
-    dot_noise = block_sum(dot_noise, red);
+    block_sum3(kl, dot_mean, dot_noise, red);
     if (threadIdx.x == 0) {
         a.kl_rows[row] = kl;
         if (a.conv) {
@@ -160,6 +178,116 @@ __global__ void __launch_bounds__(1024) kl_final_kernel(const KlFinalArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// z0, flow_q and flow_r of one kl_div() call on their single row, in ONE launch (they were 1 + n_q + n_r launches
+// plus a copy): a thread-block cluster of 8 CTAs; per flow the CTAs split the conditioner outputs, meet at a cluster
+// barrier, split the dims for the gate, and meet again before the next flow reads z.
+// ---------------------------------------------------------------------------------------------------------
+struct KlFlowDev {
+    const float *W0, *b0, *Wt, *bt, *Ws, *bs, *mask;
+    uint32_t mask_stream;
+    int Hn;
+};
+struct KlFlowsArgs {
+    int nq, nr, dim;
+    uint32_t z_stream;
+    uint64_t seed;
+    const float *q0_mean, *q0_log_var, *eps_z;
+    float *z, *zT, *ld_q, *ld_r, *ybuf;
+    KlFlowDev f[2 * MNF_KL_MAX_FLOWS];
+};
+constexpr int kKlCluster = 8;
+
+__global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flows_kernel(const __grid_constant__ KlFlowsArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int c = (int)cluster.block_rank(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dim = a.dim;
+    extern __shared__ __align__(16) float sm_kl[];
+    float *mz = sm_kl, *ys = sm_kl + dim, *red = ys + 64;
+    const int per = (dim + kKlCluster - 1) / kKlCluster, d0 = c * per, d1 = min(dim, d0 + per);
+    const Philox rng(a.seed);
+    for (int d = d0 + tid; d < d1; d += 256) {  // z0 = q0_mean + q0_std * eps (mnf_linear.py:58-62), this CTA's dims
+        const float nz = a.eps_z ? a.eps_z[d] : philox_normal(rng, (uint64_t)d, a.z_stream);
+        a.z[d] = a.q0_mean[d] + sqrtf(expf(a.q0_log_var[d])) * nz;
+    }
+    if (c == 0 && tid == 0) *a.ld_q = 0.f, *a.ld_r = 0.f;
+    __threadfence();
+    cluster.sync();
+    float *cur = a.z;
+    for (int f = 0; f < a.nq + a.nr; ++f) {
+        const KlFlowDev &fl = a.f[f];
+        if (f == a.nq) {  // flow_r runs on a copy: z itself feeds the weight pass (mnf_linear.py:83)
+            for (int d = d0 + tid; d < d1; d += 256) a.zT[d] = __ldcg(a.z + d);
+            cur = a.zT;
+            __threadfence();
+            cluster.sync();
+        }
+        const NoiseSrc mask{fl.mask, a.seed, fl.mask_stream, 0};
+        // (every loop of this kernel is latency-bound on a few warps: unrolled so that several loads are in flight)
+#pragma unroll 8
+        for (int d = tid; d < dim; d += 256) mz[d] = noise_bernoulli(mask, d, (long long)d) * __ldcg(cur + d);
+        __syncthreads();
+        // phase 1: conditioner outputs y = W0 (mask z) + b0, one WARP per output (j = c, c + 8, ... over the cluster's
+        // 64 warps), 16-byte loads, no block-level synchronisation inside the phase
+        for (int j = c + kKlCluster * warp; j < fl.Hn; j += kKlCluster * 8) {
+            const float *w0 = fl.W0 + (size_t)j * dim;
+            float acc = 0.f;
+            if ((dim & 3) == 0 && (reinterpret_cast<uintptr_t>(fl.W0) & 15) == 0) {
+#pragma unroll 8
+                for (int d = 4 * lane; d < dim; d += 128) {
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(w0 + d)), m = *reinterpret_cast<const float4 *>(mz + d);
+                    acc = fmaf(w.x, m.x, fmaf(w.y, m.y, fmaf(w.z, m.z, fmaf(w.w, m.w, acc))));
+                }
+            } else {
+                for (int d = lane; d < dim; d += 32) acc = fmaf(w0[d], mz[d], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) a.ybuf[j] = acc + fl.b0[j];
+        }
+        __threadfence();
+        cluster.sync();  // every y[j] is written, every CTA has finished reading z
+        for (int j = tid; j < fl.Hn; j += 256) ys[j] = __ldcg(a.ybuf + j);
+        __syncthreads();
+        float ldsum = 0.f;
+        for (int d = d0 + tid; d < d1; d += 256) {  // phase 2: this CTA's dims, one thread per dim
+            float shift = fl.bt[d], scale = fl.bs[d];
+            const float *wt = fl.Wt + (size_t)d * fl.Hn, *ws = fl.Ws + (size_t)d * fl.Hn;
+            if ((fl.Hn & 1) == 0 && ((reinterpret_cast<uintptr_t>(fl.Wt) | reinterpret_cast<uintptr_t>(fl.Ws)) & 7) == 0) {  // rows of Wt / Ws are 8-byte aligned: paired loads, independent of each other
+                const float2 *wt2 = reinterpret_cast<const float2 *>(wt), *ws2 = reinterpret_cast<const float2 *>(ws);
+                float sh1 = 0.f, sc1 = 0.f;
+#pragma unroll 5
+                for (int j = 0; j < fl.Hn / 2; ++j) {
+                    const float2 t2 = __ldg(wt2 + j), s2 = __ldg(ws2 + j);
+                    shift = fmaf(t2.x, ys[2 * j], shift), sh1 = fmaf(t2.y, ys[2 * j + 1], sh1);
+                    scale = fmaf(s2.x, ys[2 * j], scale), sc1 = fmaf(s2.y, ys[2 * j + 1], sc1);
+                }
+                shift += sh1, scale += sc1;
+            } else {
+                for (int j = 0; j < fl.Hn; ++j) {
+                    shift = fmaf(wt[j], ys[j], shift);
+                    scale = fmaf(ws[j], ys[j], scale);
+                }
+            }
+            const float mk = noise_bernoulli(mask, d, (long long)d);
+            const float gate = 1.f / (1.f + expf(-scale)), zz = __ldcg(cur + d);
+            cur[d] = ((1.f - mk) * zz * gate + (1.f - gate) * shift) + mk * zz;  // rnvp.py:37
+            ldsum += (1.f - mk) * logf(gate);                                     // rnvp.py:36
+        }
+        ldsum = warp_sum(ldsum);
+        if (lane == 0) red[warp] = ldsum;
+        __syncthreads();
+        if (tid == 0) {
+            float v = 0.f;
+            for (int w = 0; w < 8; ++w) v += red[w];
+            atomicAdd(f < a.nq ? a.ld_q : a.ld_r, v);
+        }
+        __threadfence();
+        cluster.sync();  // z of this flow is complete (and y, ys are free) before the next flow starts
+    }
+}
+
+
 }  // namespace mnf
 
 using namespace mnf;
@@ -188,6 +316,38 @@ int mnf_kl_div(const mnf_kl_args *a, void *stream) {
                    a->eps_b, a->seed, a->noise_stream + 1, a->out};
     kl_final_kernel<<<1, 1024, 0, st>>>(fa);
     return launch_status("kl_final_kernel");
+}
+
+int mnf_kl_div_fused(const mnf_kl_fused_args *a, void *stream) {
+    MNF_REQUIRE(a != nullptr, MNF_E_ARG, "args is NULL");
+    const mnf_kl_args &k = a->kl;
+    MNF_REQUIRE(k.z && k.zT && k.ld_q && k.ld_r && k.workspace && k.q0_log_var && a->q0_mean, MNF_E_ARG, "NULL pointer in mnf_kl_fused_args");
+    MNF_REQUIRE(a->n_flows_q >= 0 && a->n_flows_q <= MNF_KL_MAX_FLOWS && a->n_flows_r >= 0 && a->n_flows_r <= MNF_KL_MAX_FLOWS,
+                MNF_E_SHAPE, "at most %d flows per stack", MNF_KL_MAX_FLOWS);
+    MNF_REQUIRE(k.n_out >= 1 && k.n_in >= 1 && k.ksize >= 1, MNF_E_ARG, "bad shape");
+    const int dim = k.conv ? k.n_out : k.n_in;
+    MNF_REQUIRE(dim <= 11000, MNF_E_SHAPE, "dim=%d does not fit the one-row cluster kernel", dim);
+    const int fan = k.n_in * k.ksize * k.ksize, rows = k.conv ? fan : k.n_out;
+    KlFlowsArgs fa{};
+    fa.nq = a->n_flows_q, fa.nr = a->n_flows_r, fa.dim = dim, fa.z_stream = a->z_stream, fa.seed = k.seed;
+    fa.q0_mean = a->q0_mean, fa.q0_log_var = k.q0_log_var, fa.eps_z = a->eps_z;
+    fa.z = const_cast<float *>(k.z), fa.zT = const_cast<float *>(k.zT);
+    fa.ld_q = const_cast<float *>(k.ld_q), fa.ld_r = const_cast<float *>(k.ld_r);
+    fa.ybuf = k.workspace + 2 * (size_t)rows;
+    for (int f = 0; f < fa.nq + fa.nr; ++f) {
+        const int src = f < fa.nq ? f : MNF_KL_MAX_FLOWS + (f - fa.nq);
+        const mnf_rnvp_flow &fl = a->flows[src];
+        MNF_REQUIRE(fl.n_net == 1 && fl.net_sizes[0] >= 1 && fl.net_sizes[0] <= 64, MNF_E_SHAPE,
+                    "fused kl_div needs single-Linear RNVP conditioners of width <= 64");
+        MNF_REQUIRE(fl.net_w[0] && fl.net_b[0] && fl.t_w && fl.t_b && fl.s_w && fl.s_b, MNF_E_ARG, "NULL pointer in flow %d", f);
+        fa.f[f] = KlFlowDev{fl.net_w[0], fl.net_b[0], fl.t_w, fl.t_b, fl.s_w, fl.s_b, a->masks[src], a->mask_streams[src], fl.net_sizes[0]};
+    }
+    // (a one-CTA, all-shared-memory form of this kernel was measured too: 462 us at dim 4096, 46-89 us on MNF-LeNet's
+    // layers against 120 / 41-57 us for the cluster -- the time is cold-miss latency of the dependent weight reads)
+    kl_flows_kernel<<<kKlCluster, 256, sizeof(float) * (dim + 64 + 8), (cudaStream_t)stream>>>(fa);
+    int rc = launch_status("kl_flows_kernel");
+    if (rc) return rc;
+    return mnf_kl_div(&a->kl, stream);
 }
 
 }  // extern "C"

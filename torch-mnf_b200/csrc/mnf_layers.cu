@@ -13,20 +13,6 @@
 
 namespace mnf {
 
-struct NoiseSrc {
-    const float *ptr;  // injected tensor or nullptr -> Philox(seed, stream) indexed by global element
-    uint64_t seed;
-    uint32_t stream;
-    uint64_t row_offset;  // global index of local row 0 (sharded runs draw the same numbers)
-};
-
-__device__ __forceinline__ float noise_normal(const NoiseSrc &s, long long local_idx, long long global_idx) {
-    return s.ptr ? s.ptr[local_idx] : philox_normal(Philox(s.seed), (uint64_t)global_idx, s.stream);
-}
-__device__ __forceinline__ float noise_bernoulli(const NoiseSrc &s, long long local_idx, long long global_idx) {
-    return s.ptr ? s.ptr[local_idx] : philox_bernoulli(Philox(s.seed), (uint64_t)global_idx, s.stream);
-}
-
 // ---------------------------------------------------------------------------------------
 __global__ void sample_z0_kernel(const float *__restrict__ q0_mean, const float *__restrict__ q0_log_var,
                                  NoiseSrc eps, float *__restrict__ z, long long n_rows, int dim) {

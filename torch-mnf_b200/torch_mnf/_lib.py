@@ -74,6 +74,10 @@ _SIGS = {
     "mnf_flow_stack_stage": (C.c_int, [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, C.c_int, _f32p, C.c_void_p]),
     "mnf_flow_stack_workspace": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "mnf_flow_stack_plan": (C.c_int, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
+    "mnf_flow_handle_create": (C.c_int, [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, C.c_int, _f32p, _f32p, C.c_int64,
+                                         C.POINTER(C.c_void_p)]),
+    "mnf_flow_handle_destroy": (None, [C.c_void_p]),
+    "mnf_flow_handle_log_prob": (C.c_int, [C.c_void_p, _f32p, _f32p, C.c_int64, C.c_void_p]),
     "mnf_glow_assemble": (C.c_int, [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p]),
     "mnf_actnorm_init": (
         C.c_int,

@@ -202,6 +202,48 @@ class _FlowStackFn(torch.autograd.Function):
         return None, None, g_x, g_blob
 
 
+class BoundLogProb:
+    """``f(x) -> log p(x)`` through ``mnf_flow_handle_log_prob``: the program, its packed parameters and its staged net
+    image are bound once, a call is one C function of five arguments -- no cache-key check over the parameters, no
+    marshalling of descriptors.  Contract (as for a captured CUDA graph): the parameters must not change while the
+    object is in use; build a new one after an update.  Additive API, not part of the reference."""
+
+    def __init__(self, prog, device, dim, max_rows):
+        lib = _lib.lib()
+        prog._build(device)
+        if not 0 < prog._n_ops <= _lib.MAX_OPS:
+            raise NotImplementedError(f"a bound program holds between 1 and {_lib.MAX_OPS} flows")
+        self.device, self.dim, self.max_rows = prog._blob.device, dim, int(max_rows)
+        self._blob = prog._blob
+        self._staged = prog._staged_image(lib, 1, dim, None)
+        need = lib.mnf_flow_stack_workspace(prog._n_ops, self.max_rows, dim)
+        big = self._staged is None or self.max_rows > FlowProgram.STAGED_MAX_ROWS or dim != 2
+        self._ws = torch.empty(need, device=self.device, dtype=torch.float32) if (need > 0 and big) else None
+        self._handle = C.c_void_p()
+        rc = lib.mnf_flow_handle_create(prog._ops, prog._n_ops, self._blob.data_ptr(), self._blob.numel(), dim,
+                                        _lib.ptr(self._staged), _lib.ptr(self._ws), self.max_rows if self._ws is not None else 0,
+                                        C.byref(self._handle))
+        _lib.check(rc, "mnf_flow_handle_create")
+        self._call = lib.mnf_flow_handle_log_prob
+        self._stream = torch.cuda.current_stream
+
+    def __call__(self, x, out=None):
+        if out is None:
+            out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+        rc = self._call(self._handle, x.data_ptr(), out.data_ptr(), x.shape[0], self._stream(x.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "mnf_flow_handle_log_prob")
+        return out
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                _lib.lib().mnf_flow_handle_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+
 class FlowProgram:
     """Cached (descriptors, blob) for a sequence of flow modules."""
 

@@ -198,6 +198,21 @@ class NormalizingFlowModel(NormalizingFlow):
         zs, ld = self.inverse(x)
         return ld + self.base_log_prob(x)
 
+    def log_prob_fn(self, max_rows: int = 65535):
+        """``f(x [B, dim] CUDA fp32 contiguous, out=None) -> log p(x)`` with the model bound once (standard-normal base,
+        at most ``max_rows`` rows per call): for call sites that evaluate a FIXED model over and over, where the module
+        call's host work -- checking ~150 parameter tensors for changes, marshalling the descriptors -- is most of a
+        small-batch call (BASELINE config 1).  The parameters must not change while ``f`` is in use.  Additive API."""
+        from .._program import BoundLogProb
+
+        p = next(self.parameters())
+        dim = int(self.base.event_shape[0])
+        if not self._base_is_std(dim):
+            raise NotImplementedError("log_prob_fn needs a standard-normal base distribution")
+        if any(getattr(f, "data_dep_init_done", True) is False for f in self.flows):
+            raise RuntimeError("run the data-dependent initialisation (one forward / inverse call) before binding the model")
+        return BoundLogProb(self._program(), p.device, dim, max_rows)
+
     def sample(self, *num_samples: int) -> Tensor:
         """core.py:51-55.  A standard-normal base is drawn directly on the flows' device (no host round trip);
         any other base is sampled by torch.distributions and moved over."""

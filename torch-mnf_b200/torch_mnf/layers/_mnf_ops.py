@@ -38,7 +38,22 @@ class KlArgs(C.Structure):
     ]
 
 
+KL_MAX_FLOWS = 4
+
+
+class KlFusedArgs(C.Structure):
+    """struct mnf_kl_fused_args."""
+
+    _fields_ = [
+        ("kl", KlArgs), ("q0_mean", _vp), ("eps_z", _vp), ("z_stream", C.c_uint32),
+        ("n_flows_q", C.c_int32), ("n_flows_r", C.c_int32), ("reserved", C.c_int32),
+        ("flows", RnvpFlow * (2 * KL_MAX_FLOWS)), ("masks", _vp * (2 * KL_MAX_FLOWS)),
+        ("mask_streams", C.c_uint32 * (2 * KL_MAX_FLOWS)),
+    ]
+
+
 _lib.register({
+    "mnf_kl_div_fused": (_int, [C.POINTER(KlFusedArgs), _vp]),
     "mnf_sample_z0": (_int, [_vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _vp]),
     "mnf_rnvp_forward": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64,
                                 _i64, _int, _vp, _vp, _vp]),
@@ -406,17 +421,120 @@ def conv_forward_tc(layer, x, z, noise: Noise, z_rows=None, rows_per_z=1):
     return out
 
 
+def _kl_fused_plan(layer, conv, dev):
+    """Prefilled mnf_kl_fused_args of a layer (every parameter pointer, shapes, flow descriptors), cached while the
+    parameters keep their storage; None when the layer is outside the fused entry point's shape class."""
+    fq, fr = list(layer.flow_q.flows), list(layer.flow_r.flows)
+    names = ("W_mean", "W_log_var", "b_log_var", "q0_mean", "q0_log_var", "r0_c", "r0_b1", "r0_b2") + (() if conv else ("b_mean",))
+    tensors = [getattr(layer, n) for n in names]
+    for f in fq + fr:
+        tensors += [t for m in f.net.linears() for t in (m.weight, m.bias)] + [f.t.weight, f.t.bias, f.s.weight, f.s.bias]
+    key = (str(dev), conv, tuple(t.data_ptr() for t in tensors))
+    cached = layer.__dict__.get("_kl_plan")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    plan = None
+    n_out, n_in = layer.W_mean.shape[0], layer.W_mean.shape[1]
+    ks = layer.W_mean.shape[2] if conv else 1
+    dim = n_out if conv else n_in
+    ok = (len(fq) <= KL_MAX_FLOWS and len(fr) <= KL_MAX_FLOWS and dim <= 11000
+          and all(len(f.net.linears()) == 1 and f.net.linears()[0].out_features <= 64 for f in fq + fr)
+          and all(t.device == dev and t.dtype == torch.float32 and t.is_contiguous() for t in tensors))
+    if ok:
+        a = KlFusedArgs()
+        k = a.kl
+        k.conv, k.n_out, k.n_in, k.ksize = int(conv), n_out, n_in, ks
+        for n in ("W_mean", "W_log_var", "b_log_var", "q0_log_var", "r0_c", "r0_b1", "r0_b2"):
+            setattr(k, n, getattr(layer, n).data_ptr())
+        k.b_mean = None if conv else layer.b_mean.data_ptr()
+        a.q0_mean = layer.q0_mean.data_ptr()
+        a.n_flows_q, a.n_flows_r = len(fq), len(fr)
+        keep = []
+        for i, f in enumerate(fq):
+            a.flows[i] = _rnvp_struct(f, dev, keep)[0]
+        for i, f in enumerate(fr):
+            a.flows[KL_MAX_FLOWS + i] = _rnvp_struct(f, dev, keep)[0]
+        fan = n_in * ks * ks
+        # Philox stream numbering of a call without a tape (the draw order of kl_div below)
+        a.z_stream = 0
+        for i in range(len(fq)):
+            a.mask_streams[i] = 1 + i
+        a.kl.noise_stream = 1 + len(fq)  # eps_w; eps_b (conv) is noise_stream + 1 inside the library
+        for i in range(len(fr)):
+            a.mask_streams[KL_MAX_FLOWS + i] = 3 + len(fq) + i
+        plan = (a, dim, fan, max(n_out, fan), len(fq), len(fr))
+    layer.__dict__["_kl_plan"] = (key, plan, {})
+    return plan
+
+
 @torch.no_grad()
 def kl_div(layer, conv: bool, tape=None):
     """Shared driver of MNFLinear.kl_div / MNFConv2d.kl_div (draw order: SURVEY.md 8c)."""
     dev = layer.W_mean.device
     if dev.type != "cuda":
         raise RuntimeError("torch_mnf (B200) runs only on CUDA parameters (no CPU fallback)")
+    plan = _kl_fused_plan(layer, conv, dev)
+    if plan is not None and tape is None and not torch.cuda.is_current_stream_capturing():
+        # Philox mode, the common call: nothing but the seed and the result buffer changes between calls -- the noise
+        # stream numbering (z0 = 0, flow_q masks 1.., eps_w, eps_b, flow_r masks) is fixed by the layer's shape and was
+        # written into the cached argument block, the scratch buffers live with it (one set per CUDA stream)
+        a, dim, fan, rows, nq, nr = plan
+        stream = _lib.stream_ptr(dev)
+        scratch = layer.__dict__["_kl_plan"][2]
+        buf = scratch.get(stream)
+        if buf is None:
+            buf = scratch[stream] = torch.empty(2 * dim + 8 + 2 * rows + 64, device=dev, dtype=torch.float32)
+        out = torch.empty(5, device=dev, dtype=torch.float32)
+        base = buf.data_ptr()
+        k = a.kl
+        k.z, k.zT, k.ld_q, k.ld_r = base, base + 4 * dim, base + 8 * dim, base + 8 * dim + 4
+        k.workspace, k.out = base + 4 * (2 * dim + 8), out.data_ptr()
+        k.seed = int(torch.randint(0, 2**62, (1,)).item())  # follows torch.manual_seed
+        with _lib.on_device(dev):
+            rc = _lib.lib().mnf_kl_div_fused(C.byref(a), stream)
+        _lib.check(rc, "mnf_kl_div_fused")
+        _lib.launch_count += 3
+        layer.__dict__["_last_kl_terms"] = out  # kl, kl_W, kl_b, log_q, log_r
+        return out[0]
     noise = Noise(tape, dev)
     n_out = layer.W_mean.shape[0]
     n_in = layer.W_mean.shape[1]
     ks = layer.W_mean.shape[2] if conv else 1
     dim = n_out if conv else n_in
+    if plan is not None:
+        # three launches for the whole call (mnf_kl_div_fused): z0 + flow_q + flow_r in one cluster kernel, the weight
+        # pass, the final reduction.  Draw order as below: z0, flow_q masks, eps_w, eps_b, flow_r masks.
+        a, dim, fan, rows, nq, nr = plan
+        a = KlFusedArgs.from_buffer_copy(a)  # the cached block keeps its Philox defaults
+        eps_z, a.z_stream = noise.normal((dim,) if conv else (1, dim))
+        a.eps_z = _p(eps_z)
+        for i in range(nq):
+            m, a.mask_streams[i] = noise.bernoulli((1, dim))
+            a.masks[i] = _p(m)
+        eps_w, sid = noise.normal((fan,) if conv else (n_out, n_in))
+        eps_b = None
+        if conv:
+            eps_b, _ = noise.normal(())
+        else:
+            noise._next_stream()
+        for i in range(nr):
+            m, a.mask_streams[KL_MAX_FLOWS + i] = noise.bernoulli((1, dim))
+            a.masks[KL_MAX_FLOWS + i] = _p(m)
+        buf = torch.empty(2 * dim + 8 + 2 * rows + 64 + 8, device=dev, dtype=torch.float32)
+        base = buf.data_ptr()
+        k = a.kl
+        k.z, k.zT, k.ld_q, k.ld_r = base, base + 4 * dim, base + 8 * dim, base + 8 * dim + 4
+        k.workspace = base + 4 * (2 * dim + 8)
+        out = buf[2 * dim + 8 + 2 * rows + 64:2 * dim + 8 + 2 * rows + 64 + 5]
+        k.out = out.data_ptr()
+        k.eps_w, k.eps_b = _p(eps_w), _p(eps_b)
+        k.seed, k.noise_stream = noise.seed, sid
+        with _lib.on_device(dev):
+            rc = _lib.lib().mnf_kl_div_fused(C.byref(a), _lib.stream_ptr(dev))
+        _lib.check(rc, "mnf_kl_div_fused")
+        _lib.launch_count += 3
+        layer.__dict__["_last_kl_terms"] = out  # kl, kl_W, kl_b, log_q, log_r
+        return out[0]
     z = sample_z0(layer.q0_mean, layer.q0_log_var, -1 if conv else 1, noise)  # conv draws randn_like[n_out]
     ld_q, _ = rnvp_stack_inplace(list(layer.flow_q.flows), z, noise)
     fan = n_in * ks * ks
