@@ -89,7 +89,7 @@ def test_stack_vs_golden(name, kernel):
 
 
 @pytest.mark.parametrize("name", ["rnvp9_moons", "nsfcl3_stack"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5])
 def test_dim2_kernel_variants(name, variant):
     g = load_golden(name)
     sd, specs = golden_sd(g), golden_spec(g)
@@ -376,3 +376,25 @@ def test_bound_log_prob_equals_module_call(name, n_rows):
             f(torch.cat([x, x]))  # more rows than the bound workspace holds
         else:
             raise RuntimeError("staged small-batch programs need no workspace")
+
+
+@pytest.mark.parametrize("n_rows", [1, 15, 16, 17, 4096, 20001])
+def test_lane_split_kernel_matches_oracle(n_rows):
+    """Variant 5 (eight lanes per point, csrc/flow_lanes.cu) on AffineHalfFlow stacks: both directions, every output,
+    ragged sizes around the 16-point CTA, against the oracle and the interpreter; h = 24 and h = 8."""
+    for h in (24, 8):
+        specs = [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}] + [
+            {"type": "AffineHalfFlow", "dim": 2, "parity": bool(i % 2), "scale": i != 1, "shift": i != 2, "h_sizes": [h, h, h]}
+            for i in range(5)] + [{"type": "Glow", "dim": 2}]
+        sd = random_flow_sd(specs, seed=6, scale=0.3)
+        prog = load_flow_model(specs, sd)._program()
+        x = 1.2 * torch.randn(n_rows, 2, generator=torch.Generator().manual_seed(n_rows + h))
+        for inverse in (True, False):
+            y, ld, inter, lp = prog.run(x.cuda(), inverse, want_inter=True, want_base_lp=True, kernel=5)
+            yg, ldg, interg, lpg = prog.run(x.cuda(), inverse, want_inter=True, want_base_lp=True, kernel="generic")
+            torch.testing.assert_close(y, yg, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(inter, interg, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(ld, ldg, rtol=1e-5, atol=2e-5)
+            torch.testing.assert_close(lp, lpg, rtol=1e-5, atol=2e-5)
+            if n_rows >= 16:
+                close_vs_oracle((y, ld), sd, specs, x, inverse, f"lanes h={h} inverse={inverse}")

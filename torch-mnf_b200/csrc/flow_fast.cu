@@ -16,6 +16,10 @@ int launch_flow_tc(const mnf_flow_op *ops, int n_ops, const float *params, const
                    float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *workspace,
                    const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
 
+int launch_flow_lanes(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                      float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, cudaStream_t stream, bool plan_only,
+                      bool forced);
+
 // ---- host side: plan + launch ---------------------------------------------------------
 
 struct FastPlan {
@@ -194,6 +198,14 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
         if (rc != 1) return rc;
     }
     if (variant == 4) variant = -1;  // not of the tensor-core kernel's shape class: library default
+    // variant 5: eight lanes per point (flow_lanes.cu) -- small batches of AffineHalfFlow stacks, where a call is bound by
+    // the latency of one point's chain.  Default for its class up to 2048 rows (a staged image, bit 2, is simply not needed by it).
+    if (!want_gather && (variant == 5 || (variant < 0 && !plan_only))) {
+        const int rc = launch_flow_lanes(ops, n_ops, params, x, y, log_det, base_lp, inter, n_rows, dim, inverse & 3, stream, plan_only,
+                                         variant == 5);
+        if (rc != 1) return rc;
+    }
+    if (variant == 5) variant = -1;
     int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
     if (want_gather && (mode != 3 || !(inverse & 2) || (n_rows & 1))) return 1;  // caller reports the restriction
     bool has_net = false;
