@@ -398,3 +398,24 @@ def test_lane_split_kernel_matches_oracle(n_rows):
             torch.testing.assert_close(lp, lpg, rtol=1e-5, atol=2e-5)
             if n_rows >= 16:
                 close_vs_oracle((y, ld), sd, specs, x, inverse, f"lanes h={h} inverse={inverse}")
+
+
+@pytest.mark.parametrize("dim,hidden", [(8, 16), (16, 32), (32, 32), (32, 16), (64, 32), (64, 16), (8, 32), (16, 16)])
+def test_made_fast_kernel_shape_grid(dim, hidden):
+    """The exact-fp32 MADE kernels (density and sequential direction) are instantiated for a grid of (dim, hidden)
+    shapes, not only BASELINE config 3's (64, 24): each against the interpreter and the oracle."""
+    specs = [{"type": "MAF", "dim": dim, "parity": bool(i % 2), "h_sizes": [hidden] * 3} for i in range(3)]
+    sd = random_flow_sd(specs, seed=dim + hidden, scale=0.3)
+    prog = load_flow_model(specs, sd)._program()
+    assert prog.plan("cuda", dim) == 2, "shape must take the MADE kernel"
+    x = torch.randn(300 + dim, dim, generator=torch.Generator().manual_seed(dim))
+    y_f, ld_f, inter_f, lp_f = prog.run(x.cuda(), True, want_inter=True, want_base_lp=True)
+    y_g, ld_g, inter_g, lp_g = prog.run(x.cuda(), True, want_inter=True, want_base_lp=True, kernel="generic")
+    for a, b, what in ((y_f, y_g, "z"), (ld_f, ld_g, "ld"), (inter_f, inter_g, "inter"), (lp_f, lp_g, "base_lp")):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=2e-5, msg=lambda m: f"{what}: {m}")
+    close_vs_oracle((y_f, ld_f), sd, specs, x, True, f"made_fast<{dim},{hidden}>")
+    x_f, ldx_f, _, _ = prog.run(y_f, False)  # sequential direction inverts the density direction
+    x_g, ldx_g, _, _ = prog.run(y_f, False, kernel="generic")
+    torch.testing.assert_close(x_f, x_g, rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(ldx_f, ldx_g, rtol=2e-5, atol=5e-5)
+    torch.testing.assert_close(x_f, x.cuda(), rtol=1e-4, atol=1e-4)

@@ -340,13 +340,12 @@ static bool made_shape_is(const mnf_flow_op &op) {
            op.sizes[4] == 2 * D;
 }
 
-// Returns 0 when launched, 1 when the program is not an all-MADE stack of the supported shape (the
-// caller falls through to the next path), other values on error.  dir_flags: bit0 inverse, bit1 sum log-det
-// into base_lp.  scratch: [n_rows * dim] floats, needed only when y == NULL and n_ops > 1.
-int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
-                     float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
-                     cudaStream_t stream, bool plan_only) {
-    constexpr int D = 64, H = 24;
+// One (dim, hidden) instantiation: returns 0 when launched, 1 when the program is not an all-MADE stack of THIS shape,
+// other values on error.
+template <int D, int H>
+static int launch_made_fast_t(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                              float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
+                              cudaStream_t stream, bool plan_only) {
     using L = MadeLayout<D, H>;
     if (dim != D || n_ops < 1) return 1;
     const int inverse = dir_flags & 1;
@@ -362,7 +361,7 @@ int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, con
     const size_t smem = sizeof(float) * (L::kFloats + kMadeWarps * kMadeWarpRows * (D + 1));
     int dev = 0;
     MNF_CUDA(cudaGetDevice(&dev));
-    static bool attr_set[64] = {};
+    static bool attr_set[64] = {};  // per instantiation
     if (!attr_set[dev & 63]) {
         MNF_CUDA(cudaFuncSetAttribute(made_fast_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MNF_CUDA(cudaFuncSetAttribute(made_seq_kernel<D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -398,6 +397,33 @@ int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, con
         src = dst;
     }
     return rc;
+}
+
+// Returns 0 when launched, 1 when the program is not an all-MADE stack of one of the instantiated shapes (three hidden
+// layers of equal width; the caller falls through to the interpreter), other values on error.  dir_flags: bit0 inverse,
+// bit1 sum log-det into base_lp.  scratch: [n_rows * dim] floats, needed only when y == NULL and n_ops > 1.
+// Shapes: BASELINE config 3 (64, 24) plus a grid of common ones -- (dim, hidden) in {8, 16, 32, 64} x {16, 32} and (64, 24);
+// anything else (other depths, hidden > 32, which would not leave two rows' activations in registers) is interpreted.
+int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                     float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
+                     cudaStream_t stream, bool plan_only) {
+    if (n_ops < 1 || ops[0].type != MNF_OP_MADE || ops[0].n_lin != 4) return 1;
+    const int h = ops[0].sizes[1];
+#define MNF_MADE_TRY(DD, HH)                                                                                              \
+    if (dim == DD && h == HH)                                                                                             \
+        return launch_made_fast_t<DD, HH>(ops, n_ops, params, x, y, log_det, base_lp, inter, n_rows, dim, dir_flags, scratch, \
+                                          stream, plan_only);
+    MNF_MADE_TRY(64, 24)
+    MNF_MADE_TRY(64, 32)
+    MNF_MADE_TRY(64, 16)
+    MNF_MADE_TRY(32, 32)
+    MNF_MADE_TRY(32, 16)
+    MNF_MADE_TRY(16, 32)
+    MNF_MADE_TRY(16, 16)
+    MNF_MADE_TRY(8, 32)
+    MNF_MADE_TRY(8, 16)
+#undef MNF_MADE_TRY
+    return 1;
 }
 
 }  // namespace mnf
