@@ -419,3 +419,22 @@ def test_made_fast_kernel_shape_grid(dim, hidden):
     torch.testing.assert_close(x_f, x_g, rtol=2e-5, atol=2e-5)
     torch.testing.assert_close(ldx_f, ldx_g, rtol=2e-5, atol=5e-5)
     torch.testing.assert_close(x_f, x.cuda(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("n_h,K", [(8, 8), (16, 5), (32, 8), (8, 5), (24, 8)])
+@pytest.mark.parametrize("n_rows", [3001, 70001])
+def test_dim2_kernel_shape_grid(n_h, K, n_rows):
+    """The register-resident dim-2 kernels exist for a grid of (hidden width, bins), not only the BASELINE shapes: small
+    batches (shared-memory variant) and large ones (constant-bank variant where the nets fit, else shared memory),
+    against the oracle, with an AffineHalfFlow of the same width in the stack."""
+    specs = [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True},
+             {"type": "NSF_CL", "dim": 2, "K": K, "B": 3, "n_h": n_h},
+             {"type": "AffineHalfFlow", "dim": 2, "parity": True, "scale": True, "shift": True, "h_sizes": [n_h] * 3},
+             {"type": "Glow", "dim": 2}, {"type": "NSF_CL", "dim": 2, "K": K, "B": 3, "n_h": n_h}]
+    sd = random_flow_sd(specs, seed=n_h + K, scale=0.4)
+    prog = load_flow_model(specs, sd)._program()
+    assert prog.plan("cuda", 2) == 1, "shape must take the register-resident kernel"
+    x = 1.4 * torch.randn(n_rows, 2, generator=torch.Generator().manual_seed(n_h * K))
+    for inverse in (True, False):
+        y, ld, _, _ = prog.run(x.cuda(), inverse)
+        close_vs_oracle((y, ld), sd, specs, x, inverse, f"dim2 n_h={n_h} K={K} inverse={inverse}")

@@ -5,12 +5,14 @@
 
 namespace mnf {
 
-int launch_fast_16_8(MNF_FLOW_FAST_ARGS);
-int launch_fast_24_8(MNF_FLOW_FAST_ARGS);
-int launch_fast_8_5(MNF_FLOW_FAST_ARGS);
-int stage_image_16_8(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
-int stage_image_24_8(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
-int stage_image_8_5(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
+// (hidden width, spline bins) instantiations, one translation unit each (flow_fast_h*k*.cu): the BASELINE shapes
+// (16, 8), (24, 8) and the reference's defaults (8, 5), plus neighbours so that common variations stay off the interpreter
+#define MNF_FLOW_FAST_SHAPES(X) X(16, 8) X(24, 8) X(8, 5) X(8, 8) X(16, 5) X(32, 8)
+#define MNF_DECLARE_SHAPE(HH, KK)                \
+    int launch_fast_##HH##_##KK(MNF_FLOW_FAST_ARGS); \
+    int stage_image_##HH##_##KK(const FlowProgram &, const FastLayout &, const float *, float *, cudaStream_t);
+MNF_FLOW_FAST_SHAPES(MNF_DECLARE_SHAPE)
+#undef MNF_DECLARE_SHAPE
 
 int launch_flow_tc(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
                    float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *workspace,
@@ -32,8 +34,10 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
     FastPlan p;
     if (dim != 2 || n_ops < 1) return p;
     int H = 0, K = 0, slots = 0;
+    bool has_spline_op = false;
     for (int k = 0; k < n_ops; ++k) {
         const mnf_flow_op &op = ops[k];
+        has_spline_op |= op.type == MNF_OP_NSF_CL;
         p.lay.net_slot[k][0] = p.lay.net_slot[k][1] = 0;
         if (op.type == MNF_OP_AFFINE_CONST || op.type == MNF_OP_GLOW) continue;
         if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) return p;
@@ -57,7 +61,15 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
     }
     if (H == 0) H = 8, K = 5;  // conditioner-free stack (ActNorm / Glow only): pure streaming, any instantiation does
     if (K == 0) K = 8;
-    const bool have = (H == 16 && K == 8) || (H == 24 && K == 8) || (H == 8 && K == 5);
+    bool have = false;
+#define MNF_HAVE_SHAPE(HH, KK) have |= (H == HH && K == KK);
+    MNF_FLOW_FAST_SHAPES(MNF_HAVE_SHAPE)
+#undef MNF_HAVE_SHAPE
+    if (!have && !has_spline_op) {  // AffineHalfFlow-only stacks do not care about K: any instantiation of their width does
+#define MNF_HAVE_WIDTH(HH, KK) if (!have && H == HH) have = true, K = KK;
+        MNF_FLOW_FAST_SHAPES(MNF_HAVE_WIDTH)
+#undef MNF_HAVE_WIDTH
+    }
     if (!have) return p;
     p.H = H;
     p.K = K;
@@ -174,9 +186,11 @@ int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int
     FlowProgram prog;
     prog.n_ops = n_ops;
     for (int k = 0; k < n_ops; ++k) prog.ops[k] = ops[k];
-    if (p.H == 16 && p.K == 8) return stage_image_16_8(prog, p.lay, params, image, stream);
-    if (p.H == 24 && p.K == 8) return stage_image_24_8(prog, p.lay, params, image, stream);
-    return stage_image_8_5(prog, p.lay, params, image, stream);
+#define MNF_STAGE_SHAPE(HH, KK) \
+    if (p.H == HH && p.K == KK) return stage_image_##HH##_##KK(prog, p.lay, params, image, stream);
+    MNF_FLOW_FAST_SHAPES(MNF_STAGE_SHAPE)
+#undef MNF_STAGE_SHAPE
+    return fail(MNF_E_SHAPE, "no instantiation for hidden width %d, %d bins", p.H, p.K);
 }
 
 // returns 1 if the program is not eligible (caller falls back to the generic kernel)
@@ -232,15 +246,12 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     (void)n_params;
     if (!has_net && variant < 0 && !inter && workspace && !(inverse & 4) && n_rows % 2 == 0 && n_rows >= 2)
         return launch_affine_stream(prog, params, x, y, log_det, base_lp, n_rows, inverse, workspace, dp, stream);
-    if (p.H == 16 && p.K == 8)
-        return launch_fast_16_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                workspace, gather, dp, stream);
-    if (p.H == 24 && p.K == 8)
-        return launch_fast_24_8(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                                workspace, gather, dp, stream);
-    if (p.H == 8 && p.K == 5)
-        return launch_fast_8_5(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse,
-                               workspace, gather, dp, stream);
+#define MNF_LAUNCH_SHAPE(HH, KK)                                                                                           \
+    if (p.H == HH && p.K == KK)                                                                                            \
+        return launch_fast_##HH##_##KK(mode, prog, p.lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, inverse, \
+                                       workspace, gather, dp, stream);
+    MNF_FLOW_FAST_SHAPES(MNF_LAUNCH_SHAPE)
+#undef MNF_LAUNCH_SHAPE
     return 1;
 }
 

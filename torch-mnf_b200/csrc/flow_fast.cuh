@@ -876,9 +876,13 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
         if (variant == 1)                                                                                       \
             return launch_inst<HH, KK, 1>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, \
                                           inverse, dp, stream);                                                 \
-        if (variant == 3)                                                                                       \
+        /* constant-bank variant: only the shapes it is validated on at >= 65536 rows (the BASELINE ones); the   \
+           (8, 5) instantiation gave wrong results there in r02 testing and other widths are untested -- they take \
+           the shared-memory variant at every batch size */                                                      \
+        if (variant == 3 && KK == 8 && (HH == 16 || HH == 24))                                                  \
             return launch_cbank<HH, KK>(prog, params, x, y, log_det, base_lp, inter, n_rows, inverse, workspace, \
                                         gather, stream);                                                        \
+        if (variant == 3 && gather && (gather->n_peers > 0 || gather->multicast_ptr)) return 1;                 \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \
                                       inverse, dp, stream, (inverse & 4) ? workspace : nullptr);                \
     }                                                                                                           \
