@@ -413,7 +413,10 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 // descriptor expects, then fence.proxy.async + mbarrier arrive), warps 12-15 = epilogue (tcgen05.ld -> mean, sd rows).  The materialised im2col this replaces wrote and re-read
 // 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
 // =====================================================================================================================
-constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_THREADS = 512, CONV_MAX_KP = 512, CONV_BK = 64;
+constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_MAX_KP = 512, CONV_BK = 64;
+// generator threads per tile row (each takes 8 / CONV_PARTS of the k-block's eight 16-byte chunks): r02 ncu showed the kernel
+// waiting on its 8 generator warps (issue 34 %, scoreboard / barrier stalls), so a row is now split over four threads
+constexpr int CONV_PARTS = 4, CONV_GEN = 128 * CONV_PARTS, CONV_CPT = 8 / CONV_PARTS, CONV_THREADS = 128 + CONV_GEN + 128;
 constexpr float CONV_VAR_SCALE = 256.f;  // must match conv_pack_weights_f16_kernel (mnf_layers.cu)
 struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image (0 for the zero padding of K); travels as a
     int off[CONV_MAX_KP];  // kernel parameter so that the generators read it through the uniform datapath
@@ -469,7 +472,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < CONV_STAGES; ++s) {
-            mbar_init(full_a(s), 256);
+            mbar_init(full_a(s), CONV_GEN);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
@@ -532,9 +535,9 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             umma_commit(acc_full(acc));
             if (++acc == CONV_ACC) acc = 0, acc_phase ^= 1u;
         }
-    } else if (warp >= 4 && warp < 12) {
-        // ---------------- A generators: 256 threads, two per tile row (four 16-byte chunks = 32 taps of the k-block each) ----------------
-        const int gt = threadIdx.x - 128, ml = gt & 127, half = gt >> 7;
+    } else if (warp >= 4 && warp < 4 + CONV_GEN / 32) {
+        // ---------------- A generators: CONV_PARTS threads per tile row (CONV_CPT 16-byte chunks = 8 CONV_CPT taps of the k-block each) ----------------
+        const int gt = threadIdx.x - 128, ml = gt & 127, half = gt >> 7;  // half: which part of the row's chunks
         const int img_l = ml / RPI, p = ml % RPI, q = p & 3, w = p >> 2;
         const int row_base = img_l * CHW + (2 * (w / PW) + (q >> 1)) * W + 2 * (w % PW) + (q & 1);
         const uint32_t row_smem = (uint32_t)((ml >> 3) * 1024 + (ml & 7) * 128);
@@ -546,7 +549,7 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             const int n16 = (int)(left < n16_full ? left : n16_full);
             const float *src = x + (size_t)img0 * CHW;
             const uint32_t dst = xs_u32 + (uint32_t)buf * (uint32_t)(IMGS * CHW * 4);
-            for (int i = gt; i < n16; i += 256) cp_async16(dst + 16u * i, src + 4 * i);
+            for (int i = gt; i < n16; i += CONV_GEN) cp_async16(dst + 16u * i, src + 4 * i);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         int stage = 0, buf = 0;
@@ -557,19 +560,19 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
             if (next < n_tiles) prefetch(next, buf ^ 1);  // the other buffer was released by the barrier below
             else asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // every generator's copies of this tile have landed
+            asm volatile("bar.sync 1, %0;" ::"n"(CONV_GEN) : "memory");  // every generator's copies of this tile have landed
             const float *xt = xs + (size_t)buf * IMGS * CHW;
             // software pipeline: the 32 taps of the NEXT k-block are gathered into registers right after this one is
             // published, so their shared-memory latency overlaps the wait for the stage to come back from the MMAs
-            float v[32];
+            float v[8 * CONV_CPT];
             // no validity checks: the zero padding of K is done by the WEIGHT tiles (their columns >= K are zero and the
             // padded taps point at offset 0, a finite value), and rows past the last image of a half-filled tile read
             // whatever the buffer holds -- their outputs are never stored and rows do not mix in an MMA
             const float *xrow = xt + row_base;
             auto gather = [&](int kb) {
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int kk = kb * CONV_BK + 8 * (half * 4 + cc);
+                for (int cc = 0; cc < CONV_CPT; ++cc) {
+                    const int kk = kb * CONV_BK + 8 * (half * CONV_CPT + cc);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) v[8 * cc + u] = xrow[taps.off[kk + u]];
                 }
@@ -579,8 +582,8 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                 mbar_wait(empty(stage), phase ^ 1u);
                 uint8_t *sa = smem_raw + (base + stage * CONV_STAGE_BYTES - smem_u32(smem_raw)) + row_smem;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int pos = ((half * 4 + cc) ^ swz) * 16;
+                for (int cc = 0; cc < CONV_CPT; ++cc) {
+                    const int pos = ((half * CONV_CPT + cc) ^ swz) * 16;
                     const float *q = v + 8 * cc;
                     *reinterpret_cast<uint4 *>(sa + pos) =
                         make_uint4(conv_pack_h2(q[0], q[1]), conv_pack_h2(q[2], q[3]), conv_pack_h2(q[4], q[5]), conv_pack_h2(q[6], q[7]));
@@ -593,11 +596,11 @@ conv_implicit_kernel(const __grid_constant__ CUtensorMap map_bm, const __grid_co
                 if (kb + 1 < n_kblk) gather(kb + 1);
                 if (++stage == CONV_STAGES) stage = 0, phase ^= 1u;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // all rows of this tile generated: its image buffer is free
+            asm volatile("bar.sync 1, %0;" ::"n"(CONV_GEN) : "memory");  // all rows of this tile generated: its image buffer is free
             buf ^= 1;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp >= 12) {
+    } else if (warp >= 4 + CONV_GEN / 32) {
         // ---------------- epilogue: TMEM -> mean, sd rows ----------------
         const int quarter = warp & 3;
         int acc = 0;
