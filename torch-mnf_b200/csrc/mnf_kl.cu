@@ -207,6 +207,22 @@ __global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flo
     float *mz = sm_kl, *ys = sm_kl + dim, *red = ys + 64;
     const int per = (dim + kKlCluster - 1) / kKlCluster, d0 = c * per, d1 = min(dim, d0 + per);
     const Philox rng(a.seed);
+    // The flows' weights (2.4 MB per flow at dim 4096) are read in a chain of dependent phases by 8 SMs: cold, every
+    // phase pays DRAM latency with little parallelism (r02 ncu: 120 us, issue 7 %, long-scoreboard stalls).  Ask for all
+    // of them now -- one L2 prefetch per 128-byte line, spread over the cluster's 2048 threads -- so that the phases
+    // below find them in L2.
+    {
+        const int gtid = c * 256 + tid, gthreads = kKlCluster * 256;
+        for (int f = 0; f < a.nq + a.nr; ++f) {
+            const KlFlowDev &fl = a.f[f];
+            const size_t lines = ((size_t)fl.Hn * dim * sizeof(float) + 127) / 128;
+            for (size_t l = gtid; l < lines; l += gthreads) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(fl.W0) + 128 * l));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(fl.Wt) + 128 * l));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(fl.Ws) + 128 * l));
+            }
+        }
+    }
     for (int d = d0 + tid; d < d1; d += 256) {  // z0 = q0_mean + q0_std * eps (mnf_linear.py:58-62), this CTA's dims
         const float nz = a.eps_z ? a.eps_z[d] : philox_normal(rng, (uint64_t)d, a.z_stream);
         a.z[d] = a.q0_mean[d] + sqrtf(expf(a.q0_log_var[d])) * nz;

@@ -414,9 +414,9 @@ int launch(const float *A, const float *B, int M, int N, int K, const Epilogue &
 // 2 x 4 x Kp bytes per output pixel (6.6 GB + 7 GB per 25 600 LeNet samples); this kernel reads x once.
 // =====================================================================================================================
 constexpr int CONV_STAGES = 3, CONV_ACC = 4, CONV_BN = 64, CONV_MAX_KP = 512, CONV_BK = 64;
-// generator threads per tile row (each takes 8 / CONV_PARTS of the k-block's eight 16-byte chunks): r02 ncu showed the kernel
-// waiting on its 8 generator warps (issue 34 %, scoreboard / barrier stalls), so a row is now split over four threads
-constexpr int CONV_PARTS = 4, CONV_GEN = 128 * CONV_PARTS, CONV_CPT = 8 / CONV_PARTS, CONV_THREADS = 128 + CONV_GEN + 128;
+// generator threads per tile row (each takes 8 / CONV_PARTS of the k-block's eight 16-byte chunks).  Measured (cfg4, 64 MC
+// samples per step): 2 threads per row 11.87 M samples/s, 4 threads per row (16 generator warps) 11.57 M
+constexpr int CONV_PARTS = 2, CONV_GEN = 128 * CONV_PARTS, CONV_CPT = 8 / CONV_PARTS, CONV_THREADS = 128 + CONV_GEN + 128;
 constexpr float CONV_VAR_SCALE = 256.f;  // must match conv_pack_weights_f16_kernel (mnf_layers.cu)
 struct ConvTaps {  // k -> offset of tap (ci, ky, kx) inside an image (0 for the zero padding of K); travels as a
     int off[CONV_MAX_KP];  // kernel parameter so that the generators read it through the uniform datapath
