@@ -371,11 +371,31 @@ def test_bound_log_prob_equals_module_call(name, n_rows):
     out = torch.empty(n_rows, device="cuda")
     assert f(x, out) is out and torch.equal(out, want)
     assert torch.equal(f(x[: n_rows // 2].contiguous()), model.log_prob(x[: n_rows // 2].contiguous()))
-    with pytest.raises(RuntimeError):
-        if n_rows > 65535:
-            f(torch.cat([x, x]))  # more rows than the bound workspace holds
-        else:
-            raise RuntimeError("staged small-batch programs need no workspace")
+    if dim == 2:  # no row limit for dim-2 programs: twice the rows the object was made for
+        xx = torch.cat([x, x])
+        assert torch.equal(f(xx), model.log_prob(xx))
+
+
+def test_two_programs_on_two_streams_do_not_share_state():
+    """entry points are re-entrant, the library keeps no device state.  Two different models of the benchmark
+    shape, launched interleaved on two streams (tensor-core kernel: >= 65536 rows, and the small-batch kernels), must give
+    bit-identical results to running them one after the other."""
+    specs = ORACLE_CASES["cfg2_shape"]
+    models = [load_flow_model(specs, random_flow_sd(specs, seed=s, scale=0.5), return_intermediates=False) for s in (1, 2)]
+    for n_rows in (70001, 3000):
+        xs = [1.3 * torch.randn(n_rows, 2, generator=torch.Generator().manual_seed(10 + i)).cuda() for i in range(2)]
+        serial = [m.log_prob(x).clone() for m, x in zip(models, xs)]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        outs = [[], []]
+        for rep in range(6):  # interleaved: model 0 on stream 0, model 1 on stream 1, alternating
+            for i in (0, 1):
+                with torch.cuda.stream(streams[i]):
+                    outs[i].append(models[i].log_prob(xs[i]))
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            for o in outs[i]:
+                assert torch.equal(o, serial[i]), f"model {i}, {n_rows} rows: concurrent result differs from the serial one"
 
 
 @pytest.mark.parametrize("n_rows", [1, 15, 16, 17, 4096, 20001])

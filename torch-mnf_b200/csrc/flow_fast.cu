@@ -78,8 +78,7 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
     return p;
 }
 
-// default: constant-bank weights for large batches (3 segment launches + copies amortise), the
-// single-launch shared-memory variant for small ones
+// rows from which the large-batch kernels (tensor-core conditioners; constant-bank variant on request) are considered
 constexpr long long kCbankMinRows = 1 << 16;
 constexpr int kNumVariants = 4;
 constexpr bool kTcDefault = true;  // measured (profiles/r02_flow_tc.md): 3.85 vs 4.12 ms per 2^24 points at unchanged parity, one launch, 12 B/pt of DRAM traffic
@@ -220,7 +219,11 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
         if (rc != 1) return rc;
     }
     if (variant == 5) variant = -1;
-    int mode = (variant >= 0 && variant < kNumVariants) ? variant : (n_rows >= kCbankMinRows && has_spline ? 3 : 2);
+    // Default: the shared-memory variant.  The constant-bank variant (3) keeps the conditioner nets in a __constant__ array
+    // and a __device__ stage of the library -- global device state behind a mutex, which the ABI's rules exclude -- so since
+    // r02 it runs only on explicit request (tests, comparisons); spline stacks of the benchmark shape take the tensor-core
+    // kernel above, which owns nothing.
+    int mode = (variant >= 0 && variant < kNumVariants) ? variant : 2;
     if (want_gather && (mode != 3 || !(inverse & 2) || (n_rows & 1))) return 1;  // caller reports the restriction
     bool has_net = false;
     for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;

@@ -216,12 +216,14 @@ class BoundLogProb:
         self.device, self.dim, self.max_rows = prog._blob.device, dim, int(max_rows)
         self._blob = prog._blob
         self._staged = prog._staged_image(lib, 1, dim, None)
-        need = lib.mnf_flow_stack_workspace(prog._n_ops, self.max_rows, dim)
-        big = self._staged is None or self.max_rows > FlowProgram.STAGED_MAX_ROWS or dim != 2
-        self._ws = torch.empty(need, device=self.device, dtype=torch.float32) if (need > 0 and big) else None
+        # dim 2: the kernels a bound call can reach need at most the weight image of the tensor-core kernel, whatever the
+        # batch; other dims (MADE density in log-prob mode) park max_rows points in the workspace
+        need = lib.mnf_flow_stack_workspace(prog._n_ops, 0 if dim == 2 else self.max_rows, dim)
+        self._ws = torch.empty(need, device=self.device, dtype=torch.float32) if need > 0 else None
+        ws_rows = (1 << 62) if dim == 2 else self.max_rows
         self._handle = C.c_void_p()
         rc = lib.mnf_flow_handle_create(prog._ops, prog._n_ops, self._blob.data_ptr(), self._blob.numel(), dim,
-                                        _lib.ptr(self._staged), _lib.ptr(self._ws), self.max_rows if self._ws is not None else 0,
+                                        _lib.ptr(self._staged), _lib.ptr(self._ws), ws_rows if self._ws is not None else 0,
                                         C.byref(self._handle))
         _lib.check(rc, "mnf_flow_handle_create")
         self._call = lib.mnf_flow_handle_log_prob
@@ -296,9 +298,12 @@ class FlowProgram:
         return img if img is not False else None
 
     @staticmethod
-    def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False):
+    def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False, kernel=None):
         if have_y and dim != 2:
             return None  # only log-prob-only runs (no y buffer) of the MADE kernel park points in the workspace
+        if dim == 2 and kernel != 3:
+            n_rows = 0  # only the constant-bank variant (explicit request) parks points between its segments; every
+            #             other dim-2 kernel needs at most the weight image of the tensor-core kernel
         need = lib.mnf_flow_stack_workspace(n_ops, n_rows, dim)
         return torch.empty(need, device=dev, dtype=torch.float32) if need > 0 else None
 
@@ -364,7 +369,7 @@ class FlowProgram:
             if ws is not None:
                 flags |= _lib.RUN_STAGED
             else:
-                ws = self._workspace(lib, n, B, D, dev)
+                ws = self._workspace(lib, n, B, D, dev, kernel=kernel)
             with _lib.on_device(dev):
                 rc = lib.mnf_flow_stack_run(self._ops, n, self._blob.data_ptr(), self._blob.numel(), x.data_ptr(),
                                             None, None, lp.data_ptr(), None, B, D, flags, _lib.ptr(ws),
@@ -380,7 +385,7 @@ class FlowProgram:
             y.copy_(x)
             ld.zero_()
         stream = _lib.stream_ptr(dev)
-        ws = self._workspace(lib, min(n, _lib.MAX_OPS), B, D, dev, have_y=True)
+        ws = self._workspace(lib, min(n, _lib.MAX_OPS), B, D, dev, have_y=True, kernel=kernel)
         flags = _lib.RUN_INVERSE if inverse else 0
         if kernel == "generic":
             flags |= _lib.RUN_GENERIC
