@@ -288,3 +288,35 @@ def test_non_default_leaky_slope_is_rejected_not_ignored():
     with pytest.raises(NotImplementedError, match="leaky_a"):
         f._emit(ParamPacker(torch.device("cpu")))
     nf.NSF_CL(2, K=4, B=3, n_h=4)._emit(ParamPacker(torch.device("cpu")))
+
+
+def test_kl_fused_plan_numbering_matches_the_draw_order_and_follows_parameter_storage():
+    """The cached argument block of mnf_kl_div_fused carries the Philox stream ids of a tape-less call; they must be the
+    ids a Noise object hands out in kl_div's draw order (z0, flow_q masks, eps_w, eps_b, flow_r masks), and the block must
+    be rebuilt when any parameter gets new storage."""
+    from torch_mnf.layers import MNFConv2d, MNFLinear
+    from torch_mnf.layers import _mnf_ops as ops
+
+    dev = torch.device("cpu")
+    for layer, conv in ((MNFLinear(12, 7, n_flows_q=2, n_flows_r=3), False), (MNFConv2d(3, 5, 3), True)):
+        plan = ops._kl_fused_plan(layer, conv, dev)
+        assert plan is not None
+        a, dim, fan, rows, nq, nr = plan
+        assert (dim, fan) == ((5, 27) if conv else (12, 12)) and rows == max(layer.W_mean.shape[0], fan)
+        noise = ops.Noise(None, dev, seed=1)
+        _, z_sid = noise.normal((dim,))
+        q_sids = [noise.bernoulli((1, dim))[1] for _ in range(nq)]
+        _, w_sid = noise.normal((fan,))
+        noise._next_stream()  # eps_b (conv) or the skipped id (linear)
+        r_sids = [noise.bernoulli((1, dim))[1] for _ in range(nr)]
+        assert a.z_stream == z_sid and a.kl.noise_stream == w_sid
+        assert [a.mask_streams[i] for i in range(nq)] == q_sids
+        assert [a.mask_streams[ops.KL_MAX_FLOWS + i] for i in range(nr)] == r_sids
+        assert a.n_flows_q == nq and a.n_flows_r == nr and a.kl.conv == int(conv)
+        assert ops._kl_fused_plan(layer, conv, dev) is plan  # cached
+        layer.flow_r.flows[0].t.weight.data = layer.flow_r.flows[0].t.weight.data.clone()
+        again = ops._kl_fused_plan(layer, conv, dev)
+        assert again is not plan and again[0].flows[ops.KL_MAX_FLOWS].t_w == layer.flow_r.flows[0].t.weight.data_ptr()
+    # outside the fused entry point's shape class: two-layer conditioners -> the multi-launch path
+    wide = MNFLinear(12, 7, h_sizes=(8, 8))
+    assert ops._kl_fused_plan(wide, False, dev) is None

@@ -204,3 +204,26 @@ def test_mnf_lenet_mc_sharding_invariance(precision):
     both = torch.cat([lo, hi])
     torch.testing.assert_close(both, full, rtol=1e-5, atol=1e-5)
     assert not torch.equal(net(x, n_samples=S, seed=78), full)
+
+
+def test_conv_with_many_filter_taps():
+    """MNFConv2d(32, 64, 5) has 800 filter taps (the tap table of the fp32 kernel held 640 in round 1, so the reference's
+    shape was rejected): forward with injected noise vs the oracle; and a 3 x 3 x 200 layer beyond the table (1 800 taps)."""
+    from oracle import mnf_cpu
+    from oracle.noise import NoiseTape
+    from torch_mnf.layers import MNFConv2d
+
+    for c_in, c_out, ks, hw in ((32, 64, 5, 12), (200, 8, 3, 6)):
+        torch.manual_seed(c_in)
+        conv = MNFConv2d(c_in, c_out, kernel_size=ks)
+        with torch.no_grad():
+            conv.W_log_var.add_(5.0)
+        sd = {k: v.detach().clone() for k, v in conv.state_dict().items()}
+        gen = torch.Generator().manual_seed(3)
+        x = torch.rand(3, c_in, hw, hw, generator=gen)
+        o = hw - ks + 1
+        draws = [("normal", torch.randn(c_out, generator=gen)), ("bernoulli", torch.bernoulli(torch.full((1, c_out), 0.5), generator=gen)),
+                 ("bernoulli", torch.bernoulli(torch.full((1, c_out), 0.5), generator=gen)), ("normal", torch.randn(3, c_out, o, o, generator=gen))]
+        ref = mnf_cpu.conv_forward(sd, x, NoiseTape(draws))
+        got = conv.cuda()(x.cuda(), noise=NoiseTape(draws)).cpu()
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().mean()) + 1e-5)

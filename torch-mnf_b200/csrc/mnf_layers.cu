@@ -197,9 +197,15 @@ struct MnfConvProb {
             r = m / (OW * OH);
         }
     }
-    // offset of filter tap k inside an image, (ci*H + ky)*W + kx, tabulated on the host (K <= kMaxTaps)
-    static constexpr int kMaxTaps = 640;
+    // offset of filter tap k inside an image, (ci*H + ky)*W + kx, tabulated on the host for the first kMaxTaps taps
+    // (the table travels as a kernel parameter); wider filters compute the remaining offsets arithmetically
+    static constexpr int kMaxTaps = 1600;
     int koff[kMaxTaps];
+    __device__ __forceinline__ int tap_offset(int k) const {
+        if (k < kMaxTaps) return koff[k];
+        const int kx = k % ks, ky = (k / ks) % ks, ci = k / (ks * ks);
+        return (ci * H + ky) * W + kx;
+    }
     using RowCtx = size_t;  // offset of the output pixel's receptive-field origin in x
     __device__ RowCtx row_ctx(int m) const {
         int r, oy, ox;
@@ -207,7 +213,7 @@ struct MnfConvProb {
         return ((size_t)(r % x_imgs) * C * H + oy) * W + ox;
     }
     __device__ void load_a(const RowCtx &r, int, int k, float (&a)[2]) const {
-        const float xv = x[r + koff[k]];
+        const float xv = x[r + tap_offset(k)];
         a[0] = xv;
         a[1] = xv * xv;
     }
@@ -549,7 +555,6 @@ int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, cons
     MNF_REQUIRE(n_imgs >= 0 && OH >= 1 && OW >= 1, MNF_E_SHAPE, "bad shape");
     const long long M = (long long)n_imgs * OH * OW;
     MNF_REQUIRE(M <= 0x7fffffff - 64, MNF_E_SHAPE, "too many output pixels for one call (%lld)", M);
-    MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "too many filter taps");
     if (n_imgs == 0) return 0;
     if (c_in * ksize * ksize <= 64 && c_out <= 32 && c_in * height * width <= 4096) {  // few taps, few channels: direct form
         if (c_out <= 20)
@@ -560,7 +565,7 @@ int mnf_conv2d_moments(const float *x, const float *z, const float *W_mean, cons
     }
     MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)(n_imgs > 0 ? n_imgs : 1), c_in, height, width, ksize,
                   OH, OW, W_mean, W_log_var, b_log_var, z, mean_out, NoiseSrc{nullptr, 0, 0, 0}, 0, sd_out, {}};
-    for (int k = 0; k < p.K; ++k) {
+    for (int k = 0; k < p.K && k < MnfConvProb::kMaxTaps; ++k) {
         const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
         p.koff[k] = (ci * height + ky) * width + kx;
     }
@@ -713,12 +718,10 @@ int mnf_conv2d_forward(const float *x, int64_t x_imgs, const float *z, const flo
                 "fused 2x2 max-pool needs even output size, got %dx%d", OH, OW);
     const long long M = (long long)n_imgs * OH * OW;
     MNF_REQUIRE(M <= 0x7fffffff - 64, MNF_E_SHAPE, "too many output pixels for one call (%lld): chunk the batch", M);
-    MNF_REQUIRE(c_in * ksize * ksize <= MnfConvProb::kMaxTaps, MNF_E_SHAPE, "c_in*k*k = %d exceeds %d filter taps",
-                c_in * ksize * ksize, MnfConvProb::kMaxTaps);
     MnfConvProb p{(int)M, c_out, c_in * ksize * ksize, x, (int)x_imgs, c_in, height, width, ksize, OH, OW,
                   W_mean, W_log_var, b_log_var, z, out, NoiseSrc{eps, seed, noise_stream, row_offset}, relu_pool,
                   nullptr, {}};
-    for (int k = 0; k < p.K; ++k) {
+    for (int k = 0; k < p.K && k < MnfConvProb::kMaxTaps; ++k) {
         const int kx = k % ksize, ky = (k / ksize) % ksize, ci = k / (ksize * ksize);
         p.koff[k] = (ci * height + ky) * width + kx;
     }
