@@ -723,11 +723,8 @@ def cfg4(args, dev, world, rank, total_samples=500, per_gpu_samples=None):
     def step(from_host=False):
         counter[0] += 1
         x = imgs_host.to(dev, non_blocking=True) if from_host else imgs
-        sums = torch.zeros(n_img, 10, device=dev)
-        for c in range(s_lo, s_hi, chunk):
-            s_here = min(chunk, s_hi - c)
-            lp = net(x, n_samples=s_here, seed=1000 + counter[0] * 131, row_offset=c * n_img)
-            sums += lp.exp().view(s_here, n_img, 10).sum(0)
+        # the public MC-prediction call (MNFLeNet.predict): this rank's samples, partial probability sums
+        sums = net.predict(x, n_samples=total_s, chunk=chunk, seed=1000 + counter[0] * 131, sample_range=(s_lo, s_hi))
         if world > 1:
             dist.all_reduce(sums)
         probs = sums / total_s

@@ -227,3 +227,27 @@ def test_conv_with_many_filter_taps():
         ref = mnf_cpu.conv_forward(sd, x, NoiseTape(draws))
         got = conv.cuda()(x.cuda(), noise=NoiseTape(draws)).cpu()
         torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4 * float(ref.abs().mean()) + 1e-5)
+
+
+def test_lenet_predict_equals_chunked_forward_and_is_shard_invariant():
+    """MNFLeNet.predict (conv z and conv1 moments once per prediction) gives, bit for bit, the sum over chunks of
+    forward(x, n_samples=chunk, seed, row_offset) -- the way the prediction was evaluated before -- for any chunk size,
+    and sharded over sample ranges."""
+    from torch_mnf.models import MNFLeNet
+
+    g = load_golden("mnf_lenet")
+    net = MNFLeNet()
+    net.load_state_dict(golden_sd(g))
+    net.cuda()
+    x = torch.rand(64, 1, 28, 28, generator=torch.Generator().manual_seed(4)).cuda()
+    S, seed = 24, 77
+    want = torch.zeros(64, 10, device="cuda")
+    for c in range(0, S, 8):
+        want += net(x, n_samples=8, seed=seed, row_offset=c * 64).exp().view(8, 64, 10).sum(0)
+    got = net.predict(x, n_samples=S, chunk=8, seed=seed)
+    assert torch.equal(got, want / S)
+    torch.testing.assert_close(net.predict(x, n_samples=S, chunk=12, seed=seed), want / S, rtol=1e-6, atol=1e-7)
+    parts = (net.predict(x, n_samples=S, chunk=8, seed=seed, sample_range=(0, 16))
+             + net.predict(x, n_samples=S, chunk=8, seed=seed, sample_range=(16, 24)))
+    assert torch.equal(parts, want)
+    assert torch.allclose(got.sum(1), torch.ones(64, device="cuda"), atol=1e-5)

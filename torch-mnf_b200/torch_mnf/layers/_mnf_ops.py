@@ -372,10 +372,9 @@ def conv_sample_z_rows(layer, n_z, noise: Noise, z_offset=0):
 
 
 @torch.no_grad()
-def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows, z_rows=None, rows_per_z=1):
-    """maxpool2(relu(MNFConv2d(x.repeat(...)))) for n_rows = len(x) * S rows: mean and variance are evaluated once
-    per distinct image (z is shared by the call), only the noise / ReLU / pool tail runs per sample.
-    z_rows [n_z, c_out] (with z = None): per-sample z, row r scaled by z_rows[r // rows_per_z] (SURVEY 8f-4)."""
+def conv_moments(layer, x, z):
+    """(mean, sd) [B, c_out, OH, OW] of MNFConv2d.forward without its noise (mnf_conv.py:69-75): the part of the layer
+    that does not depend on the Monte-Carlo sample when z is shared by the call.  z = None: unit scale."""
     dev = x.device
     B, c_in, H, W = x.shape
     c_out, ks = layer.W_mean.shape[0], layer.W_mean.shape[2]
@@ -383,20 +382,35 @@ def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows, z_rows=None, rows_per_z
     mean = torch.empty((B, c_out, OH, OW), device=dev, dtype=torch.float32)
     sd = torch.empty_like(mean)
     args = _conv_args(layer, dev)
-    lib = _lib.lib()
     with torch.cuda.device(dev):
-        rc = lib.mnf_conv2d_moments(x.data_ptr(), _p(z), *(a.data_ptr() for a in args), mean.data_ptr(),
-                                    sd.data_ptr(), B, c_in, H, W, c_out, ks, _lib.stream_ptr(dev))
+        rc = _lib.lib().mnf_conv2d_moments(x.data_ptr(), _p(z), *(a.data_ptr() for a in args), mean.data_ptr(),
+                                           sd.data_ptr(), B, c_in, H, W, c_out, ks, _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv2d_moments")
+    _lib.launch_count += 1
+    return mean, sd
+
+
+def conv_noise_relu_pool(mean, sd, noise: Noise, n_rows, z_rows=None, rows_per_z=1):
+    """maxpool2(relu(mean[r % B] + sd[r % B] * eps[r])) for n_rows rows: the per-sample tail of an MNFConv2d."""
+    dev = mean.device
+    B, c_out, OH, OW = mean.shape
     eps, sid = noise.normal((n_rows, c_out, OH, OW))
     out = torch.empty((n_rows, c_out, OH // 2, OW // 2), device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
-        rc = lib.mnf_conv_noise_relu_pool_z(mean.data_ptr(), sd.data_ptr(), B, _p(eps), noise.seed, sid, noise.row_offset,
-                                            out.data_ptr(), n_rows, c_out, OH, OW, _p(z_rows), rows_per_z,
-                                            _lib.stream_ptr(dev))
+        rc = _lib.lib().mnf_conv_noise_relu_pool_z(mean.data_ptr(), sd.data_ptr(), B, _p(eps), noise.seed, sid,
+                                                   noise.row_offset, out.data_ptr(), n_rows, c_out, OH, OW, _p(z_rows),
+                                                   rows_per_z, _lib.stream_ptr(dev))
     _lib.check(rc, "mnf_conv_noise_relu_pool")
-    _lib.launch_count += 2
+    _lib.launch_count += 1
     return out
+
+
+def conv_mc_relu_pool(layer, x, z, noise: Noise, n_rows, z_rows=None, rows_per_z=1):
+    """maxpool2(relu(MNFConv2d(x.repeat(...)))) for n_rows = len(x) * S rows: mean and variance are evaluated once
+    per distinct image (z is shared by the call), only the noise / ReLU / pool tail runs per sample.
+    z_rows [n_z, c_out] (with z = None): per-sample z, row r scaled by z_rows[r // rows_per_z] (SURVEY 8f-4)."""
+    mean, sd = conv_moments(layer, x, z)
+    return conv_noise_relu_pool(mean, sd, noise, n_rows, z_rows, rows_per_z)
 
 
 @torch.no_grad()

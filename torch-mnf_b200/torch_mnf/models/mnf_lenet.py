@@ -96,6 +96,48 @@ class MNFLeNet(nn.Sequential):
         h = self[9].forward(h, nz, precision=prec)
         return torch.log_softmax(h, dim=-1)
 
+    @torch.no_grad()
+    def predict(self, x, n_samples: int = 500, chunk: int = 25, seed=None, sample_range=None):
+        """Monte-Carlo predictive class probabilities ``[B, 10]``: the mean over ``n_samples`` stochastic forward passes of
+        ``softmax(model(x))`` -- ``model(img.repeat(500, 1, 1, 1))`` followed by the mean over the copies in
+        examples/mnf_mnist.ipynb:316-318 -- without materialising the repeat.  As in that single reference call the two conv
+        layers draw ONE z each for the whole prediction (mnf_conv.py:80-88), so their sample-independent parts (z, conv1's
+        mean / variance maps) are evaluated once instead of once per chunk of samples; everything per-row is drawn with
+        Philox keyed by the global row (sample s, image b), so the result does not depend on ``chunk`` or on how the samples
+        are sharded.  ``sample_range=(lo, hi)``: only samples lo..hi-1 and the SUM of their probabilities is returned (a
+        rank's share under MC-sample sharding: all-reduce the sums, divide by n_samples -- torch_mnf.distributed).
+        Identical, draw for draw, to summing ``forward(x, n_samples=chunk, seed=seed, row_offset=c * B).exp()`` over the chunks."""
+        x = _lib.require_cuda_f32(x, "input")
+        B = x.size(0)
+        lo, hi = (0, n_samples) if sample_range is None else sample_range
+        if seed is None:
+            seed = int(torch.randint(0, 2**62, (1,)).item())  # follows torch.manual_seed
+        sums = torch.zeros(B, 10, device=x.device, dtype=torch.float32)
+        if self.precision == "fp32" or B * min(chunk, max(hi - lo, 1)) < self.TC_MIN_ROWS:
+            for c in range(lo, hi, chunk):  # exact-fp32 pipeline: nothing sample-independent to share across chunks
+                s_here = min(chunk, hi - c)
+                sums += self.forward(x, n_samples=s_here, seed=seed, row_offset=c * B).exp().view(s_here, B, 10).sum(0)
+            return sums if sample_range is not None else sums / n_samples
+        # the call's two conv z draws (row offset 0 on every rank) and conv1's moments: once
+        nz0 = ops.Noise(None, x.device, 0, seed=seed)
+        z1, _ = self[0].sample_z(nz0)
+        mean1, sd1 = ops.conv_moments(self[0], x, z1)
+        nz0._next_stream()  # conv1's noise draw (per chunk below)
+        z2, _ = self[3].sample_z(nz0)
+        n_z = 1 + len(self[0].flow_q.flows)  # noise streams one conv sample_z consumes: z0 + one mask per q-flow
+        for c in range(lo, hi, chunk):
+            s_here = min(chunk, hi - c)
+            R = B * s_here
+            nz = ops.Noise(None, x.device, c * B, seed=seed)
+            nz.streams += n_z  # conv1's z: drawn above
+            h = ops.conv_noise_relu_pool(mean1, sd1, nz, R)
+            nz.streams += 1 + len(self[3].flow_q.flows)  # conv2's z: drawn above
+            h = ops.conv_forward_tc(self[3], h, z2, nz)
+            h = self[7].forward(h.view(R, -1), nz, relu=True)
+            h = self[9].forward(h, nz)
+            sums += torch.log_softmax(h, dim=-1).exp().view(s_here, B, 10).sum(0)
+        return sums if sample_range is not None else sums / n_samples
+
     def kl_div(self, noise=None):
         """Sum of the MNF layers' KL estimates (mnf_lenet.py:28-32)."""
         return sum(layer.kl_div(noise) for layer in self if hasattr(layer, "kl_div"))
