@@ -113,7 +113,7 @@ typedef struct mnf_flow_op {
  * log-probability straight into the gather buffers of the other ranks (peer-mapped device pointers, e.g. from
  * torch.distributed._symmetric_memory) at element row_offset + i -- or, when multicast_ptr is set, with ONE
  * multimem.st per element that the switch replicates to every rank.  The data transfer overlaps the kernel's
- * arithmetic; the only collective left after the launch is a barrier.  Supported by the constant-bank dim-2
+ * arithmetic; the only collective left after the launch is a barrier.  Supported by the tensor-core dim-2
  * kernel in MNF_RUN_LOGPROB mode. */
 #define MNF_MAX_PEERS 8
 typedef struct mnf_gather_out {
@@ -166,8 +166,8 @@ int mnf_flow_stack_backward(const mnf_flow_op *ops_host, int n_ops, const float 
                             float *grad_x, int64_t n_rows, int dim, int flags, void *stream);
 
 /* Floats of scratch `workspace` must provide for a run of this shape (0 = none needed; NULL is then
- * accepted).  The constant-bank variant of the dim-2 kernel parks points and log-dets there between
- * stack segments. */
+ * accepted).  dim 2: room for the weight image of the tensor-core kernel (the library keeps no device state of its own:
+ * per-call staging lives here); dim 64: a log-prob-only MADE run parks the points between flows. */
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 
 #define MNF_RUN_INVERSE 1
@@ -175,20 +175,24 @@ int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 #define MNF_RUN_LOGPROB 4
 #define MNF_RUN_STAGED 8  /* `workspace` holds the image written by mnf_flow_stack_stage for these params (below) */
 #define MNF_RUN_VARIANT_MASK 0x70
-#define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK) /* v in {0,1,2,3} */
+#define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK)
+/* v: 0, 1, 2 = shared-memory weight variants of the register-resident dim-2 kernel (2 = library default for its class),
+ *    4 = conditioner MLPs on the tensor cores (default for NSF_CL(K=8, n_h=16) stacks from 65 536 rows),
+ *    5 = eight lanes per point (default for AffineHalfFlow stacks up to 2048 rows); 3 (round 1's constant-bank variant,
+ *    removed) runs 2.  A variant the program is not eligible for falls back to the library default. */
 
 /* Small batches of a dim-2 stack spend most of their kernel time re-laying the conditioner nets out in every CTA's
  * shared memory.  mnf_flow_stack_stage writes that layout ONCE (call it again whenever a parameter changes) into a
  * caller-owned, 16-byte aligned buffer of mnf_flow_stack_stage_size() floats (0 = the program has no such form);
  * mnf_flow_stack_run with MNF_RUN_STAGED and that buffer as `workspace` then starts with a plain vector copy.  Only for
- * runs of fewer than 65 536 rows (larger runs of spline stacks use `workspace` for the constant-bank variant). */
+ * runs of fewer than 65 536 rows. */
 int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
 int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
                          float *staged, void *stream);
 
 /* Which kernel mnf_flow_stack_run would pick: 0 = generic interpreter, 1 = specialised
- * D=2 register-resident kernel, 2 = the constant-bank MADE kernel (all-MAF/IAF stacks of the BASELINE
- * config-3 shape, dim 64 / hidden 24-24-24, in their one-pass direction).  Host-only, no launch. */
+ * D=2 kernels (tensor cores / register-resident / lane-split by shape and batch), 2 = the exact-fp32 MADE kernels
+ * (all-MAF/IAF stacks of an instantiated (dim, hidden) shape with three hidden layers).  Host-only, no launch. */
 int mnf_flow_stack_plan(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
 
 /* Glow._assemble_W + torch.inverse (glow.py:20-24, 34-35):  W = P (tril(L,-1)+I)(triu(U,1)+diag S),

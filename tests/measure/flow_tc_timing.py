@@ -1,5 +1,5 @@
-"""Timing + error statistics of the tensor-core spline kernel (variant 4) next to the constant-bank FFMA2 kernel
-(variant 3) on BASELINE config 2.  Run on a GPU box:  python tests/measure/flow_tc_timing.py [log2_rows]
+"""Timing + error statistics of the tensor-core spline kernel (variant 4) next to the shared-memory FFMA2 kernel
+(variant 2; round 1's constant-bank variant 3 was removed in round 2) on BASELINE config 2.  Run on a GPU box:  python tests/measure/flow_tc_timing.py [log2_rows]
 Env: MNF_FTC_V (groups * 10 + tiles per thread, + 100 = biases in the epilogue), MNF_FTC_DEBUG (1 no spline, 2 no MMAs, 4 truncating hi split)."""
 import json
 import os
@@ -21,7 +21,7 @@ n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 24)
 x = 1.5 * torch.randn(n, 2, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
 out = {"rows": n, "V": os.environ.get("MNF_FTC_V"), "debug": os.environ.get("MNF_FTC_DEBUG")}
 lp_out = torch.empty(n, device="cuda")
-for kernel in (3, 4):
+for kernel in (2, 4):
     for _ in range(3):
         prog.run(x, True, log_prob_only=True, kernel=kernel, log_prob_out=lp_out)
     torch.cuda.synchronize()
@@ -35,7 +35,7 @@ for kernel in (3, 4):
     out[f"k{kernel}_ms"] = ms
     out[f"k{kernel}_gpts"] = n / ms / 1e6
     out[f"k{kernel}_lp"] = lp_out[: 1 << 16].clone()
-d = (out.pop("k3_lp") - out.pop("k4_lp")).abs()
-out["max_abs_diff_k3_k4"] = float(d.max())
-out["mean_abs_diff_k3_k4"] = float(d.mean())
+d = (out.pop("k2_lp") - out.pop("k4_lp")).abs()
+out["max_abs_diff_k2_k4"] = float(d.max())
+out["mean_abs_diff_k2_k4"] = float(d.mean())
 print(json.dumps(out))

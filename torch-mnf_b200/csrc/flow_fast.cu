@@ -78,9 +78,9 @@ static FastPlan plan_fast(const mnf_flow_op *ops, int n_ops, int dim, int varian
     return p;
 }
 
-// rows from which the large-batch kernels (tensor-core conditioners; constant-bank variant on request) are considered
+// rows from which the large-batch kernel (tensor-core conditioners, flow_tc.cu) is considered
 constexpr long long kCbankMinRows = 1 << 16;
-constexpr int kNumVariants = 4;
+constexpr int kNumVariants = 3;  // 0, 1, 2 (variant 3, round 1's constant-bank kernel, was removed: a request for it runs 2)
 constexpr bool kTcDefault = true;  // measured (profiles/r02_flow_tc.md): 3.85 vs 4.12 ms per 2^24 points at unchanged parity, one launch, 12 B/pt of DRAM traffic
 
 // ---------------------------------------------------------------------------------------------------
@@ -197,10 +197,11 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
                      float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int dim, int inverse,
                      int variant, float *workspace, const mnf_gather_out *gather, cudaStream_t stream,
                      bool plan_only) {
-    bool has_spline = false;
-    for (int k = 0; k < n_ops; ++k) has_spline |= ops[k].type == MNF_OP_NSF_CL;
-    // measured (r01): the constant-bank variant wins on spline stacks (4.10 vs 5.52 ms per 2^24 points) and loses
-    // slightly on pure AffineHalfFlow stacks (16.1 vs 15.0 ms), where a segment still holds two conditioners
+    bool has_spline = false, has_net = false;
+    for (int k = 0; k < n_ops; ++k) {
+        has_spline |= ops[k].type == MNF_OP_NSF_CL;
+        has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
+    }
     const bool want_gather = gather && (gather->n_peers > 0 || gather->multicast_ptr);
     // variant 4: conditioners on the tensor cores (flow_tc.cu), one launch for the whole stack, weights in the caller's
     // workspace.  Spline stacks of its shape class take it by default from kCbankMinRows rows up.
@@ -219,24 +220,17 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
         if (rc != 1) return rc;
     }
     if (variant == 5) variant = -1;
-    // Default: the shared-memory variant.  The constant-bank variant (3) keeps the conditioner nets in a __constant__ array
-    // and a __device__ stage of the library -- global device state behind a mutex, which the ABI's rules exclude -- so since
-    // r02 it runs only on explicit request (tests, comparisons); spline stacks of the benchmark shape take the tensor-core
-    // kernel above, which owns nothing.
+    // every remaining variant keeps its weights in shared memory and needs no workspace; 2 (output-packed FFMA2) is the default
     int mode = (variant >= 0 && variant < kNumVariants) ? variant : 2;
-    if (want_gather && (mode != 3 || !(inverse & 2) || (n_rows & 1))) return 1;  // caller reports the restriction
-    bool has_net = false;
-    for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
-    if (!has_net && mode == 3) mode = 2;
-    if (mode != 2) inverse &= ~4;  // a staged image (bit 2) is in the variant-2 layout; other variants use workspace differently
+    if (want_gather) return 1;  // the fused peer-memory gather lives in the tensor-core kernel only: caller reports the restriction
+    if (mode != 2) inverse &= ~4;  // a staged image (bit 2) is in the variant-2 layout
     FastPlan p = plan_fast(ops, n_ops, dim, mode);
     if (!p.ok) return 1;
-    if (mode == 3 && inter && (n_rows % 2)) return 1;
     const DeviceProps *dp = plan_only ? nullptr : device_props();
     const size_t smem_bytes = (size_t)p.lay.total_slots * sizeof(float);
-    if (plan_only) return (mode == 3 || smem_bytes <= 227 * 1024) ? 0 : 1;
+    if (plan_only) return smem_bytes <= 227 * 1024 ? 0 : 1;
     MNF_REQUIRE(dp != nullptr, MNF_E_DEVICE, "no CUDA device");
-    if (mode != 3 && smem_bytes > (size_t)dp->smem_optin) return 1;
+    if (smem_bytes > (size_t)dp->smem_optin) return 1;
     MNF_REQUIRE(((uintptr_t)x % 16) == 0 && (!y || ((uintptr_t)y % 16) == 0), MNF_E_ALIGN,
                 "x and y must be 16-byte aligned for the dim-2 kernel");
     MNF_REQUIRE(!log_det || ((uintptr_t)log_det % 8) == 0, MNF_E_ALIGN, "log_det must be 8-byte aligned");

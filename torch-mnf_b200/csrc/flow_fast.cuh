@@ -16,12 +16,11 @@
 //   1: point-packed FFMA2, (w,w) operand built with a MOV per weight
 //   2: output-packed FFMA2: weights stored transposed ([in][out]) so one LDS.128 delivers two
 //      ready (w_j, w_j+1) operands; the activation is duplicated once per input instead
-//   3: as 2, but the weights sit in the CONSTANT bank: they reach the FMA pipe through uniform
-//      registers (LDCU.128 -> FFMA2 R, R.F32, UR.F32x2, R), no shared-memory -> register-file
-//      traffic at all.  Needs the staged nets to fit in 64 KB (config 2: 23 KB).
+//   (3: round 1's constant-bank variant -- weights as uniform-register operands, the stack cut into one launch per
+//      conditioner.  Removed in round 2: it kept the nets in __constant__ / __device__ arrays of the library behind a
+//      mutex (global state the ABI excludes), and the tensor-core kernel of flow_tc.cu replaced it as the large-batch
+//      path; a request for variant 3 runs variant 2.)
 #pragma once
-#include <mutex>
-
 #include "flow_math.cuh"
 
 namespace mnf {
@@ -78,27 +77,12 @@ __device__ __forceinline__ float4 lds4(const float *base, int i) {  // i: compil
     return reinterpret_cast<const float4 *>(base)[i >> 2];
 }
 
-// constant-bank staging area of this translation unit's kernels (variant 3) and the global
-// scratch the nets are re-laid-out into before the device-to-device copy into the bank
-constexpr int kConstFloats = 16384 - 64;
-__constant__ float c_flow_w[kConstFloats];
-
 // weight accessors: offsets are in floats from the start of the staged net
 struct WShared {
     const float *p;
     __device__ __forceinline__ float4 ld4(int i) const { return reinterpret_cast<const float4 *>(p)[i >> 2]; }
     __device__ __forceinline__ float ld1(int i) const { return p[i]; }
 };
-// constant-bank accessor with a COMPILE-TIME base: every load becomes LDCU c[0x3][imm] into uniform
-// registers (ptxas keeps a run-time base in vector registers and falls back to per-thread LDC)
-template <int BASE>
-struct WConstAt {
-    __device__ __forceinline__ float4 ld4(int i) const {
-        return reinterpret_cast<const float4 *>(c_flow_w)[(BASE + i) >> 2];
-    }
-    __device__ __forceinline__ float ld1(int i) const { return c_flow_w[BASE + i]; }
-};
-
 // =====================================================================================
 // point-packed engine (variants 0, 1): float2 = (value for point A, value for point B)
 // smem net layout = blob layout: per Linear weight[out][in], bias[out]
@@ -567,302 +551,6 @@ int launch_inst(const FlowProgram &prog, const FastLayout &lay, size_t smem_byte
 }
 
 
-// =====================================================================================
-// VARIANT 3: constant-bank weights.  The stack is cut into segments with at most one
-// net-bearing flow each; a segment's two nets are copied (device to device, stream ordered) to
-// FIXED offsets of the constant bank, so every weight load is LDCU c[0x3][imm] -> uniform register
-// -> FFMA2, with no shared-memory or register-file traffic for weights.  Between segments the points
-// and the running log-det make one round trip through HBM (20 B/point, noise next to the FMA time).
-// =====================================================================================
-// launcher-internal op flags: an NSF_CL flow is cut into its two conditioner/spline halves, one per segment,
-// so a segment kernel holds ONE unrolled conditioner (~30 KB of code) instead of two
-constexpr uint32_t kFlagHalfA = 0x100u, kFlagHalfB = 0x200u;
-
-template <int H, int K>
-struct CbankLayout {
-    static constexpr int kSpline = fast_net_slots(H, 3 * K - 1, 2);  // floats per staged spline conditioner
-    static constexpr int kAffine = fast_net_slots(H, 1, 2);
-    static constexpr int kSegStride = 2 * (kSpline > kAffine ? kSpline : kAffine);
-};
-static_assert(CbankLayout<24, 8>::kSegStride <= kConstFloats, "segment nets must fit the constant bank");
-
-__device__ float g_flow_stage[MNF_MAX_OPS * 2 * 1900];  // staged nets of a whole program, execution order
-static_assert(CbankLayout<24, 8>::kSegStride <= 2 * 1900 && CbankLayout<16, 8>::kSegStride <= 2 * 1900, "stage size");
-
-// one CTA per (segment, slot): re-lay-out the segment's net(s) from the parameter blob into the stage.
-// NSF_CL halves own one net (slot 0); an AffineHalfFlow segment owns s_net (slot 0) and t_net (slot 1).
-template <int H>
-__global__ void cbank_stage_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
-                                   int seg_stride, int second_off_affine, int inverse) {
-    // prog is in EXECUTION order; segment index = number of net-bearing ops before this one
-    int target = blockIdx.x >> 1, slot = blockIdx.x & 1, seg = 0;
-    for (int k = 0; k < prog.n_ops; ++k) {
-        const mnf_flow_op &op = prog.ops[k];
-        if (op.type != MNF_OP_AFFINE_HALF && op.type != MNF_OP_NSF_CL) continue;
-        if (seg++ != target) continue;
-        int which = slot;
-        if (op.type == MNF_OP_NSF_CL) {
-            if (slot) return;
-            // forward: half A = f1, half B = f2 (spline_flow.py:249-266); inverse: half A = f2, half B = f1 (:268-285)
-            const bool half_b = op.flags & kFlagHalfB;
-            which = (half_b != (inverse != 0)) ? 1 : 0;
-        } else if (!(op.flags & (which ? MNF_FLAG_SHIFT : MNF_FLAG_SCALE))) {
-            return;
-        }
-        stage_net<H, 3>(params + op.net_off[which], g_flow_stage + target * seg_stride + (slot ? second_off_affine : 0),
-                        op.sizes[op.n_lin]);
-        return;
-    }
-}
-
-template <int H, int K, int BASE>
-__device__ __forceinline__ void cb_spline_half(const mnf_flow_op &op, float2 cond, float2 &trans, bool rqs_inverse,
-                                               float2 &ld) {
-    constexpr int NB = 3 * K - 1, NP2 = round4(NB) / 2;
-    constexpr bool FAST = MNF_SPLINE_FAST != 0;
-    float2 rA[NP2], rB[NP2];
-    {
-        const WConstAt<BASE> W;
-        float2 hA[H / 2], hB[H / 2];
-        op_hidden<H>(W, cond.x, cond.y, hA, hB);
-        const int wo = 2 * H + 2 * (H * H + H);
-        op_dense<H, NP2>(W, wo, wo + H * 2 * NP2, hA, hB, rA, rB);
-    }
-#pragma unroll 1
-    for (int pt = 0; pt < 2; ++pt) {
-        float raw[NB];
-#pragma unroll
-        for (int o = 0; o < NB; ++o) {
-            const float2 q = pt ? rB[o >> 1] : rA[o >> 1];
-            raw[o] = (o & 1) ? q.y : q.x;
-        }
-        float v = pt ? trans.y : trans.x;
-        float l = 0.f;
-        rq_spline<K, FAST>(raw, K, op.bound, op.edge_deriv, rqs_inverse, v, l);
-        if (pt) { trans.y = v; ld.y += l; } else { trans.x = v; ld.x += l; }
-    }
-}
-
-template <int H, int BASE>
-__device__ __forceinline__ float2 cb_affine_net(float2 cond) {
-    const WConstAt<BASE> W;
-    float2 hA[H / 2], hB[H / 2];
-    op_hidden<H>(W, cond.x, cond.y, hA, hB);
-    float2 o;
-    op_last1<H>(W, hA, hB, o.x, o.y);
-    return o;
-}
-
-// one segment of the stack (ops in execution order, <= 1 net-bearing op); one pair of points per thread
-template <int H, int K>
-__global__ void __launch_bounds__(128, 4)
-flow_cbank_kernel(const __grid_constant__ FlowProgram prog, const float *__restrict__ params,
-                  const float *__restrict__ x, const float *__restrict__ ld_in, float *__restrict__ y,
-                  float *__restrict__ log_det, float *__restrict__ base_lp, float *__restrict__ inter,
-                  long long n_rows, int dir_flags, const __grid_constant__ mnf_gather_out gather) {
-    using L = CbankLayout<H, K>;
-    const int inverse = dir_flags & 1;
-    const bool sum_lp = dir_flags & 2;
-    const long long n_pairs = (n_rows + 1) >> 1;
-    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = first < n_pairs;
-    const long long pair = live ? first : n_pairs - 1;  // idle threads redo the last pair, stores predicated off
-    const bool has_b = 2 * pair + 1 < n_rows;
-    float2 v0, v1, ld = make_float2(0.f, 0.f);
-    if (has_b) {
-        const float4 q = ld_stream4(reinterpret_cast<const float4 *>(x) + pair);
-        v0 = make_float2(q.x, q.z);
-        v1 = make_float2(q.y, q.w);
-        if (ld_in) ld = ld_stream2(reinterpret_cast<const float2 *>(ld_in) + pair);
-    } else {
-        const float2 q = ld_stream2(reinterpret_cast<const float2 *>(x) + 2 * pair);
-        v0 = make_float2(q.x, q.x);
-        v1 = make_float2(q.y, q.y);
-        if (ld_in) ld.x = ld.y = ld_in[2 * pair];
-    }
-    int slot = 0;  // per-flow output slot within this segment
-#pragma unroll 1
-    for (int kk = 0; kk < prog.n_ops; ++kk) {
-        const mnf_flow_op &op = prog.ops[kk];
-        if (op.type == MNF_OP_AFFINE_CONST) {
-            const float s0 = params[op.aux_off], s1 = params[op.aux_off + 1];
-            const float t0 = params[op.aux_off + 2], t1 = params[op.aux_off + 3];
-            if (inverse) {  // affine_constant_flow.py:24
-                const float e0 = expf(-s0), e1 = expf(-s1);
-                v0 = make_float2((v0.x - t0) * e0, (v0.y - t0) * e0);
-                v1 = make_float2((v1.x - t1) * e1, (v1.y - t1) * e1);
-                ld.x -= s0 + s1;
-                ld.y -= s0 + s1;
-            } else {  // affine_constant_flow.py:19
-                const float e0 = expf(s0), e1 = expf(s1);
-                v0 = make_float2(v0.x * e0 + t0, v0.y * e0 + t0);
-                v1 = make_float2(v1.x * e1 + t1, v1.y * e1 + t1);
-                ld.x += s0 + s1;
-                ld.y += s0 + s1;
-            }
-        } else if (op.type == MNF_OP_GLOW) {
-            const float *W = params + op.aux_off + (inverse ? 4 : 0);  // glow.py:28,36: v @ W
-            const float w00 = W[0], w01 = W[1], w10 = W[2], w11 = W[3];
-            const float lg = params[op.aux_off + 8];
-            const float2 n0 = make_float2(fmaf(v1.x, w10, v0.x * w00), fmaf(v1.y, w10, v0.y * w00));
-            const float2 n1 = make_float2(fmaf(v1.x, w11, v0.x * w01), fmaf(v1.y, w11, v0.y * w01));
-            v0 = n0;
-            v1 = n1;
-            ld.x += inverse ? -lg : lg;
-            ld.y += inverse ? -lg : lg;
-        } else if (op.type == MNF_OP_AFFINE_HALF) {
-            const bool parity = op.flags & MNF_FLAG_PARITY;
-            const float2 cond = parity ? v1 : v0;  // affine_half_flow.py:46-50
-            float2 tr = parity ? v0 : v1;
-            float2 s = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
-            if (op.flags & MNF_FLAG_SCALE) s = cb_affine_net<H, 0>(cond);
-            if (op.flags & MNF_FLAG_SHIFT) t = cb_affine_net<H, L::kAffine>(cond);
-            if (inverse) {  // affine_half_flow.py:54-56
-                tr = make_float2((tr.x - t.x) / expf(s.x), (tr.y - t.y) / expf(s.y));
-                ld.x -= s.x;
-                ld.y -= s.y;
-            } else {  // affine_half_flow.py:58
-                tr = make_float2(expf(s.x) * tr.x + t.x, expf(s.y) * tr.y + t.y);
-                ld.x += s.x;
-                ld.y += s.y;
-            }
-            if (parity) v0 = tr; else v1 = tr;
-        } else if (op.type == MNF_OP_NSF_CL) {
-            // one half of the coupling layer per segment (its conditioner sits at constant-bank offset 0).
-            // Half A conditions on v0 going forward (f1: lower -> upper) and on v1 going backward (f2);
-            // half B the other way round.
-            const bool cond_v0 = ((op.flags & kFlagHalfB) != 0) == (inverse != 0);
-            const float2 cond = cond_v0 ? v0 : v1;
-            float2 tr = cond_v0 ? v1 : v0;
-            cb_spline_half<H, K, 0>(op, cond, tr, inverse != 0, ld);
-            if (cond_v0) v1 = tr; else v0 = tr;
-        }
-        // per-flow outputs are defined after the flow's LAST half
-        if ((op.flags & kFlagHalfA) != 0) continue;
-        if (inter && live) {
-            float *dst = inter + ((size_t)slot * n_rows + 2 * pair) * 2;
-            if (has_b)
-                st_stream4(reinterpret_cast<float4 *>(dst), make_float4(v0.x, v1.x, v0.y, v1.y));
-            else
-                st_stream2(reinterpret_cast<float2 *>(dst), make_float2(v0.x, v1.x));
-        }
-        ++slot;
-    }
-    if (!live) return;
-    const float c = -1.8378770664093453f;  // -(D/2) log(2 pi), D = 2
-    float2 lp = make_float2(fmaf(-0.5f, fmaf(v0.x, v0.x, v1.x * v1.x), c),
-                            fmaf(-0.5f, fmaf(v0.y, v0.y, v1.y * v1.y), c));
-    if (sum_lp) lp = make_float2(lp.x + ld.x, lp.y + ld.y);
-    if (has_b) {
-        if (y) st_stream4(reinterpret_cast<float4 *>(y) + pair, make_float4(v0.x, v1.x, v0.y, v1.y));
-        if (log_det) st_stream2(reinterpret_cast<float2 *>(log_det) + pair, ld);
-        if (base_lp) st_stream2(reinterpret_cast<float2 *>(base_lp) + pair, lp);
-        // fused gather: the result also goes straight to the other ranks over NVLink (n_rows is even here)
-        if (gather.multicast_ptr) {
-            asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(gather.multicast_ptr + gather.row_offset + 2 * pair),
-                         "f"(lp.x), "f"(lp.y)
-                         : "memory");
-        } else {
-            for (int p = 0; p < gather.n_peers; ++p)
-                st_stream2(reinterpret_cast<float2 *>(gather.peer_ptrs[p] + gather.row_offset) + pair, lp);
-        }
-    } else {
-        if (y) st_stream2(reinterpret_cast<float2 *>(y) + 2 * pair, make_float2(v0.x, v1.x));
-        if (log_det) log_det[2 * pair] = ld.x;
-        if (base_lp) base_lp[2 * pair] = lp.x;
-    }
-}
-
-struct ConstBankGuard {  // the bank and the stage are shared by every launch of this TU's kernels on a device
-    std::mutex mu;
-    cudaEvent_t done[64] = {};
-};
-
-// prog: ops in MODULE order.  workspace: 3 * n_rows floats (points + log-det between segments).
-template <int H, int K>
-int launch_cbank(const FlowProgram &prog, const float *params, const float *x, float *y, float *log_det,
-                 float *base_lp, float *inter, int64_t n_rows, int dir_flags, float *workspace,
-                 const mnf_gather_out *gather, cudaStream_t stream) {
-    using L = CbankLayout<H, K>;
-    mnf_gather_out no_gather{};
-    if (gather) MNF_REQUIRE(gather->n_peers >= 0 && gather->n_peers <= MNF_MAX_PEERS, MNF_E_ARG, "bad n_peers");
-    const int inverse = dir_flags & 1;
-    // execution order, NSF_CL flows cut into halves; every net-bearing entry starts a new segment
-    struct Exec {
-        int n = 0;
-        mnf_flow_op ops[2 * MNF_MAX_OPS];
-        int flow_index[2 * MNF_MAX_OPS];  // execution index of the flow an entry belongs to (for intermediates)
-    } ex;
-    for (int k = 0; k < prog.n_ops; ++k) {
-        const mnf_flow_op &op = prog.ops[inverse ? prog.n_ops - 1 - k : k];
-        if (op.type == MNF_OP_NSF_CL) {
-            ex.ops[ex.n] = op, ex.ops[ex.n].flags |= kFlagHalfA, ex.flow_index[ex.n++] = k;
-            ex.ops[ex.n] = op, ex.ops[ex.n].flags |= kFlagHalfB, ex.flow_index[ex.n++] = k;
-        } else {
-            ex.ops[ex.n] = op, ex.flow_index[ex.n++] = k;
-        }
-    }
-    int seg_begin[2 * MNF_MAX_OPS + 1], n_seg = 0, nets_seen = 0;
-    seg_begin[n_seg++] = 0;
-    for (int k = 0; k < ex.n; ++k) {
-        const bool net = ex.ops[k].type == MNF_OP_AFFINE_HALF || ex.ops[k].type == MNF_OP_NSF_CL;
-        if (net && nets_seen++ > 0) seg_begin[n_seg++] = k;
-    }
-    seg_begin[n_seg] = ex.n;
-    MNF_REQUIRE(n_seg == 1 || workspace != nullptr, MNF_E_ARG,
-                "multi-segment constant-bank run needs a workspace of 3*n_rows floats");
-    MNF_REQUIRE(nets_seen <= MNF_MAX_OPS, MNF_E_SHAPE, "too many conditioner nets for the stage (%d)", nets_seen);
-
-    static ConstBankGuard guard;
-    int dev = 0;
-    MNF_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(guard.mu);
-    if (!guard.done[dev]) MNF_CUDA(cudaEventCreateWithFlags(&guard.done[dev], cudaEventDisableTiming));
-    else MNF_CUDA(cudaStreamWaitEvent(stream, guard.done[dev], 0));  // other streams: wait, no host sync
-
-    if (nets_seen > 0) {
-        // the stage kernel walks net-bearing entries only; hand it those (<= MNF_MAX_OPS of them)
-        FlowProgram nets;
-        nets.n_ops = 0;
-        for (int k = 0; k < ex.n; ++k)
-            if (ex.ops[k].type == MNF_OP_AFFINE_HALF || ex.ops[k].type == MNF_OP_NSF_CL) nets.ops[nets.n_ops++] = ex.ops[k];
-        cbank_stage_kernel<H><<<2 * nets_seen, 128, 0, stream>>>(nets, params, L::kSegStride, L::kAffine, inverse);
-        int rc = launch_status("cbank_stage_kernel");
-        if (rc) return rc;
-    }
-    void *stage_ptr = nullptr;
-    MNF_CUDA(cudaGetSymbolAddress(&stage_ptr, g_flow_stage));
-    const long long n_pairs = (n_rows + 1) / 2;
-    const unsigned blocks = (unsigned)((n_pairs + 127) / 128);
-    float *z_tmp = workspace, *ld_tmp = workspace ? workspace + 2 * n_rows : nullptr;
-    int net_idx = 0, rc = 0;
-    for (int sgm = 0; sgm < n_seg; ++sgm) {
-        FlowProgram sp;
-        sp.n_ops = seg_begin[sgm + 1] - seg_begin[sgm];
-        bool has_net = false;
-        for (int k = 0; k < sp.n_ops; ++k) {
-            sp.ops[k] = ex.ops[seg_begin[sgm] + k];
-            has_net |= sp.ops[k].type == MNF_OP_AFFINE_HALF || sp.ops[k].type == MNF_OP_NSF_CL;
-        }
-        if (has_net) {
-            MNF_CUDA(cudaMemcpyToSymbolAsync(c_flow_w, (const float *)stage_ptr + (size_t)net_idx * L::kSegStride,
-                                             sizeof(float) * L::kSegStride, 0, cudaMemcpyDeviceToDevice, stream));
-            ++net_idx;
-        }
-        const bool first = sgm == 0, last = sgm == n_seg - 1;
-        // per-flow outputs: entry k of the segment writes slot flow_index (half A entries are skipped in-kernel)
-        float *inter_seg = inter ? inter + (size_t)ex.flow_index[seg_begin[sgm]] * n_rows * 2 : nullptr;
-        flow_cbank_kernel<H, K><<<blocks, 128, 0, stream>>>(sp, params, first ? x : z_tmp, first ? nullptr : ld_tmp,
-                                                            last ? y : z_tmp, last ? log_det : ld_tmp,
-                                                            last ? base_lp : nullptr, inter_seg, n_rows, dir_flags,
-                                                            (last && gather) ? *gather : no_gather);
-        rc = launch_status("flow_cbank_kernel");
-        if (rc) break;
-    }
-    MNF_CUDA(cudaEventRecord(guard.done[dev], stream));
-    return rc;
-}
-
 #define MNF_FLOW_FAST_ARGS                                                                                    \
     int variant, const FlowProgram &prog, const FastLayout &lay, size_t smem_bytes, const float *params,      \
         const float *x, float *y, float *log_det, float *base_lp, float *inter, int64_t n_rows, int inverse,  \
@@ -876,13 +564,6 @@ int launch_cbank(const FlowProgram &prog, const float *params, const float *x, f
         if (variant == 1)                                                                                       \
             return launch_inst<HH, KK, 1>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows, \
                                           inverse, dp, stream);                                                 \
-        /* constant-bank variant: only the shapes it is validated on at >= 65536 rows (the BASELINE ones); the   \
-           (8, 5) instantiation gave wrong results there in r02 testing and other widths are untested -- they take \
-           the shared-memory variant at every batch size */                                                      \
-        if (variant == 3 && KK == 8 && (HH == 16 || HH == 24))                                                  \
-            return launch_cbank<HH, KK>(prog, params, x, y, log_det, base_lp, inter, n_rows, inverse, workspace, \
-                                        gather, stream);                                                        \
-        if (variant == 3 && gather && (gather->n_peers > 0 || gather->multicast_ptr)) return 1;                 \
         return launch_inst<HH, KK, 2>(prog, lay, smem_bytes, params, x, y, log_det, base_lp, inter, n_rows,     \
                                       inverse, dp, stream, (inverse & 4) ? workspace : nullptr);                \
     }                                                                                                           \

@@ -139,7 +139,7 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
         if (rc != 1) return rc;
     }
     MNF_REQUIRE(!gather || (gather->n_peers == 0 && !gather->multicast_ptr), MNF_E_SHAPE,
-                "peer-memory gather output needs the constant-bank dim-2 kernel (spline stack, >= 65536 rows)");
+                "peer-memory gather output needs the tensor-core dim-2 kernel (NSF_CL(K=8, n_h=16) stack in log-prob mode, >= 65536 rows)");
     return launch_flow_generic(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
                                n_rows, dim, inverse & 3, st);
 }
@@ -214,8 +214,9 @@ int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *pa
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim) {
     (void)n_ops;
     if (dim == 64) return n_rows * 64;  // MADE density stack in log-prob mode parks z here between flows
-    // dim 2: points + log-det between the segments of the constant-bank kernel, or the weight image of the tensor-core kernel
-    return dim == 2 ? 3 * (n_rows + (n_rows & 1)) + flow_tc_workspace_floats() : 0;
+    // dim 2: the weight image of the tensor-core kernel (every other dim-2 kernel needs none)
+    (void)n_rows;
+    return dim == 2 ? flow_tc_workspace_floats() : 0;
 }
 
 int mnf_glow_assemble(const float *P, const float *L, const float *U, const float *S, float *out, int dim,

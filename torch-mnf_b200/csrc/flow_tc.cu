@@ -464,11 +464,21 @@ static int launch_v(const Params &p, long long n_tiles, int sm_count, size_t sme
 //   an activation beyond the fp16 range becomes inf, which reaches every output of the conditioner as inf / NaN: the
 //   owning thread then re-evaluates ITS point's conditioner in plain fp32 from the parameter blob (rare, divergent).
 // Weight tile row n (K-major, 128-byte swizzle): (W_hi[16] | W_hi[16] | W_lo[16] | 0[16]) fp16; biases are added by the
-// epilogue from shared memory.
+// epilogue from shared memory.  Only the second hidden layer and the output layer are GEMMs (see the table below).
 // =========================================================================================================
-constexpr uint32_t W16L_BYTES = H * 128, W16O_BYTES = NOUT * 128, NET16_BYTES = 2 * W16L_BYTES + W16O_BYTES;  // 8 KB
+constexpr uint32_t W16L_BYTES = H * 128, W16O_BYTES = NOUT * 128, NET16_BYTES = W16L_BYTES + W16O_BYTES;  // 6 KB: hidden layer 2, output layer
+// Layers 0 and 1 of a conditioner need no GEMM at all: its input is ONE scalar c, so W1 leaky(w0 c + b0) + b1 is a
+// piecewise-linear function of c with the H breakpoints -b0_j / w0_j -- on each of the H + 1 intervals it is A_i c + B_i.
+// The image holds the sorted breakpoints and the (A_i | B_i) rows (built in fp64 per parameter version); a thread finds its
+// interval with H compares and forms the layer-1 pre-activations with H FMAs: 16 instead of 16 + 256 multiply-adds per
+// point, and one MMA round trip per conditioner less.
+constexpr int TBL_STRIDE = 36;                                    // floats per (A_i | B_i) row, padded off the bank period
+constexpr int VEC16_B2 = 0, VEC16_B3 = H, VEC16_TB = H + NOUT, VEC16_TBL = VEC16_TB + H;
+constexpr int VEC16_FLOATS = VEC16_TBL + (H + 1) * TBL_STRIDE;   // b2[16] b3[32] breakpoints[16] table[17][36]
+constexpr uint32_t VEC16_BYTES = VEC16_FLOATS * 4;
+static_assert(VEC16_BYTES % 16 == 0 && (VEC16_TBL * 4) % 16 == 0 && (TBL_STRIDE * 4) % 16 == 0, "16-byte loads / bulk copies");
 constexpr uint32_t SLOT16_COLS = 48;  // A: 8 columns hi, 8 columns lo; D: 32 columns at + 16
-__host__ __device__ constexpr uint32_t image16_bytes(int n_nets) { return (uint32_t)n_nets * (NET16_BYTES + VEC_BYTES); }
+__host__ __device__ constexpr uint32_t image16_bytes(int n_nets) { return (uint32_t)n_nets * (NET16_BYTES + VEC16_BYTES); }
 __host__ __device__ constexpr uint32_t f16_instr_desc(int m, int n) {  // D = F32, A = B = F16, both K-major
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -492,14 +502,12 @@ __global__ void flow_tc16_image_kernel(const __grid_constant__ NetList nets, con
     uint16_t *tiles = reinterpret_cast<uint16_t *>(image + (size_t)net * NET16_BYTES);
     constexpr int OFF1 = 2 * H, OFF2 = OFF1 + H * H + H, OFF3 = OFF2 + H * H + H;
     for (int e = threadIdx.x; e < (int)(NET16_BYTES / 2); e += blockDim.x) {
-        int layer, r = e;
-        if (r < (int)(W16L_BYTES / 2)) layer = 0;
-        else if (r < (int)(2 * W16L_BYTES / 2)) layer = 1, r -= W16L_BYTES / 2;
-        else layer = 2, r -= 2 * W16L_BYTES / 2;
+        int layer = 1, r = e;  // MLP layer index: 1 = second hidden layer (blob offset OFF2), 2 = output layer (OFF3)
+        if (r >= (int)(W16L_BYTES / 2)) layer = 2, r -= W16L_BYTES / 2;
         const int n_out = layer == 2 ? NB : H;
         const int n = r >> 6, pos = (r >> 3) & 7, j = r & 7;
         const int k = ((pos ^ (n & 7)) << 3) + j;  // logical K index of this half (128-byte swizzle: 16-byte chunk ^= row & 7)
-        const float *W = src + (layer == 0 ? OFF1 : layer == 1 ? OFF2 : OFF3);
+        const float *W = src + (layer == 1 ? OFF2 : OFF3);
         __half v = __float2half_rn(0.f);
         if (n < n_out && k < 48) {
             const float w = W[n * H + (k & 15)];
@@ -508,14 +516,43 @@ __global__ void flow_tc16_image_kernel(const __grid_constant__ NetList nets, con
         }
         tiles[e] = __half_as_ushort(v);
     }
-    float *vec = reinterpret_cast<float *>(image + (size_t)nets.n * NET16_BYTES + (size_t)net * VEC_BYTES);
-    for (int e = threadIdx.x; e < VEC_FLOATS; e += blockDim.x) {
+    float *vec = reinterpret_cast<float *>(image + (size_t)nets.n * NET16_BYTES + (size_t)net * VEC16_BYTES);
+    for (int e = threadIdx.x; e < VEC16_TB; e += blockDim.x) {
         float v = 0.f;
-        if (e < 2 * H) v = src[e];
-        else if (e < 3 * H) v = src[OFF1 + H * H + (e - 2 * H)];
-        else if (e < 4 * H) v = src[OFF2 + H * H + (e - 3 * H)];
-        else if (e < 4 * H + NB) v = src[OFF3 + NB * H + (e - 4 * H)];
+        if (e < H) v = src[OFF2 + H * H + e];                   // b2
+        else if (e < H + NB) v = src[OFF3 + NB * H + (e - H)];   // b3
         vec[e] = v;
+    }
+    // layers 0 + 1 as a piecewise-linear table: thread i builds interval i (between the sorted breakpoints i - 1 and i)
+    if (threadIdx.x <= H) {
+        const int i = threadIdx.x;
+        const float *w0 = src, *b0 = src + H, *W1 = src + OFF1, *b1 = src + OFF1 + H * H;
+        double ts[H];
+        for (int j = 0; j < H; ++j) ts[j] = w0[j] != 0.f ? -(double)b0[j] / (double)w0[j] : INFINITY;
+        for (int a = 1; a < H; ++a) {  // insertion sort, ascending (+inf = "no breakpoint" last)
+            const double v = ts[a];
+            int b = a - 1;
+            while (b >= 0 && ts[b] > v) ts[b + 1] = ts[b], --b;
+            ts[b + 1] = v;
+        }
+        if (i < H) vec[VEC16_TB + i] = (float)ts[i];
+        const double lo = i > 0 ? ts[i - 1] : -INFINITY, hi = i < H ? ts[i] : INFINITY;
+        double c = 0.0;  // a point inside the interval: fixes the sign of every first-layer pre-activation on it
+        if (isfinite(lo) && isfinite(hi)) c = 0.5 * (lo + hi);
+        else if (isfinite(hi)) c = hi - 1.0 - fabs(hi);
+        else if (isfinite(lo)) c = lo + 1.0 + fabs(lo);
+        float *row = vec + VEC16_TBL + i * TBL_STRIDE;
+        for (int k = 0; k < H; ++k) {
+            double A = 0.0, B = (double)b1[k];
+            for (int j = 0; j < H; ++j) {
+                const double pre = (double)w0[j] * c + (double)b0[j];
+                const double slope = pre > 0.0 ? 1.0 : 0.2;  // LeakyReLU(0.2), mlp.py:9
+                A += (double)W1[k * H + j] * slope * (double)w0[j];
+                B += (double)W1[k * H + j] * slope * (double)b0[j];
+            }
+            row[k] = (float)A, row[H + k] = (float)B;
+        }
+        for (int k = 2 * H; k < TBL_STRIDE; ++k) row[k] = 0.f;
     }
 }
 
@@ -584,7 +621,7 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int n_nets = p.n_nets;
-    const uint32_t off_vec = (uint32_t)n_nets * NET16_BYTES, off_bar = off_vec + (uint32_t)n_nets * VEC_BYTES;
+    const uint32_t off_vec = (uint32_t)n_nets * NET16_BYTES, off_bar = off_vec + (uint32_t)n_nets * VEC16_BYTES;
     const uint32_t bars = base + off_bar;
     const uint32_t w_bar = bars;
     auto acc_ready = [&](int s) { return bars + 8u * (1 + s); };
@@ -614,7 +651,7 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         mbar_expect_tx(w_bar, image16_bytes(n_nets));
         for (int n = 0; n < n_nets; ++n) bulk_load(base + (uint32_t)n * NET16_BYTES, p.image + (size_t)n * NET16_BYTES, NET16_BYTES, w_bar);
-        bulk_load(base + off_vec, p.image + (size_t)n_nets * NET16_BYTES, (uint32_t)n_nets * VEC_BYTES, w_bar);
+        bulk_load(base + off_vec, p.image + (size_t)n_nets * NET16_BYTES, (uint32_t)n_nets * VEC16_BYTES, w_bar);
     }
 
     const int slot = warp >> 2, q = warp & 3, row = q * 32 + lane;
@@ -682,23 +719,29 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
                 for (int step = 0; step < 2; ++step, ++net) {
                     const bool use_f1 = (step == 0) != (inverse != 0);
                     const float c = use_f1 ? v0 : v1;
-                    const float *vec = svec + net * VEC_FLOATS;
+                    const float *vec = svec + net * VEC16_FLOATS;
                     const uint32_t tiles = (uint32_t)net * NET16_BYTES;
                     uint32_t r[16];
-                    {  // layer 0 (1 -> 16) on the FMA pipe
-                        const float4 *wb = reinterpret_cast<const float4 *>(vec);
+                    {  // layers 0 and 1: interval of c among the sorted breakpoints, then pre1 = A_i c + B_i
+                        const float4 *tb = reinterpret_cast<const float4 *>(vec + VEC16_TB);
+                        int iv = 0;
+#pragma unroll
+                        for (int j = 0; j < H / 4; ++j) {
+                            const float4 t4 = tb[j];
+                            iv += (c > t4.x) + (c > t4.y) + (c > t4.z) + (c > t4.w);
+                        }
+                        const float4 *row = reinterpret_cast<const float4 *>(vec + VEC16_TBL + iv * TBL_STRIDE);
                         float pre[16];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 w = wb[j], b = wb[4 + j];
-                            pre[4 * j] = fmaf(w.x, c, b.x), pre[4 * j + 1] = fmaf(w.y, c, b.y);
-                            pre[4 * j + 2] = fmaf(w.z, c, b.z), pre[4 * j + 3] = fmaf(w.w, c, b.w);
+                            const float4 a4 = row[j], b4 = row[4 + j];
+                            pre[4 * j] = fmaf(a4.x, c, b4.x), pre[4 * j + 1] = fmaf(a4.y, c, b4.y);
+                            pre[4 * j + 2] = fmaf(a4.z, c, b4.z), pre[4 * j + 3] = fmaf(a4.w, c, b4.w);
                         }
                         act_split16_h(pre, r);
                     }
-                    publish(r, tiles, IDESC16_H);
-#pragma unroll 1
-                    for (int l = 0; l < 2; ++l) {
+                    publish(r, tiles, IDESC16_H);  // second hidden layer
+                    {
                         acquire();
                         uint32_t t[16];
                         if (!(p.debug & 128)) {  // (timing experiment: no TMEM loads)
@@ -708,7 +751,7 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
 #pragma unroll
                             for (int j = 0; j < 16; ++j) t[j] = r[j];
                         }
-                        const float4 *bb = reinterpret_cast<const float4 *>(vec + 2 * H + l * H);
+                        const float4 *bb = reinterpret_cast<const float4 *>(vec + VEC16_B2);
                         float pre[16];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -717,7 +760,7 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
                             pre[4 * j + 2] = __uint_as_float(t[4 * j + 2]) + b.z, pre[4 * j + 3] = __uint_as_float(t[4 * j + 3]) + b.w;
                         }
                         act_split16_h(pre, r);
-                        publish(r, tiles + (uint32_t)(l + 1) * W16L_BYTES, l == 1 ? IDESC16_O : IDESC16_H);
+                        publish(r, tiles + W16L_BYTES, IDESC16_O);  // output layer
                     }
                     acquire();
                     float raw[NB];
@@ -734,9 +777,9 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
                             for (int j = 0; j < 8; ++j) t1[j] = r[j + 8];
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) raw[j] = __uint_as_float(t0[j]) + vec[4 * H + j];
+                        for (int j = 0; j < 16; ++j) raw[j] = __uint_as_float(t0[j]) + vec[VEC16_B3 + j];
 #pragma unroll
-                        for (int j = 0; j < NB - 16; ++j) raw[16 + j] = __uint_as_float(t1[j]) + vec[5 * H + j];
+                        for (int j = 0; j < NB - 16; ++j) raw[16 + j] = __uint_as_float(t1[j]) + vec[VEC16_B3 + 16 + j];
                     }
                     if (!(fabsf(raw[0] + raw[KBINS] + raw[2 * KBINS]) < 3.0e38f)) {  // an activation left the fp16 range
                         float exact[NB];

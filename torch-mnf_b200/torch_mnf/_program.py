@@ -278,7 +278,7 @@ class FlowProgram:
         self._staged = {}  # dim -> pre-staged shared-memory image of the nets (or False), rebuilt with the blob
         self._key = key
 
-    STAGED_MAX_ROWS = (1 << 16) - 1  # above this the dim-2 spline stacks switch to the constant-bank variant
+    STAGED_MAX_ROWS = (1 << 16) - 1  # above this the dim-2 spline stacks of the benchmark shape take the tensor-core kernel
 
     def _staged_image(self, lib, n_rows, dim, kernel):
         """Pre-staged net image for small dim-2 batches (mnf_flow_stack_stage), cached until a parameter changes."""
@@ -301,9 +301,6 @@ class FlowProgram:
     def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False, kernel=None):
         if have_y and dim != 2:
             return None  # only log-prob-only runs (no y buffer) of the MADE kernel park points in the workspace
-        if dim == 2 and kernel != 3:
-            n_rows = 0  # only the constant-bank variant (explicit request) parks points between its segments; every
-            #             other dim-2 kernel needs at most the weight image of the tensor-core kernel
         need = lib.mnf_flow_stack_workspace(n_ops, n_rows, dim)
         return torch.empty(need, device=dev, dtype=torch.float32) if need > 0 else None
 
