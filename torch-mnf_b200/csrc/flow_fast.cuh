@@ -37,11 +37,19 @@ struct FastLayout {
 
 constexpr int round4(int n) { return (n + 3) / 4 * 4; }
 
+// Variant 2 does not evaluate layers 0 and 1 of a conditioner as layers: its input is ONE scalar c, so
+// W1 leaky(w0 c + b0) + b1 is a piecewise-linear function of c with the H breakpoints -b0_j / w0_j; on each of the H + 1
+// intervals it is A_i c + B_i.  The staged net holds the sorted breakpoints and the (A_i | B_i) rows: a point finds its
+// interval with H compares and forms the layer-1 pre-activations with H FMAs instead of H + H^2 (RNVP, H = 24: 648 instead
+// of 1 224 multiply-adds per conditioner -- and a small-batch call is bound by exactly that dependent chain).
+//   staged layout: tb[H] | table[H + 1][pl_stride(H)] | Wt2[in][out] b2[H] | last layer
+constexpr int pl_stride(int H) { return 2 * H + 4; }  // padded off the 32-bank period: rows of different intervals do not collide
+constexpr int pl_hidden_slots(int H) { return H + (H + 1) * pl_stride(H) + H * H + H; }
+
 // floats one staged net occupies in shared memory
 constexpr int fast_net_slots(int H, int n_out, int variant) {
-    const int hidden = 2 * H + 2 * (H * H + H);
-    if (variant >= 2) return hidden + (n_out == 1 ? H + 4 : H * round4(n_out) + round4(n_out));
-    return hidden + n_out * H + round4(n_out);
+    if (variant >= 2) return pl_hidden_slots(H) + (n_out == 1 ? H + 4 : H * round4(n_out) + round4(n_out));
+    return 2 * H + 2 * (H * H + H) + n_out * H + round4(n_out);
 }
 
 __device__ __forceinline__ float2 fma2_packed(float2 a, float2 b, float2 c) {
@@ -185,28 +193,32 @@ template <int H, class WT>
 __device__ __forceinline__ void op_hidden(const WT W, float xA, float xB, float2 (&hA)[H / 2],
                                           float2 (&hB)[H / 2]) {
     static_assert(H % 4 == 0, "hidden width must be a multiple of 4");
+    constexpr int TS = pl_stride(H), TBL = H, L2 = H + (H + 1) * TS;
     float2 gA[H / 2], gB[H / 2];
-    const float2 xa = make_float2(xA, xA), xb = make_float2(xB, xB);
+    // layers 0 + 1: interval of each point among the sorted breakpoints, then pre1 = A_i c + B_i
+    int ia = 0, ib = 0;
 #pragma unroll
-    for (int j = 0; j < H / 2; j += 2) {  // layer 0
-        const float4 w = W.ld4(2 * j), b = W.ld4(H + 2 * j);
-        gA[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xa, make_float2(b.x, b.y)));
-        gB[j] = leaky2(fma2_packed(make_float2(w.x, w.y), xb, make_float2(b.x, b.y)));
-        gA[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xa, make_float2(b.z, b.w)));
-        gB[j + 1] = leaky2(fma2_packed(make_float2(w.z, w.w), xb, make_float2(b.z, b.w)));
+    for (int j = 0; j < H; j += 4) {
+        const float4 t = W.ld4(j);
+        ia += (xA > t.x) + (xA > t.y) + (xA > t.z) + (xA > t.w);
+        ib += (xB > t.x) + (xB > t.y) + (xB > t.z) + (xB > t.w);
     }
-    const int l1 = 2 * H, l2 = 2 * H + H * H + H;
-    op_dense<H, H / 2>(W, l1, l1 + H * H, gA, gB, hA, hB);
+    const float2 xa = make_float2(xA, xA), xb = make_float2(xB, xB);
+    const int ra = TBL + ia * TS, rb = TBL + ib * TS;
+#pragma unroll
+    for (int j = 0; j < H / 2; j += 2) {
+        const float4 aA = W.ld4(ra + 2 * j), bA = W.ld4(ra + H + 2 * j);
+        const float4 aB = W.ld4(rb + 2 * j), bB = W.ld4(rb + H + 2 * j);
+        gA[j] = leaky2(fma2_packed(make_float2(aA.x, aA.y), xa, make_float2(bA.x, bA.y)));
+        gA[j + 1] = leaky2(fma2_packed(make_float2(aA.z, aA.w), xa, make_float2(bA.z, bA.w)));
+        gB[j] = leaky2(fma2_packed(make_float2(aB.x, aB.y), xb, make_float2(bB.x, bB.y)));
+        gB[j + 1] = leaky2(fma2_packed(make_float2(aB.z, aB.w), xb, make_float2(bB.z, bB.w)));
+    }
+    op_dense<H, H / 2>(W, L2, L2 + H * H, gA, gB, hA, hB);  // layer 2
 #pragma unroll
     for (int j = 0; j < H / 2; ++j) {
         hA[j] = leaky2(hA[j]);
         hB[j] = leaky2(hB[j]);
-    }
-    op_dense<H, H / 2>(W, l2, l2 + H * H, hA, hB, gA, gB);
-#pragma unroll
-    for (int j = 0; j < H / 2; ++j) {
-        hA[j] = leaky2(gA[j]);
-        hB[j] = leaky2(gB[j]);
     }
 }
 
@@ -214,7 +226,7 @@ __device__ __forceinline__ void op_hidden(const WT W, float xA, float xB, float2
 template <int H, class WT>
 __device__ __forceinline__ void op_last1(const WT W, const float2 (&hA)[H / 2], const float2 (&hB)[H / 2],
                                          float &oA, float &oB) {
-    const int wo = 2 * H + 2 * (H * H + H);
+    const int wo = pl_hidden_slots(H);
     float2 accA = make_float2(0.f, 0.f), accB = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < H / 2; i += 2) {
@@ -251,7 +263,7 @@ __device__ __forceinline__ void spline_half(const float *smem, int slot, const m
             const auto Wa = WSel<VARIANT>::make(smem, slot);
             float2 hA[H / 2], hB[H / 2];
             op_hidden<H>(Wa, cond.x, cond.y, hA, hB);
-            const int wo = 2 * H + 2 * (H * H + H);
+            const int wo = pl_hidden_slots(H);
             op_dense<H, NP2>(Wa, wo, wo + H * 2 * NP2, hA, hB, rA, rB);
         }
 #pragma unroll 1
@@ -306,9 +318,67 @@ __device__ __forceinline__ float2 affine_net(const float *smem, int slot, float2
     }
 }
 
-// stage one net from the parameter blob into shared memory in the variant's layout
+// variant 2: piecewise-linear table of layers 0 + 1, transposed layer 2, last layer (see pl_hidden_slots).  Called by every
+// thread of the CTA (block barriers inside); dst may be shared or global memory.
+template <int H>
+__device__ __forceinline__ void stage_net_pl(const float *__restrict__ src, float *dst, int n_out) {
+    constexpr int TS = pl_stride(H), TBL = H, L2 = H + (H + 1) * TS, B2 = L2 + H * H, LAST = B2 + H;
+    // blob: w0[H] b0[H] | W1[H][H] b1[H] | W2[H][H] b2[H] | W3[n_out][H] b3[n_out]
+    const float *w0 = src, *b0 = src + H, *W1 = src + 2 * H, *b1 = W1 + H * H, *W2 = b1 + H, *b2 = W2 + H * H, *W3 = b2 + H,
+                *b3 = W3 + n_out * H;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = tid; j < H; j += nt) {  // breakpoint j goes to its rank (ties by index); w0 = 0: no breakpoint (+inf, last)
+        const float tj = w0[j] != 0.f ? -b0[j] / w0[j] : INFINITY;
+        int rank = 0;
+        for (int k = 0; k < H; ++k) {
+            const float tk = w0[k] != 0.f ? -b0[k] / w0[k] : INFINITY;
+            rank += (tk < tj || (tk == tj && k < j)) ? 1 : 0;
+        }
+        dst[rank] = tj;
+    }
+    __syncthreads();
+    for (int i = tid; i <= H; i += nt) {  // interval i lies between sorted breakpoints i - 1 and i
+        const float lo = i > 0 ? dst[i - 1] : -INFINITY, hi = i < H ? dst[i] : INFINITY;
+        float c = 0.f;  // a point inside the interval: fixes the sign of every first-layer pre-activation on it
+        if (isfinite(lo) && isfinite(hi)) c = 0.5f * lo + 0.5f * hi;
+        else if (isfinite(hi)) c = hi - 1.f - fabsf(hi);
+        else if (isfinite(lo)) c = lo + 1.f + fabsf(lo);
+        float *row = dst + TBL + i * TS;
+        for (int k = 0; k < H; ++k) {
+            float A = 0.f, B = b1[k];
+            for (int j = 0; j < H; ++j) {
+                const float slope = fmaf(w0[j], c, b0[j]) > 0.f ? 1.f : 0.2f;  // LeakyReLU(0.2), mlp.py:9
+                const float w = W1[k * H + j] * slope;
+                A = fmaf(w, w0[j], A);
+                B = fmaf(w, b0[j], B);
+            }
+            row[k] = A, row[H + k] = B;
+        }
+        for (int k = 2 * H; k < TS; ++k) row[k] = 0.f;
+    }
+    for (int e = tid; e < H * H; e += nt) dst[L2 + (e % H) * H + e / H] = W2[e];  // [in][out]
+    for (int e = tid; e < H; e += nt) dst[B2 + e] = b2[e];
+    if (n_out == 1) {  // w3[H] b3[4]
+        for (int e = tid; e < H; e += nt) dst[LAST + e] = W3[e];
+        for (int e = tid; e < 4; e += nt) dst[LAST + H + e] = e == 0 ? b3[0] : 0.f;
+    } else {  // Wt3[in][NOP] b3[NOP], padding lanes zero
+        const int nop = round4(n_out);
+        for (int e = tid; e < H * nop; e += nt) {
+            const int i = e / nop, o = e % nop;
+            dst[LAST + e] = o < n_out ? W3[o * H + i] : 0.f;
+        }
+        for (int e = tid; e < nop; e += nt) dst[LAST + H * nop + e] = e < n_out ? b3[e] : 0.f;
+    }
+    __syncthreads();
+}
+
+// stage one net from the parameter blob into shared memory in the variant's layout (variants 0, 1: the blob's own layout)
 template <int H, int VARIANT>
 __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *dst, int n_out) {
+    if constexpr (VARIANT >= 2) {
+        stage_net_pl<H>(src, dst, n_out);
+        return;
+    }
     const int hidden = 2 * H + 2 * (H * H + H);
     const int n = hidden + n_out * H + n_out;
     // eight independent loads in flight per thread: with one load per trip the copy runs at one L2 latency per
@@ -323,18 +393,7 @@ __device__ __forceinline__ void stage_net(const float *__restrict__ src, float *
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * blockDim.x;
-            if (e >= n) continue;
-            int d = e;
-            if constexpr (VARIANT >= 2) {
-                if (e >= 2 * H && e < hidden) {  // the two H x H layers: transpose weight blocks
-                    const int r = (e - 2 * H) % (H * H + H), base = e - r;
-                    if (r < H * H) d = base + (r % H) * H + (r / H);
-                } else if (e >= hidden && n_out > 1) {
-                    const int nop = round4(n_out), r = e - hidden;
-                    d = r < n_out * H ? hidden + (r % H) * nop + (r / H) : hidden + H * nop + (r - n_out * H);
-                }
-            }
-            dst[d] = w8[u];
+            if (e < n) dst[e] = w8[u];
         }
     }
 }
