@@ -578,15 +578,33 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
-// LeakyReLU(0.2) (mlp.py:9) of 16 pre-activations -> 8 columns of packed fp16 hi, 8 columns of packed fp16 lo
-__device__ __forceinline__ void act_split16_h(const float (&pre)[16], uint32_t (&r)[16]) {
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): the kernel is bound by instruction issue, one instruction per pair
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+// LeakyReLU(0.2) (mlp.py:9) of 16 pre-activations (8 pairs) -> 8 columns of packed fp16 hi, 8 columns of packed fp16 lo
+__device__ __forceinline__ void act_split16_h(const float2 (&pre)[8], uint32_t (&r)[16]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float a0 = fmaxf(pre[2 * j], 0.2f * pre[2 * j]), a1 = fmaxf(pre[2 * j + 1], 0.2f * pre[2 * j + 1]);
-        const uint32_t h = pack_h2(a0, a1);
-        const float2 hf = unpack_h2(h);
+        const float2 s = f2_mul(pre[j], make_float2(0.2f, 0.2f));
+        const float2 a = make_float2(fmaxf(pre[j].x, s.x), fmaxf(pre[j].y, s.y));
+        const uint32_t h = pack_h2(a.x, a.y);
+        const float2 lo = f2_fma(unpack_h2(h), make_float2(-1.f, -1.f), a);  // a - hi, exact
         r[j] = h;
-        r[8 + j] = pack_h2(a0 - hf.x, a1 - hf.y);
+        r[8 + j] = pack_h2(lo.x, lo.y);
     }
 }
 // exact-fp32 re-evaluation of one point's conditioner (activations outside the fp16 range): plain loops over the
@@ -731,12 +749,13 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
                             iv += (c > t4.x) + (c > t4.y) + (c > t4.z) + (c > t4.w);
                         }
                         const float4 *row = reinterpret_cast<const float4 *>(vec + VEC16_TBL + iv * TBL_STRIDE);
-                        float pre[16];
+                        float2 pre[8];
+                        const float2 cc = make_float2(c, c);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 a4 = row[j], b4 = row[4 + j];
-                            pre[4 * j] = fmaf(a4.x, c, b4.x), pre[4 * j + 1] = fmaf(a4.y, c, b4.y);
-                            pre[4 * j + 2] = fmaf(a4.z, c, b4.z), pre[4 * j + 3] = fmaf(a4.w, c, b4.w);
+                            pre[2 * j] = f2_fma(make_float2(a4.x, a4.y), cc, make_float2(b4.x, b4.y));
+                            pre[2 * j + 1] = f2_fma(make_float2(a4.z, a4.w), cc, make_float2(b4.z, b4.w));
                         }
                         act_split16_h(pre, r);
                     }
@@ -752,12 +771,12 @@ __global__ void __launch_bounds__(128 * G, 1) flow_tc16_kernel(const __grid_cons
                             for (int j = 0; j < 16; ++j) t[j] = r[j];
                         }
                         const float4 *bb = reinterpret_cast<const float4 *>(vec + VEC16_B2);
-                        float pre[16];
+                        float2 pre[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 b = bb[j];
-                            pre[4 * j] = __uint_as_float(t[4 * j]) + b.x, pre[4 * j + 1] = __uint_as_float(t[4 * j + 1]) + b.y;
-                            pre[4 * j + 2] = __uint_as_float(t[4 * j + 2]) + b.z, pre[4 * j + 3] = __uint_as_float(t[4 * j + 3]) + b.w;
+                            pre[2 * j] = f2_add(make_float2(__uint_as_float(t[4 * j]), __uint_as_float(t[4 * j + 1])), make_float2(b.x, b.y));
+                            pre[2 * j + 1] = f2_add(make_float2(__uint_as_float(t[4 * j + 2]), __uint_as_float(t[4 * j + 3])), make_float2(b.z, b.w));
                         }
                         act_split16_h(pre, r);
                         publish(r, tiles + W16L_BYTES, IDESC16_O);  // output layer
