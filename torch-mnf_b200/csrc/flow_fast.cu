@@ -18,6 +18,12 @@ int launch_flow_tc(const mnf_flow_op *ops, int n_ops, const float *params, const
                    float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *workspace,
                    const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
 
+int launch_flow_pl(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
+                   float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *workspace,
+                   const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
+int64_t flow_pl_image_floats(const mnf_flow_op *ops, int n_ops, int dim);
+int flow_pl_build(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream);
+
 int launch_flow_lanes(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
                       float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, cudaStream_t stream, bool plan_only,
                       bool forced);
@@ -171,6 +177,8 @@ static int launch_affine_stream(const FlowProgram &prog, const float *params, co
 // has no such form.  Small-batch calls spend most of their kernel time re-laying the nets out in every CTA; with the
 // image (built once per parameter change) the prologue is a plain vector copy.
 int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim) {
+    // programs with a piecewise-linear form (flow_pl.cu) stage their conditioner TABLES; the image below is for the rest
+    if (const int64_t pl = flow_pl_image_floats(ops, n_ops, dim)) return pl;
     FastPlan p = plan_fast(ops, n_ops, dim, 2);
     bool has_net = false;
     for (int k = 0; k < n_ops; ++k) has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
@@ -179,6 +187,7 @@ int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim) {
 }
 
 int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream) {
+    if (flow_pl_image_floats(ops, n_ops, dim) > 0) return flow_pl_build(ops, n_ops, params, dim, image, stream);
     FastPlan p = plan_fast(ops, n_ops, dim, 2);
     MNF_REQUIRE(p.ok && flow_stage_size(ops, n_ops, dim) > 0, MNF_E_SHAPE, "program has no staged form");
     MNF_REQUIRE(params && image && ((uintptr_t)image % 16) == 0, MNF_E_ARG, "NULL or misaligned pointer");
@@ -203,6 +212,15 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
         has_net |= ops[k].type == MNF_OP_NSF_CL || ops[k].type == MNF_OP_AFFINE_HALF;
     }
     const bool want_gather = gather && (gather->n_peers > 0 || gather->multicast_ptr);
+    // variant 6 (default wherever it applies): every conditioner as a piecewise-linear table of its scalar input
+    // (flow_pl.cu), one launch for the whole stack after the table builder; any hidden widths up to 64, K in {5, 8}.
+    // A staged image (bit 2) of such a program IS its tables, so a staged call always lands here.
+    if ((variant == 6 || variant < 0 || (inverse & 4)) && (!want_gather || (inverse & 2)) && (workspace || plan_only)) {
+        const int rc = launch_flow_pl(ops, n_ops, params, x, y, log_det, base_lp, inter, n_rows, dim, inverse & 7, workspace, gather,
+                                      stream, plan_only);
+        if (rc != 1) return rc;
+    }
+    if (variant == 6) variant = -1;
     // variant 4: conditioners on the tensor cores (flow_tc.cu), one launch for the whole stack, weights in the caller's
     // workspace.  Spline stacks of its shape class take it by default from kCbankMinRows rows up.
     if (!(inverse & 4) && (variant == 4 || (variant < 0 && kTcDefault && has_spline && (plan_only || n_rows >= kCbankMinRows))) &&

@@ -15,6 +15,8 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
                      int mode, float *workspace, const mnf_gather_out *gather, cudaStream_t stream, bool plan_only);
 int64_t flow_stage_size(const mnf_flow_op *ops, int n_ops, int dim);
 int64_t flow_tc_workspace_floats();
+int64_t flow_pl_workspace_floats(int n_ops);
+int64_t flow_pl_image_floats(const mnf_flow_op *ops, int n_ops, int dim);
 int flow_stage_image(const mnf_flow_op *ops, int n_ops, const float *params, int dim, float *image, cudaStream_t stream);
 int launch_made_fast(const mnf_flow_op *ops, int n_ops, const float *params, const float *x, float *y, float *log_det,
                      float *base_lp, float *inter, int64_t n_rows, int dim, int dir_flags, float *scratch,
@@ -183,7 +185,8 @@ int mnf_flow_handle_log_prob(const mnf_flow_handle *h, const float *x, float *lo
         rc = launch_made_fast(h->ops, h->n_ops, h->params, x, nullptr, nullptr, log_prob, nullptr, n_rows, h->dim, base,
                               n_rows <= h->workspace_rows ? h->workspace : nullptr, st, false);
         if (rc != 1) return rc;
-    } else if (h->staged && n_rows < (1 << 16)) {  // small batches: the pre-staged shared-memory image (variant 2)
+    } else if (h->staged && (n_rows < (1 << 16) || flow_pl_image_floats(h->ops, h->n_ops, h->dim) > 0)) {
+        // the staged conditioner tables (any batch), or for programs without them the pre-staged shared-memory image (small batches)
         rc = launch_flow_fast(h->ops, h->n_ops, h->params, h->n_params, x, nullptr, nullptr, log_prob, nullptr, n_rows, 2,
                               base | 4, -1, const_cast<float *>(h->staged), nullptr, st, false);
         if (rc != 1) return rc;
@@ -212,11 +215,13 @@ int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *pa
 }
 
 int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim) {
-    (void)n_ops;
     if (dim == 64) return n_rows * 64;  // MADE density stack in log-prob mode parks z here between flows
-    // dim 2: the weight image of the tensor-core kernel (every other dim-2 kernel needs none)
+    // dim 2: the conditioner tables of the piecewise-linear kernel or the weight image of the tensor-core kernel, whichever
+    // is larger (every other dim-2 kernel needs none)
     (void)n_rows;
-    return dim == 2 ? flow_tc_workspace_floats() : 0;
+    if (dim != 2) return 0;
+    const int64_t tc = flow_tc_workspace_floats(), pl = flow_pl_workspace_floats(n_ops);
+    return tc > pl ? tc : pl;
 }
 
 int mnf_glow_assemble(const float *P, const float *L, const float *U, const float *S, float *out, int dim,

@@ -282,7 +282,7 @@ class FlowProgram:
 
     def _staged_image(self, lib, n_rows, dim, kernel):
         """Pre-staged net image for small dim-2 batches (mnf_flow_stack_stage), cached until a parameter changes."""
-        if dim != 2 or n_rows > self.STAGED_MAX_ROWS or kernel not in (None, 2) or not 0 < self._n_ops <= _lib.MAX_OPS:
+        if dim != 2 or n_rows > self.STAGED_MAX_ROWS or kernel is not None or not 0 < self._n_ops <= _lib.MAX_OPS:
             return None
         img = self._staged.get(dim)
         if img is None:
