@@ -459,7 +459,13 @@ def run_ours(args):
                      "frac": achieved / hbm_peak, "traffic": traffic_for("cfg2", n),
                      "kernel": k_sites,
                      "kernel_ms": k_ms, "bytes_per_point": BYTES_PER_POINT, "peak_source": peak_src,
-                     "note": ("one launch per step (flow_tc16_kernel): conditioner MLPs on tcgen05 as fp16-split 3-term products, "
+                     "note": ("table builder + ONE launch per step (flow_pl_kernel): every conditioner MLP is a piecewise-linear function of "
+                              "its scalar input, evaluated as a binary search over its breakpoints in shared memory and one FMA per "
+                              "output (tables rebuilt from the weights in fp64 inside every step); DRAM traffic is the algorithmic "
+                              "12 B/pt. The kernel is instruction-issue / MUFU bound on the spline arithmetic, not HBM bound: "
+                              "profiles/r02_flow_pl.md"
+                              if any("flow_pl" in k for k in k_sites) else
+                              "one launch per step (flow_tc16_kernel): conditioner MLPs on tcgen05 as fp16-split 3-term products, "
                               "weights resident in shared memory, points in registers; DRAM traffic is the algorithmic 12 B/pt. "
                               "The kernel is instruction-issue bound (spline arithmetic + operand splitting), not HBM bound: "
                               "profiles/r02_flow_tc.md"
@@ -469,7 +475,10 @@ def run_ours(args):
                               "bound (DESIGN.md): see fma_pipe")},
         "fma_pipe": {"mlp_tflops": mlp_tflops, "fp32_peak_tflops_at_sampled_clock": fp32_peak,
                      "frac_mlp_only": mlp_tflops / fp32_peak, "fma_per_point_mlp": MLP_FMA_PER_POINT,
-                     "note": ("conditioner-MLP multiply-adds per second against the fp32 FMA peak, for comparison with the FFMA2 "
+                     "note": ("the conditioner MLPs' NOMINAL multiply-adds per second (layer-by-layer count) against the fp32 FMA peak; "
+                              "the table kernel does not execute them (one FMA per output per point), so this can exceed 1"
+                              if any("flow_pl" in k for k in k_sites) else
+                              "conditioner-MLP multiply-adds per second against the fp32 FMA peak, for comparison with the FFMA2 "
                               "kernel of round 1 (this kernel runs them on the tensor pipe)"
                               if any("flow_tc" in k for k in k_sites) else
                               "conditioner-MLP FMAs only; spline arithmetic shares the same pipe")},

@@ -1,0 +1,157 @@
+"""GPU parity of the piecewise-linear table kernel (csrc/flow_pl.cu, dim-2 kernel variant 6 and the library default for
+AffineHalfFlow / NSF_CL stacks): golden vectors of the reference, the CPU oracle on seeded batches, and the exact-fp32
+interpreter on the cases that exercise the kernel's own machinery (tables staged per parameter version or built per call,
+tables larger than shared memory, tables that overflow and fall back to the layer-by-layer evaluation, inputs far outside
+the breakpoints, conditioner shapes no other fast kernel covers)."""
+
+import pytest
+import torch
+
+from tests.helpers import golden_sd, golden_spec, load_flow_model, load_golden, random_flow_sd, t
+from tests.test_flows_gpu import ORACLE_CASES, close, close_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+PL = 6  # MNF_RUN_VARIANT(6)
+
+
+def _launched(fn):
+    from torch_mnf import _lib
+
+    _lib.launch_stats(reset=True)
+    fn()
+    torch.cuda.synchronize()
+    return _lib.launch_stats()
+
+
+@pytest.mark.parametrize("name", ["rnvp9_moons", "nsfcl3_stack"])
+def test_pl_vs_golden(name):
+    g = load_golden(name)
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    x = t(g, "inv/x").cuda()
+    sites = _launched(lambda: prog.run(x, inverse=True, kernel=PL))
+    assert "flow_pl_kernel" in sites and "flow_pl_build_kernel" in sites, sites
+    y, ld, inter, lp = prog.run(x, inverse=True, want_inter=True, want_base_lp=True, kernel=PL)
+    close(y, t(g, "inv/z"), "z", atol_scale=2e-5)
+    close(ld, t(g, "inv/ld"), "log_det", atol_scale=4e-5)
+    close(lp, t(g, "inv/base_log_prob"), "base_log_prob", atol_scale=4e-5)
+    close(inter[(len(specs) + 1) // 2 - 1], t(g, "inv/z_mid"), "z_mid")
+    close_vs_oracle((y, ld), sd, specs, t(g, "inv/x"), True, f"{name} pl")
+    z = t(g, "fwd/z").cuda()
+    y, ld, _, _ = prog.run(z, inverse=False, kernel=PL)
+    close(y, t(g, "fwd/x"), "x")
+    close(ld, t(g, "fwd/ld"), "log_det fwd", atol_scale=4e-5)
+    close_vs_oracle((y, ld), sd, specs, t(g, "fwd/z"), False, f"{name} pl fwd")
+
+
+def test_default_path_is_the_table_kernel():
+    """Module calls of the BASELINE dim-2 stacks: staged tables below 65536 rows (one launch), tables built per call above."""
+    for name, rows, want in (("cfg1_shape", 4096, {"flow_pl_kernel": 1}), ("cfg2_shape", 1 << 16, {"flow_pl_build_kernel": 1, "flow_pl_kernel": 1})):
+        specs = ORACLE_CASES[name]
+        model = load_flow_model(specs, random_flow_sd(specs, seed=1, scale=0.4), return_intermediates=False)
+        x = torch.randn(rows, 2, device="cuda")
+        model.log_prob(x)  # first call stages
+        assert _launched(lambda: model.log_prob(x)) == want
+
+
+@pytest.mark.parametrize("name,scale", [("cfg2_shape", 0.6), ("cfg1_shape", 0.3), ("nsf_default", 0.6)])
+def test_pl_vs_oracle_seeded(name, scale):
+    specs = ORACLE_CASES[name]
+    sd = random_flow_sd(specs, seed=7, scale=scale)
+    model = load_flow_model(specs, sd)
+    g = torch.Generator().manual_seed(13)
+    x = 1.5 * torch.randn(30001, 2, generator=g)
+    x[0, :], x[1, :], x[2, :] = 3.0, -3.0, 0.0
+    for inverse in (True, False):
+        y, ld, _, _ = model._program().run(x.cuda(), inverse=inverse, kernel=PL)
+        close_vs_oracle((y, ld), sd, specs, x, inverse, f"{name} pl inverse={inverse}")
+
+
+SHAPES = {
+    # conditioner shapes outside the (hidden, bins) grid of the register-resident kernels: any depth 2..6, any widths <= 64
+    "affine_32_16": [{"type": "AffineHalfFlow", "dim": 2, "parity": bool(i % 2), "scale": True, "shift": True, "h_sizes": [32, 16]} for i in range(4)],
+    "affine_one_hidden": [{"type": "AffineHalfFlow", "dim": 2, "parity": bool(i % 2), "scale": True, "shift": True, "h_sizes": [40]} for i in range(3)],
+    "affine_scale_only": [{"type": "AffineHalfFlow", "dim": 2, "parity": False, "scale": True, "shift": False, "h_sizes": [24, 24, 24]},
+                          {"type": "AffineHalfFlow", "dim": 2, "parity": True, "scale": False, "shift": True, "h_sizes": [24, 24, 24]}],
+    "nsf_h20": [{"type": "Glow", "dim": 2}, {"type": "NSF_CL", "dim": 2, "K": 8, "B": 2.5, "n_h": 20}] * 2,
+    "mixed": [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True},
+              {"type": "AffineHalfFlow", "dim": 2, "parity": True, "scale": True, "shift": True, "h_sizes": [16, 16, 16]},
+              {"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}, {"type": "Glow", "dim": 2},
+              {"type": "AffineHalfFlow", "dim": 2, "parity": False, "scale": True, "shift": True, "h_sizes": [16, 16, 16]}],
+    # tables that do not fit: 6 tables of ~200 pieces x 208 B > 227 KB of shared memory -> read from the image in global memory
+    "nsf_h64_x3": [{"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 64}] * 3,
+    # an (s, t) pair of 1-64-64-64-64-64-1 nets has ~600 breakpoints > 511: flagged by the builder, evaluated layer by layer
+    "affine_overflow": [{"type": "AffineHalfFlow", "dim": 2, "parity": bool(i % 2), "scale": True, "shift": True, "h_sizes": [64] * 5} for i in range(2)]
+                       + [{"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}],
+}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+@pytest.mark.parametrize("rows", [777, 70001])
+def test_pl_shapes_match_interpreter(name, rows):
+    specs = SHAPES[name]
+    model = load_flow_model(specs, random_flow_sd(specs, seed=5, scale=0.6 if "affine" not in name else 0.3))
+    prog = model._program()
+    x = 1.3 * torch.randn(rows, 2, generator=torch.Generator().manual_seed(rows)).cuda()
+    for inverse in (True, False):
+        sites = _launched(lambda: prog.run(x, inverse, kernel=PL))
+        assert "flow_pl_kernel" in sites, sites
+        y, ld, inter, lp = prog.run(x, inverse, want_inter=True, want_base_lp=True, kernel=PL)
+        yg, ldg, interg, lpg = prog.run(x, inverse, want_inter=True, want_base_lp=True, kernel="generic")
+        torch.testing.assert_close(y, yg, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(inter, interg, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ld, ldg, rtol=1e-4, atol=3e-4)
+        torch.testing.assert_close(lp, lpg, rtol=1e-4, atol=3e-4)
+
+
+def test_pl_staged_equals_built_per_call():
+    """The same points through the staged tables (module call, < 65536 rows) and through tables built inside the call."""
+    specs = ORACLE_CASES["cfg2_shape"]
+    model = load_flow_model(specs, random_flow_sd(specs, seed=2, scale=0.6), return_intermediates=False)
+    x = 1.5 * torch.randn(1 << 17, 2, device="cuda")
+    big = model.log_prob(x)
+    small = torch.cat([model.log_prob(x[i:i + 30000].contiguous()) for i in range(0, x.size(0), 30000)])
+    assert torch.equal(big, small)
+    bound = model.log_prob_fn(1 << 17)
+    assert torch.equal(bound(x), big)
+
+
+def test_pl_tracks_parameter_updates():
+    """The staged tables are rebuilt when a parameter changes (cache keyed on every tensor's version)."""
+    specs = ORACLE_CASES["cfg1_shape"]
+    model = load_flow_model(specs, random_flow_sd(specs, seed=2, scale=0.3), return_intermediates=False)
+    x = torch.randn(2048, 2, device="cuda")
+    a = model.log_prob(x)
+    with torch.no_grad():
+        model.flows[4].s_net[2].weight.mul_(1.5)
+    b = model.log_prob(x)
+    _, _, _, ref = model._program().run(x, True, log_prob_only=True, kernel="generic")
+    assert not torch.equal(a, b)
+    torch.testing.assert_close(b, ref, rtol=1e-4, atol=3e-4)
+
+
+def test_pl_far_inputs_and_non_finite():
+    """Coordinates far beyond every breakpoint use the outermost pieces (exact: the net is linear there); NaN / inf inputs
+    give what the layer-by-layer evaluation gives."""
+    specs = ORACLE_CASES["cfg1_shape"]
+    sd = random_flow_sd(specs, seed=9, scale=0.05)  # small weights: exp(s) stays finite at |c| ~ 1e4
+    model = load_flow_model(specs, sd)
+    x = torch.randn(4096, 2, generator=torch.Generator().manual_seed(3))
+    x[:1024] *= 1e4
+    x[5, 0], x[6, 1], x[7, 0] = float("nan"), float("inf"), float("-inf")
+    prog = model._program()
+    for inverse in (True, False):
+        y, ld, _, _ = prog.run(x.cuda(), inverse, kernel=PL)
+        yg, ldg, _, _ = prog.run(x.cuda(), inverse, kernel="generic")
+        fin = torch.isfinite(yg).all(dim=1) & torch.isfinite(ldg)
+        assert torch.equal(torch.isfinite(y).all(dim=1) & torch.isfinite(ld), fin)
+        torch.testing.assert_close(y[fin], yg[fin], rtol=2e-5, atol=1e-5)
+        torch.testing.assert_close(ld[fin], ldg[fin], rtol=2e-5, atol=1e-4)
+    specs = ORACLE_CASES["cfg2_shape"]
+    sd = random_flow_sd(specs, seed=9, scale=0.6)
+    model = load_flow_model(specs, sd)
+    x = 1e6 * torch.randn(4096, 2, generator=torch.Generator().manual_seed(4))  # spline tails: identity, log-det 0
+    y, ld, _, _ = model._program().run(x.cuda(), True, kernel=PL)
+    close_vs_oracle((y, ld), sd, specs, x, True, "cfg2 far inputs")

@@ -89,7 +89,7 @@ def test_stack_vs_golden(name, kernel):
 
 
 @pytest.mark.parametrize("name", ["rnvp9_moons", "nsfcl3_stack"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 5, 6])
 def test_dim2_kernel_variants(name, variant):
     g = load_golden(name)
     sd, specs = golden_sd(g), golden_spec(g)

@@ -43,7 +43,7 @@ def _fractions(got, ref, floor):
 def _kernels_for(prog, dim):
     ks = [("default", None), ("generic", "generic")]
     if dim == 2 and prog.plan(torch.device("cuda"), 2) == 1:
-        ks += [(f"dim2_variant{v}", v) for v in (2, 3)]
+        ks += [(f"dim2_variant{v}", v) for v in (2, 4, 6)]  # shared-memory FFMA2, tensor-core (its shape class only), table kernel
     return ks
 
 

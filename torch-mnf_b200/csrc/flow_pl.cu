@@ -13,13 +13,13 @@
 //                          piece's origin of every output.  Exact up to fp64 rounding -- closer to the real-number net than
 //                          an fp32 evaluation of its layers.
 //   flow_pl_kernel<K>      one thread per point, the whole stack in one launch: a conditioner is a branch-free binary
-//                          search over <= 255 sorted breakpoints in shared memory and one FMA per output
+//                          search over <= 511 sorted breakpoints in shared memory and one FMA per output
 //                          (out = V_i + A_i (c - origin_i)); the spline (flow_math.cuh) then runs on the raw outputs, and only
 //                          the two knot derivatives of the bin the point falls into are ever formed.
 //
 // Per point and conditioner: ~60 instructions instead of 5 376 multiply-adds (or three MMA round trips).  No tensor core
 // and no FMA chain is left to feed: what remains is the spline arithmetic and 12 B/pt of HBM traffic.
-// A conditioner with more than 255 breakpoints (never seen; the bound is pieces x width per layer) is flagged by the
+// A table with more than 511 breakpoints (e.g. a pair of 1-64-64-64-64-64-1 nets; the bound is pieces x width per layer) is flagged by the
 // builder and evaluated layer by layer in fp32 by the threads that need it.  The library owns no device memory: the
 // tables live in the caller's workspace (built per call) or in the image of mnf_flow_stack_stage (built per parameter
 // version).
@@ -30,8 +30,8 @@ namespace mnf {
 namespace fpl {
 using tc::smem_u32; using tc::mbar_init; using tc::mbar_arrive; using tc::mbar_wait; using tc::bulk_load;
 
-constexpr int PMAX = 255;       // breakpoints per table
-constexpr int BP_FLOATS = 256;  // sorted breakpoints, padded with +inf (search array)
+constexpr int PMAX = 511;       // breakpoints per table
+constexpr int BP_FLOATS = 512;  // sorted breakpoints, padded with +inf (search array)
 constexpr int MAX_GROUPS = 2 * MNF_MAX_OPS;
 constexpr int HDR_INTS = 4;     // per table: breakpoints, overflow flag, 2 spare
 constexpr int HDR_FLOATS = MAX_GROUPS * HDR_INTS;
