@@ -250,46 +250,111 @@ __device__ __noinline__ float mlp_fp32_scalar(const float *__restrict__ net, int
     return out[0];
 }
 
-// piece of c: count of breakpoints below it, branch-free over the +inf padded array
-__device__ __forceinline__ int find_piece(const float *tb, float c) {
-    int pos = 0;
-#pragma unroll
-    for (int s = (PMAX + 1) / 2; s >= 1; s >>= 1) pos += (c > tb[pos + s - 1]) ? s : 0;
-    return pos;
+template <int S>
+__device__ __forceinline__ void search_steps(uint32_t &a, float c) {
+    float t;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(t) : "r"(a), "n"(4 * (S - 1)));
+    if (c > t) a += 4u * S;
+    if constexpr (S > 1) search_steps<S / 2>(a, c);
 }
 
-// The rational-quadratic spline of flow_math.cuh::rq_spline (FAST flavour, same formulas and constants) on the 2K width /
-// height outputs; the raw derivatives of the two knots around the point's bin are fetched through `deriv(j)` once the bin
-// is known (the conditioner's other K - 3 derivative outputs are never formed).
+// piece of c: count of breakpoints below it, branch-free over the +inf padded array.  SM: the table is in shared memory and
+// the search walks a byte address (load, compare, predicated add per step).
+template <bool SM>
+__device__ __forceinline__ int find_piece(const float *tb, float c) {
+    if constexpr (SM) {
+        const uint32_t base = smem_u32(tb);
+        uint32_t a = base;
+        search_steps<(PMAX + 1) / 2>(a, c);
+        return (int)((a - base) >> 2);
+    } else {
+        int pos = 0;
+#pragma unroll
+        for (int s = (PMAX + 1) / 2; s >= 1; s >>= 1) pos += (c > tb[pos + s - 1]) ? s : 0;
+        return pos;
+    }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Knots of one spline axis in units of B: t[0] = -1, t[K] = 1.  The formulas of flow_math.cuh::spline_knots (both
+// softmaxes of spline_flow.py:253-255 and :95, floor :96-97, cumsum :99, pinned ends :100-101) with the cumulative sum
+// taken over the second softmax's terms while they are summed: x_{k+1} / B = -1 + 2 (k + 1) min_bin + (2 span / sum f) * (f_0 + .. + f_k),
+// one FFMA per knot.
+template <int K>
+__device__ __forceinline__ void unit_knots(const float *raw, float twoB, float *t) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float span = 1.f - kMinBin * (float)K;
+    float m = raw[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) m = fmaxf(m, raw[k]);
+    const float mneg = -m * LOG2E;
+    float e[K], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        e[k] = ex2_approx(fmaf(raw[k], LOG2E, mneg));
+        sum += e[k];
+    }
+    const float sc = twoB * frcp<true>(sum) * LOG2E;  // first softmax scaled by 2B, in log2 units
+    const float off = twoB > 80.f ? -sc : 0.f;        // arguments of the second softmax lie in [0, 2B]
+    float pre = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        pre += ex2_approx(fmaf(e[k], sc, off));
+        e[k] = pre;
+    }
+    const float c1 = 2.f * span * frcp<true>(pre);
+    t[0] = -1.f;
+#pragma unroll
+    for (int k = 0; k + 1 < K; ++k) t[k + 1] = fmaf(e[k], c1, -1.f + 2.f * (float)(k + 1) * kMinBin);
+    t[K] = 1.f;
+}
+
+// The rational-quadratic spline of flow_math.cuh::rq_spline (FAST flavour) for a point already known to lie in [-B, B],
+// evaluated in units of B (the bin ratios, the knot derivatives and the log-det do not depend on the unit).  The raw
+// derivatives of the two knots around the point's bin are fetched through `deriv(j)` once the bin is known -- the
+// conditioner's other K - 3 derivative outputs are never formed.
 template <int K, class DerivFn>
-__device__ __forceinline__ void rq_spline_lazy(const float *raw, float B, float edge_deriv, bool inverse, float &v, float &ld,
+__device__ __forceinline__ void rq_spline_lazy(const float *raw, float B, float inv_B, float edge_deriv, bool inverse, float &v, float &ld,
                                                DerivFn deriv) {
     float cw[K + 1], ch[K + 1];
-    spline_knots<K, true>(raw, K, B, cw);
-    spline_knots<K, true>(raw + K, K, B, ch);
-    const float *sk = inverse ? ch : cw;  // bin search (spline_flow.py:22-24,115-118)
-    int idx = -1;
+    unit_knots<K>(raw, 2.f * B, cw);
+    unit_knots<K>(raw + K, 2.f * B, ch);
+    const float u = v * inv_B;
+    const float *sk = inverse ? ch : cw;
+    // bin = number of interior knots <= u (spline_flow.py:22-24,115-118; u lies inside [t_0, t_K], so the count needs no
+    // clamp); the knots of both axes around it are picked with the same predicates
+    int idx = 0;
+    float xk = cw[0], xk1 = cw[1], yk = ch[0], yk1 = ch[1];
 #pragma unroll
-    for (int k = 0; k < K; ++k) idx += (v >= sk[k]) ? 1 : 0;
-    idx += (v >= sk[K] + 1e-6f) ? 1 : 0;
-    idx = min(max(idx, 0), K - 1);
-    float xk = 0.f, xk1 = 0.f, yk = 0.f, yk1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-        if (k == idx) xk = cw[k], xk1 = cw[k + 1], yk = ch[k], yk1 = ch[k + 1];
+    for (int k = 1; k < K; ++k) {
+        const bool ge = u >= sk[k];
+        idx += ge ? 1 : 0;
+        xk = ge ? cw[k] : xk, xk1 = ge ? cw[k + 1] : xk1;
+        yk = ge ? ch[k] : yk, yk1 = ge ? ch[k + 1] : yk1;
+    }
     const float wk = xk1 - xk, hk = yk1 - yk;  // spline_flow.py:102,113
-    const float dk = (idx > 0) ? knot_derivative<true>(deriv(idx - 1)) : edge_deriv;       // spline_flow.py:256,104; :46-49
+    const float dk = (idx > 0) ? knot_derivative<true>(deriv(idx - 1)) : edge_deriv;  // spline_flow.py:256,104; :46-49
     const float dk1 = (idx < K - 1) ? knot_derivative<true>(deriv(idx)) : edge_deriv;
     const float sk_ = __fdividef(hk, wk);  // spline_flow.py:123
     const float dsum = dk + dk1 - 2.f * sk_;
     if (inverse) {  // spline_flow.py:133-162
-        const float dy = v - yk;
+        const float dy = u - yk;
         const float a = dy * dsum + hk * (sk_ - dk);
         const float b = hk * dk - dy * dsum;
         const float c = -sk_ * dy;
         const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
-        const float root = __fdividef(2.f * c, -b - sqrtf(disc));
-        v = root * wk + xk;
+        const float root = __fdividef(2.f * c, -b - sqrt_approx(disc));
+        v = (root * wk + xk) * B;
         const float tt = root * (1.f - root);
         const float den = sk_ + dsum * tt;
         const float omr = 1.f - root;
@@ -297,14 +362,14 @@ __device__ __forceinline__ void rq_spline_lazy(const float *raw, float B, float 
         const float rd = frcp<true>(den);
         ld -= __logf(num * rd * rd);
     } else {  // spline_flow.py:163-179
-        const float th = __fdividef(v - xk, wk);
+        const float th = __fdividef(u - xk, wk);
         const float tt = th * (1.f - th);
         const float numer = hk * (sk_ * (th * th) + dk * tt);
         const float den = sk_ + dsum * tt;
         const float omt = 1.f - th;
         const float num = (sk_ * sk_) * (dk1 * (th * th) + 2.f * sk_ * tt + dk * (omt * omt));
         const float rd = frcp<true>(den);
-        v = fmaf(numer, rd, yk);
+        v = fmaf(numer, rd, yk) * B;
         ld += __logf(num * rd * rd);
     }
 }
@@ -356,7 +421,7 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
                 if (g < 0) {  // neither net: s = t = 0
                 } else if (!s_over[g]) {
                     const float *tb = table(g);
-                    const float4 *row = reinterpret_cast<const float4 *>(tb + BP_FLOATS) + find_piece(tb, c) * AFF_STRIDE4;
+                    const float4 *row = reinterpret_cast<const float4 *>(tb + BP_FLOATS) + find_piece<SM>(tb, c) * AFF_STRIDE4;
                     const float4 q = row[0];
                     const float d = c - row[1].x;
                     s = fmaf(q.x, d, q.z), t = fmaf(q.y, d, q.w);
@@ -382,7 +447,7 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
                         const int g = p.gl.group_of[k][use_f1 ? 0 : 1];
                         if (!s_over[g]) {
                             const float *tb = table(g);
-                            const float4 *row = reinterpret_cast<const float4 *>(tb + BP_FLOATS) + find_piece(tb, c) * nsf_stride4(K);
+                            const float4 *row = reinterpret_cast<const float4 *>(tb + BP_FLOATS) + find_piece<SM>(tb, c) * nsf_stride4(K);
                             const float d = c - row[nsf_org(K) / 4].x;
                             const float2 dd = make_float2(d, d);
                             float raw[2 * K];
@@ -393,7 +458,7 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
                                 raw[2 * j] = o.x, raw[2 * j + 1] = o.y;
                             }
                             const float2 *dv = reinterpret_cast<const float2 *>(row) + nsf_doff(K) / 2;
-                            rq_spline_lazy<K>(raw, B, op.edge_deriv, inverse != 0, tr, ld, [&](int j) {
+                            rq_spline_lazy<K>(raw, B, 1.f / B, op.edge_deriv, inverse != 0, tr, ld, [&](int j) {
                                 const float2 q = dv[j];
                                 return fmaf(q.x, d, q.y);
                             });
