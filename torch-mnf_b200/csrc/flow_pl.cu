@@ -376,11 +376,84 @@ __device__ __forceinline__ void rq_spline_lazy(const float *raw, float B, float 
 
 constexpr int THREADS = 1024;
 
+// The stack as the point loop walks it (execution order, built once per CTA): runs of AffineConstantFlow / ActNormFlow / Glow
+// are composed into ONE affine map v -> v M + b with a constant log-det (fp64; not when per-flow outputs are requested),
+// the coupling flows carry their constants and table indices -- the loop never touches the descriptors again.
+struct Exec {
+    int type;   // 0 affine map, 1 AffineHalfFlow, 2 NSF_CL
+    int k;      // flow index (parameters of the fp32 fallback)
+    int g0, g1; // tables: AffineHalfFlow g0; NSF_CL g0 = first step's, g1 = second step's
+    int flag;   // AffineHalfFlow: parity; NSF_CL: the first step is f1 (forward direction)
+    int pad[3];
+    float c[8]; // affine: m00 m01 m10 m11 | b0 b1 dld - ; NSF_CL: B 1/B edge_deriv - ; AffineHalfFlow: -
+};
+static_assert(sizeof(Exec) == 64, "two 16-byte rows of ints, two of floats");
+
+__device__ __forceinline__ void build_exec(const Params &p, Exec *ex, int *n_exec, int lane) {
+    const int n = p.prog.n_ops, inverse = p.dir_flags & 1;
+    if (lane < n) {
+        const int k = inverse ? n - 1 - lane : lane;
+        const mnf_flow_op &op = p.prog.ops[k];
+        Exec e{};
+        e.k = k;
+        if (op.type == MNF_OP_AFFINE_CONST) {
+            const double s0 = p.params[op.aux_off], s1 = p.params[op.aux_off + 1];
+            const double t0 = p.params[op.aux_off + 2], t1 = p.params[op.aux_off + 3];
+            if (inverse) {  // (v - t) exp(-s), affine_constant_flow.py:24
+                const double e0 = exp(-s0), e1 = exp(-s1);
+                e.c[0] = (float)e0, e.c[3] = (float)e1, e.c[4] = (float)(-t0 * e0), e.c[5] = (float)(-t1 * e1), e.c[6] = (float)(-(s0 + s1));
+            } else {  // v exp(s) + t, affine_constant_flow.py:19
+                e.c[0] = (float)exp(s0), e.c[3] = (float)exp(s1), e.c[4] = (float)t0, e.c[5] = (float)t1, e.c[6] = (float)(s0 + s1);
+            }
+        } else if (op.type == MNF_OP_GLOW) {  // v @ W (glow.py:28) or v @ W^-1 (glow.py:36)
+            const float *W = p.params + op.aux_off + (inverse ? 4 : 0);
+            e.c[0] = W[0], e.c[1] = W[1], e.c[2] = W[2], e.c[3] = W[3];
+            e.c[6] = inverse ? -p.params[op.aux_off + 8] : p.params[op.aux_off + 8];
+        } else if (op.type == MNF_OP_AFFINE_HALF) {
+            e.type = 1, e.g0 = p.gl.group_of[k][0], e.flag = (op.flags & MNF_FLAG_PARITY) ? 1 : 0;
+        } else {  // forward: f1 then f2 (spline_flow.py:249-266); inverse: f2 then f1 (:268-285)
+            e.type = 2, e.flag = inverse ? 0 : 1;
+            e.g0 = p.gl.group_of[k][inverse ? 1 : 0], e.g1 = p.gl.group_of[k][inverse ? 0 : 1];
+            e.c[0] = op.bound, e.c[1] = 1.f / op.bound, e.c[2] = op.edge_deriv;
+        }
+        ex[lane] = e;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int j = 0;
+        bool open = false;  // ex[j - 1] is an affine map that may still absorb the next one
+        double M[4], b[2], ld;
+        for (int i = 0; i < n; ++i) {
+            const Exec e = ex[i];
+            if (e.type != 0 || p.inter) {
+                ex[j++] = e, open = false;
+                continue;
+            }
+            if (!open) {
+                for (int q = 0; q < 4; ++q) M[q] = e.c[q];
+                b[0] = e.c[4], b[1] = e.c[5], ld = e.c[6];
+                ++j, open = true;
+            } else {  // (v M + b) W + t = v (M W) + (b W + t)
+                const double W0 = e.c[0], W1 = e.c[1], W2 = e.c[2], W3 = e.c[3];
+                const double n00 = M[0] * W0 + M[1] * W2, n01 = M[0] * W1 + M[1] * W3;
+                const double n10 = M[2] * W0 + M[3] * W2, n11 = M[2] * W1 + M[3] * W3;
+                const double nb0 = b[0] * W0 + b[1] * W2 + e.c[4], nb1 = b[0] * W1 + b[1] * W3 + e.c[5];
+                M[0] = n00, M[1] = n01, M[2] = n10, M[3] = n11, b[0] = nb0, b[1] = nb1, ld += e.c[6];
+            }
+            Exec f{};
+            for (int q = 0; q < 4; ++q) f.c[q] = (float)M[q];
+            f.c[4] = (float)b[0], f.c[5] = (float)b[1], f.c[6] = (float)ld;
+            ex[j - 1] = f;
+        }
+        *n_exec = j;
+    }
+}
+
 // SM: every table of the program sits in shared memory (plain LDS); otherwise a table is read through a generic pointer
 // (shared memory if it fitted, the image in global memory if not).
 template <int K, bool SM>
-__device__ __forceinline__ void run_points(const Params &p, const float *smem, const int *s_off, const int *s_over) {
-    const int inverse = p.dir_flags & 1;
+__device__ __forceinline__ void run_points(const Params &p, const float *smem, const int *s_off, const int *s_over, const Exec *ex,
+                                           int n_exec) {
     const bool sum_lp = p.dir_flags & 2;
     auto table = [&](int g) -> const float * {
         if constexpr (SM) return smem + s_off[g];
@@ -396,27 +469,18 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
             v0 = xin.x, v1 = xin.y;
         }
 #pragma unroll 1
-        for (int kk = 0; kk < p.prog.n_ops; ++kk) {
-            const int k = inverse ? p.prog.n_ops - 1 - kk : kk;
-            const mnf_flow_op &op = p.prog.ops[k];
-            if (op.type == MNF_OP_AFFINE_CONST) {
-                const float4 st = *reinterpret_cast<const float4 *>(p.params + op.aux_off);  // s0 s1 t0 t1
-                if (inverse) {  // affine_constant_flow.py:24
-                    v0 = (v0 - st.z) * expf(-st.x), v1 = (v1 - st.w) * expf(-st.y), ld -= st.x + st.y;
-                } else {  // affine_constant_flow.py:19
-                    v0 = v0 * expf(st.x) + st.z, v1 = v1 * expf(st.y) + st.w, ld += st.x + st.y;
-                }
-            } else if (op.type == MNF_OP_GLOW) {
-                const float4 W = *reinterpret_cast<const float4 *>(p.params + op.aux_off + (inverse ? 4 : 0));  // glow.py:28,36: v @ W
-                const float lg = p.params[op.aux_off + 8];
-                const float n0 = fmaf(v1, W.z, v0 * W.x), n1 = fmaf(v1, W.w, v0 * W.y);
-                v0 = n0, v1 = n1;
-                ld += inverse ? -lg : lg;
-            } else if (op.type == MNF_OP_AFFINE_HALF) {
-                const bool parity = op.flags & MNF_FLAG_PARITY;
+        for (int kk = 0; kk < n_exec; ++kk) {
+            const int4 ei = *reinterpret_cast<const int4 *>(&ex[kk]);  // type, k, g0, g1
+            if (ei.x == 0) {
+                const float4 m = *reinterpret_cast<const float4 *>(ex[kk].c), b = *reinterpret_cast<const float4 *>(ex[kk].c + 4);
+                const float n0 = fmaf(v1, m.z, fmaf(v0, m.x, b.x)), n1 = fmaf(v1, m.w, fmaf(v0, m.y, b.y));
+                v0 = n0, v1 = n1, ld += b.z;
+            } else if (ei.x == 1) {
+                const mnf_flow_op &op = p.prog.ops[ei.y];
+                const bool parity = ex[kk].flag != 0;
                 const float c = parity ? v1 : v0;  // affine_half_flow.py:46-50
                 float tr = parity ? v0 : v1;
-                const int g = p.gl.group_of[k][0];
+                const int g = ei.z;
                 float s = 0.f, t = 0.f;
                 if (g < 0) {  // neither net: s = t = 0
                 } else if (!s_over[g]) {
@@ -429,22 +493,23 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
                     if (op.flags & MNF_FLAG_SCALE) s = mlp_fp32_scalar(p.params + op.net_off[0], op.n_lin, op.sizes, c);
                     if (op.flags & MNF_FLAG_SHIFT) t = mlp_fp32_scalar(p.params + op.net_off[1], op.n_lin, op.sizes, c);
                 }
-                if (inverse) {  // affine_half_flow.py:54-56
+                if (p.dir_flags & 1) {  // affine_half_flow.py:54-56
                     tr = (tr - t) / expf(s), ld -= s;
                 } else {  // affine_half_flow.py:58
                     tr = expf(s) * tr + t, ld += s;
                 }
                 if (parity) v0 = tr; else v1 = tr;
-            } else {  // NSF_CL: f1 on (lower -> upper) then f2 on (upper -> lower) going forward (spline_flow.py:249-266);
-                      // f2 first, then f1, both with the spline inverse, going backward (:268-285)
+            } else {
+                const float4 cs = *reinterpret_cast<const float4 *>(ex[kk].c);  // B, 1/B, edge_deriv
+                const bool first_f1 = ex[kk].flag != 0;
 #pragma unroll 1
                 for (int step = 0; step < 2; ++step) {
-                    const bool use_f1 = (step == 0) != (inverse != 0);
+                    const bool use_f1 = (step == 0) == first_f1;
                     const float c = use_f1 ? v0 : v1;
                     float tr = use_f1 ? v1 : v0;
-                    const float B = op.bound;
+                    const float B = cs.x;
                     if (tr >= -B && tr <= B) {  // identity tails (also NaN), spline_flow.py:40,51-52: the conditioner is not needed
-                        const int g = p.gl.group_of[k][use_f1 ? 0 : 1];
+                        const int g = step ? ei.w : ei.z;
                         if (!s_over[g]) {
                             const float *tb = table(g);
                             const float4 *row = reinterpret_cast<const float4 *>(tb + BP_FLOATS) + find_piece<SM>(tb, c) * nsf_stride4(K);
@@ -458,13 +523,14 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
                                 raw[2 * j] = o.x, raw[2 * j + 1] = o.y;
                             }
                             const float2 *dv = reinterpret_cast<const float2 *>(row) + nsf_doff(K) / 2;
-                            rq_spline_lazy<K>(raw, B, 1.f / B, op.edge_deriv, inverse != 0, tr, ld, [&](int j) {
+                            rq_spline_lazy<K>(raw, B, cs.y, cs.z, (p.dir_flags & 1) != 0, tr, ld, [&](int j) {
                                 const float2 q = dv[j];
                                 return fmaf(q.x, d, q.y);
                             });
                         } else {
-                            const float2 o = nsf_fallback<K>(p.params + op.net_off[use_f1 ? 0 : 1], op.n_lin, op.sizes, B, op.edge_deriv, c,
-                                                             inverse != 0, tr);
+                            const mnf_flow_op &op = p.prog.ops[ei.y];
+                            const float2 o = nsf_fallback<K>(p.params + op.net_off[use_f1 ? 0 : 1], op.n_lin, op.sizes, B, cs.z, c,
+                                                             (p.dir_flags & 1) != 0, tr);
                             tr = o.x, ld += o.y;
                         }
                         if (use_f1) v1 = tr; else v0 = tr;
@@ -491,8 +557,9 @@ __device__ __forceinline__ void run_points(const Params &p, const float *smem, c
 template <int K>
 __global__ void __launch_bounds__(THREADS, 1) flow_pl_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) Exec s_exec[MNF_MAX_OPS];
     __shared__ int s_off[MAX_GROUPS], s_over[MAX_GROUPS];
-    __shared__ int s_allfit;
+    __shared__ int s_allfit, s_nexec;
     __shared__ __align__(8) unsigned long long s_bar;
     const int lane = threadIdx.x & 31, ng = p.gl.n;
     const uint32_t bar = smem_u32(&s_bar);
@@ -501,6 +568,7 @@ __global__ void __launch_bounds__(THREADS, 1) flow_pl_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < 64) build_exec(p, s_exec, &s_nexec, lane);
     if (threadIdx.x < 32) {
         // table sizes from the builder's header -> shared-memory offsets, one bulk copy per table
         const int *hdr = reinterpret_cast<const int *>(p.image);
@@ -541,8 +609,8 @@ __global__ void __launch_bounds__(THREADS, 1) flow_pl_kernel(const __grid_consta
     }
     __syncthreads();
     mbar_wait(bar, 0);
-    if (s_allfit) run_points<K, true>(p, smem, s_off, s_over);
-    else run_points<K, false>(p, smem, s_off, s_over);
+    if (s_allfit) run_points<K, true>(p, smem, s_off, s_over, s_exec, s_nexec);
+    else run_points<K, false>(p, smem, s_off, s_over, s_exec, s_nexec);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -670,7 +738,7 @@ int launch_flow_pl(const mnf_flow_op *ops, int n_ops, const float *params, const
     }
     // shared memory: every table at its largest, capped by what a CTA can have
     size_t want = (size_t)(pl.image_floats - HDR_FLOATS) * sizeof(float);
-    const size_t cap = (size_t)dp->smem_optin - 2048;
+    const size_t cap = (size_t)dp->smem_optin - 4096;  // static shared memory of the kernel: execution list, offsets, barrier
     if (want > cap) want = cap;
     want &= ~(size_t)15;
     p.smem_floats = (int)(want / sizeof(float));
