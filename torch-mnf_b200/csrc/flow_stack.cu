@@ -141,7 +141,7 @@ int mnf_flow_stack_run(const mnf_flow_op *ops_host, int n_ops, const float *para
         if (rc != 1) return rc;
     }
     MNF_REQUIRE(!gather || (gather->n_peers == 0 && !gather->multicast_ptr), MNF_E_SHAPE,
-                "peer-memory gather output needs the tensor-core dim-2 kernel (NSF_CL(K=8, n_h=16) stack in log-prob mode, >= 65536 rows)");
+                "peer-memory gather output needs the piecewise-linear or the tensor-core dim-2 kernel (AffineHalfFlow / NSF_CL stack in log-prob mode, with a workspace)");
     return launch_flow_generic(ops_host, n_ops, params, n_params, x, y, log_det, base_log_prob, intermediates,
                                n_rows, dim, inverse & 3, st);
 }
