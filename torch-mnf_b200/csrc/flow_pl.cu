@@ -343,8 +343,11 @@ __device__ __forceinline__ void rq_spline_lazy(const float *raw, float B, float 
         yk = ge ? ch[k] : yk, yk1 = ge ? ch[k + 1] : yk1;
     }
     const float wk = xk1 - xk, hk = yk1 - yk;  // spline_flow.py:102,113
-    const float dk = (idx > 0) ? knot_derivative<true>(deriv(idx - 1)) : edge_deriv;  // spline_flow.py:256,104; :46-49
-    const float dk1 = (idx < K - 1) ? knot_derivative<true>(deriv(idx)) : edge_deriv;
+    // interior knot derivatives (spline_flow.py:256,104), the padded constant at the two ends (:46-49); the loads are
+    // unconditional on a clamped index so that lanes in different bins do not diverge
+    const float r0 = deriv(max(idx - 1, 0)), r1 = deriv(min(idx, K - 2));
+    const float dk = (idx > 0) ? knot_derivative<true>(r0) : edge_deriv;
+    const float dk1 = (idx < K - 1) ? knot_derivative<true>(r1) : edge_deriv;
     const float sk_ = __fdividef(hk, wk);  // spline_flow.py:123
     const float dsum = dk + dk1 - 2.f * sk_;
     if (inverse) {  // spline_flow.py:133-162
