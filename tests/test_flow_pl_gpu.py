@@ -155,3 +155,57 @@ def test_pl_far_inputs_and_non_finite():
     x = 1e6 * torch.randn(4096, 2, generator=torch.Generator().manual_seed(4))  # spline tails: identity, log-det 0
     y, ld, _, _ = model._program().run(x.cuda(), True, kernel=PL)
     close_vs_oracle((y, ld), sd, specs, x, True, "cfg2 far inputs")
+
+
+@pytest.mark.parametrize("name", ["rnvp9_moons", "nsfcl3_stack"])
+def test_cuda_builder_matches_numpy_restatement(name):
+    """The tables flow_pl_build_kernel writes (the staged image) against tests/pl_reference.py: same breakpoints, same
+    per-piece slopes and values.  Image layout: flow_pl.cu (header of 4 ints per table, then per table 512 padded
+    breakpoints and 512 rows)."""
+    import numpy as np
+
+    from tests import pl_reference as plr
+    from torch_mnf import _lib
+
+    g = load_golden(name)
+    sd, specs = golden_sd(g), golden_spec(g)
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    prog._build(torch.device("cuda:0"))
+    img = prog._staged_image(_lib.lib(), 1, 2, None)
+    torch.cuda.synchronize()
+    assert img is not None
+    raw = img.cpu().numpy()
+    hdr = raw[:256].view(np.int32).reshape(64, 4)
+    off, gi = 256, 0
+    for i, spec in enumerate(specs):
+        if spec["type"] not in ("NSF_CL", "AffineHalfFlow"):
+            continue
+        nsf = spec["type"] == "NSF_CL"
+        stride = 52 if nsf else 12
+        for nets in plr.nets_of_flow(sd, i, spec):
+            bp = plr.breakpoints(nets)
+            tab = plr.tables(nets, bp)
+            n = int(hdr[gi, 0])
+            assert hdr[gi, 1] == 0 and n == len(bp), (gi, n, len(bp))
+            got_bp = raw[off:off + 512]
+            np.testing.assert_allclose(got_bp[:n], bp.astype(np.float32), rtol=1e-6, atol=1e-30)
+            assert np.isinf(got_bp[n:]).all()
+            rows = raw[off + 512:off + 512 + (n + 1) * stride].reshape(n + 1, stride)
+            for piece in range(n + 1):
+                org = float(got_bp[0] if piece == 0 else got_bp[piece - 1]) if n else 0.0
+                assert rows[piece, 48 if nsf else 4] == np.float32(org)
+                for q, (A, B) in enumerate(tab[piece]):
+                    V = A * org + B
+                    if nsf:
+                        K = spec["K"]
+                        ia = np.array([4 * (o >> 1) + (o & 1) if o < 2 * K else 4 * K + 2 * (o - 2 * K) for o in range(3 * K - 1)])
+                        iv = np.array([ia[o] + 2 if o < 2 * K else ia[o] + 1 for o in range(3 * K - 1)])
+                    else:
+                        ia, iv = np.array([q]), np.array([2 + q])
+                    scale = np.abs(A).max() + np.abs(V).max() + 1e-30
+                    np.testing.assert_allclose(rows[piece, ia], A, rtol=0, atol=3e-7 * scale)
+                    np.testing.assert_allclose(rows[piece, iv], V, rtol=0, atol=3e-7 * scale)
+            off += 512 + 512 * stride
+            gi += 1
+    assert gi > 0
