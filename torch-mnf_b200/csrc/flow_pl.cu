@@ -669,10 +669,12 @@ static Plan make_plan(const mnf_flow_op *ops, int n_ops, int dim) {
 
 template <int K>
 static int launch_k(const Params &p, const DeviceProps *dp, size_t smem_bytes, cudaStream_t st) {
-    static thread_local size_t attr_set = 0;
-    if (attr_set < smem_bytes) {
+    static thread_local size_t attr_set[64] = {};  // per device: the attribute belongs to the device's copy of the function
+    int dev = 0;
+    MNF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || attr_set[dev] < smem_bytes) {
         MNF_CUDA(cudaFuncSetAttribute(flow_pl_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = smem_bytes;
+        if (dev >= 0 && dev < 64) attr_set[dev] = smem_bytes;
     }
     // small batches are bound by the latency of one point's chain: spread the points over the SMs
     const int threads = p.n_rows <= (long long)dp->sm_count * 64 ? 64 : p.n_rows <= (long long)dp->sm_count * 256 ? 256 : THREADS;
