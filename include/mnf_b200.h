@@ -179,7 +179,7 @@ int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
 #define MNF_RUN_VARIANT_MASK 0x70
 #define MNF_RUN_VARIANT(v) ((((v) + 1) << 4) & MNF_RUN_VARIANT_MASK)
 /* v: 6 = every conditioner as a piecewise-linear table of its scalar input (csrc/flow_pl.cu) -- the library default for
- *        dim-2 stacks of AffineConstantFlow / ActNormFlow / Glow / AffineHalfFlow / NSF_CL(K = 5 or 8) whose conditioners
+ *        dim-2 stacks of AffineConstantFlow / ActNormFlow / Glow / AffineHalfFlow / NSF_CL(K in {4, 5, 6, 8, 10, 12, 16}) whose conditioners
  *        have 1..5 hidden layers of width <= 64, any batch size;
  *    0, 1, 2 = shared-memory weight variants of the register-resident dim-2 kernel (2 = default of the remaining shapes of
  *        its (hidden, bins) grid, and of calls without a workspace);

@@ -80,6 +80,12 @@ SHAPES = {
               {"type": "AffineHalfFlow", "dim": 2, "parity": True, "scale": True, "shift": True, "h_sizes": [16, 16, 16]},
               {"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16}, {"type": "Glow", "dim": 2},
               {"type": "AffineHalfFlow", "dim": 2, "parity": False, "scale": True, "shift": True, "h_sizes": [16, 16, 16]}],
+    # every instantiated bin count
+    "nsf_k4_k16": [{"type": "NSF_CL", "dim": 2, "K": 4, "B": 3, "n_h": 12}, {"type": "Glow", "dim": 2}, {"type": "NSF_CL", "dim": 2, "K": 4, "B": 3, "n_h": 12}],
+    "nsf_k6": [{"type": "NSF_CL", "dim": 2, "K": 6, "B": 2, "n_h": 16}] * 2,
+    "nsf_k10": [{"type": "NSF_CL", "dim": 2, "K": 10, "B": 4, "n_h": 16}] * 2,
+    "nsf_k12": [{"type": "NSF_CL", "dim": 2, "K": 12, "B": 3, "n_h": 24}] * 2,
+    "nsf_k16": [{"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}, {"type": "NSF_CL", "dim": 2, "K": 16, "B": 3, "n_h": 16}] * 2,
     # tables that do not fit: 6 tables of ~200 pieces x 208 B > 227 KB of shared memory -> read from the image in global memory
     "nsf_h64_x3": [{"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 64}] * 3,
     # an (s, t) pair of 1-64-64-64-64-64-1 nets has ~600 breakpoints > 511: flagged by the builder, evaluated layer by layer

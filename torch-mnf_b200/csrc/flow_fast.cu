@@ -213,7 +213,7 @@ int launch_flow_fast(const mnf_flow_op *ops, int n_ops, const float *params, int
     }
     const bool want_gather = gather && (gather->n_peers > 0 || gather->multicast_ptr);
     // variant 6 (default wherever it applies): every conditioner as a piecewise-linear table of its scalar input
-    // (flow_pl.cu), one launch for the whole stack after the table builder; any hidden widths up to 64, K in {5, 8}.
+    // (flow_pl.cu), one launch for the whole stack after the table builder; any hidden widths up to 64, K in {4, 5, 6, 8, 10, 12, 16}.
     // A staged image (bit 2) of such a program IS its tables, so a staged call always lands here.
     if ((variant == 6 || variant < 0 || (inverse & 4)) && (!want_gather || (inverse & 2)) && (workspace || plan_only)) {
         const int rc = launch_flow_pl(ops, n_ops, params, x, y, log_det, base_lp, inter, n_rows, dim, inverse & 7, workspace, gather,

@@ -619,6 +619,16 @@ __global__ void __launch_bounds__(THREADS, 1) flow_pl_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------
+// bins K the point kernel is instantiated for (the spline lives in registers: K is a template parameter)
+#define MNF_PL_BINS(X) X(4) X(5) X(6) X(8) X(10) X(12) X(16)
+constexpr int K_MAX = 16;
+static bool k_instantiated(int K) {
+#define MNF_PL_HAVE(KK) if (K == KK) return true;
+    MNF_PL_BINS(MNF_PL_HAVE)
+#undef MNF_PL_HAVE
+    return false;
+}
+
 struct Plan {
     bool ok = false;
     int K = 8;
@@ -640,7 +650,7 @@ static Plan make_plan(const mnf_flow_op *ops, int n_ops, int dim) {
         for (int l = 1; l < op.n_lin; ++l)
             if (op.sizes[l] < 1 || op.sizes[l] > MAX_H) return pl;
         if (op.type == MNF_OP_NSF_CL) {
-            if (op.K != 5 && op.K != 8) return pl;
+            if (!k_instantiated(op.K)) return pl;
             if (K && op.K != K) return pl;
             K = op.K;
             if (op.sizes[op.n_lin] != 3 * K - 1) return pl;
@@ -690,7 +700,7 @@ static int launch_k(const Params &p, const DeviceProps *dp, size_t smem_bytes, c
 int64_t flow_pl_workspace_floats(int n_ops) {
     if (n_ops < 1) n_ops = 1;
     if (n_ops > MNF_MAX_OPS) n_ops = MNF_MAX_OPS;
-    return fpl::HDR_FLOATS + (int64_t)2 * n_ops * fpl::region_floats(fpl::nsf_stride4(8));
+    return fpl::HDR_FLOATS + (int64_t)2 * n_ops * fpl::region_floats(fpl::nsf_stride4(fpl::K_MAX));
 }
 
 // floats of the table image of this program, 0 if it has no piecewise-linear form
@@ -747,8 +757,10 @@ int launch_flow_pl(const mnf_flow_op *ops, int n_ops, const float *params, const
     if (want > cap) want = cap;
     want &= ~(size_t)15;
     p.smem_floats = (int)(want / sizeof(float));
-    if (pl.K == 5) return launch_k<5>(p, dp, want, stream);
-    return launch_k<8>(p, dp, want, stream);
+#define MNF_PL_LAUNCH(KK) if (pl.K == KK) return launch_k<KK>(p, dp, want, stream);
+    MNF_PL_BINS(MNF_PL_LAUNCH)
+#undef MNF_PL_LAUNCH
+    return 1;
 }
 
 }  // namespace mnf
