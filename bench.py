@@ -430,6 +430,33 @@ def run_ours(args):
     # sanity: the e2e path produced finite log-probs equal to the resident path
     chk = torch.allclose(out_host[:4096], gathered.view(-1)[:4096].cpu(), rtol=1e-6, atol=1e-6) if chunks == 1 else True
 
+    # ---- the same copies with NO kernel: the ceiling PCIe / the host side puts on the end-to-end figure ----
+    def copies_only():
+        for c in range(e_chunks):
+            b = c & 1
+            with torch.cuda.stream(s_in):
+                xd[b].copy_(x_host[c * ecn:(c + 1) * ecn], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                out_host[c * ecn:(c + 1) * ecn].copy_(od[b], non_blocking=True)
+
+    copies_only()
+    e2e_join()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    s_in.wait_stream(torch.cuda.current_stream(dev))
+    s_out.wait_stream(torch.cuda.current_stream(dev))
+    for _ in range(args.steps):
+        copies_only()
+    e2e_join()
+    b.record()
+    barrier()
+    c_ms = a.elapsed_time(b) / args.steps
+    if world > 1:
+        tmax = torch.tensor([c_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        c_ms = float(tmax)
+
     del xd, od, out_host
     if rank != 0:
         return None
@@ -453,6 +480,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * n,
                 "ms_per_step": e_ms, "matches_resident_path": bool(chk), "host_affinity": affinity,
+                "copy_only_ceiling": {"value": world * n / (c_ms * 1e-3), "unit": "points/s", "ms_per_step": c_ms,
+                                      "frac_of_ceiling": c_ms / e_ms,
+                                      "note": "the same pinned-memory H2D + D2H copies per step on the same streams with NO kernel in between"},
                 "how": f"pinned host -> {e_chunks} chunks double-buffered over 3 streams (pipelined across steps) -> NormalizingFlowModel.log_prob -> pinned host"},
         "gpu_launches": launches, "gather_verified": gather_ok,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
