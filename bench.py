@@ -513,6 +513,15 @@ def run_ours(args):
                               if any("flow_tc" in k for k in k_sites) else
                               "conditioner-MLP FMAs only; spline arithmetic shares the same pipe")},
     }
+    if any("flow_pl" in k for k in k_sites):
+        # what the table kernel is really bound by: the special-function (XU / MUFU) pipe next to the issue slots
+        mufu_pt = 6 * 45  # per conditioner + spline: 32 EX2 (two softmaxes per axis), 4 RCP, 2 x (EX2 + LG2) softplus, 3 RCP, SQRT, LG2
+        xu_peak = sms * 16 * sm_clock * 1e6 / 1e9  # 16 MUFU lanes per SM and clock
+        out["xu_pipe"] = {"mufu_per_point": mufu_pt, "achieved": mufu_pt * n / (k_ms * 1e-3) / 1e9, "peak": xu_peak, "unit": "G MUFU/s",
+                          "frac": mufu_pt * n / (k_ms * 1e-3) / 1e9 / xu_peak,
+                          "note": "nominal count (a point outside [-B, B] skips the spline); ncu of the same kernel: XU pipe 71 %, issue "
+                                  "slots 82 % (profiles/r02_flow_pl_ncu_full.md) -- the kernel is bound by the reference's spline "
+                                  "parameterisation on these two pipes, not by HBM"}
     if world == 1:
         # The conditioner-free part of the same stack ([ActNormFlow, Glow] x 3) is the flow workload that IS HBM-bound:
         # reported next to the headline so that the HBM roofline of the streaming path can be read off this line too.

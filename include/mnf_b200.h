@@ -424,6 +424,10 @@ typedef struct mnf_kl_fused_args {
     uint32_t mask_streams[2 * MNF_KL_MAX_FLOWS];
 } mnf_kl_fused_args;
 int mnf_kl_div_fused(const mnf_kl_fused_args *args_host, void *stream);
+/* The same for n_layers layers at once (MNFLeNet.kl_div sums four, mnf_lenet.py:28-32): still three launches -- the
+ * layers are independent and each one's flow kernel is latency-bound on 8 SMs, so they run side by side.  layers[l] as
+ * for mnf_kl_div_fused (host array of host pointers); every layer writes its own kl.out[5]. */
+int mnf_kl_div_fused_multi(const mnf_kl_fused_args *const *layers_host, int n_layers, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Training path of the MNF layers.  The reference differentiates MNFLinear.forward /

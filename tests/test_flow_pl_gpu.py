@@ -215,3 +215,33 @@ def test_cuda_builder_matches_numpy_restatement(name):
             off += 512 + 512 * stride
             gi += 1
     assert gi > 0
+
+
+def test_pl_degenerate_conditioners():
+    """Dead first-layer units (zero weight: no kink), an all-zero hidden layer (constant conditioner), duplicated units
+    (coincident kinks), and very large weights (kinks packed around zero, steep pieces): the builder's tables against the
+    layer-by-layer interpreter."""
+    specs = [{"type": "AffineHalfFlow", "dim": 2, "parity": False, "scale": True, "shift": True, "h_sizes": [16, 16, 16]},
+             {"type": "NSF_CL", "dim": 2, "K": 8, "B": 3, "n_h": 16},
+             {"type": "AffineHalfFlow", "dim": 2, "parity": True, "scale": True, "shift": True, "h_sizes": [16, 16, 16]}]
+    sd = random_flow_sd(specs, seed=21, scale=0.5)
+    sd["flows.0.s_net.0.weight"][:5] = 0.0                    # dead units
+    sd["flows.0.t_net.2.weight"].zero_()                      # t_net is a constant
+    sd["flows.0.t_net.2.bias"].zero_()
+    sd["flows.1.f1.0.weight"][3] = sd["flows.1.f1.0.weight"][2]  # two identical units: coincident breakpoints
+    sd["flows.1.f1.0.bias"][3] = sd["flows.1.f1.0.bias"][2]
+    sd["flows.1.f2.0.weight"].mul_(1e4)                       # kinks within 1e-4 of zero
+    sd["flows.2.s_net.4.weight"].mul_(0.01)
+    sd["flows.2.t_net.0.weight"].zero_()                      # no breakpoint at all from layer 0
+    model = load_flow_model(specs, sd)
+    prog = model._program()
+    x = torch.randn(20000, 2, generator=torch.Generator().manual_seed(2)).cuda()
+    x[:100, 0] = 0.0
+    x[100:200] *= 1e-5
+    for inverse in (True, False):
+        sites = _launched(lambda: prog.run(x, inverse, kernel=PL))
+        assert "flow_pl_kernel" in sites, sites
+        y, ld, _, _ = prog.run(x, inverse, kernel=PL)
+        yg, ldg, _, _ = prog.run(x, inverse, kernel="generic")
+        torch.testing.assert_close(y, yg, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(ld, ldg, rtol=1e-4, atol=3e-4)

@@ -319,3 +319,36 @@ def test_graphed_inference_draws_fresh_noise_per_replay():
     # same distribution as eager calls: means agree within 6 standard errors of the 200-sample means
     se = (eager.std(0) + m.std(0)) / 200**0.5
     assert ((m.mean(0) - eager.mean(0)).abs() < 6 * se + 1e-3).all()
+
+
+def test_lenet_kl_div_multi_matches_loop():
+    """MNFLeNet.kl_div through mnf_kl_div_fused_multi (four layers, three launches) against the per-layer loop under
+    the same seeds: same draws, same value, same per-layer terms; deep copies and training mode keep working."""
+    import copy
+
+    from torch_mnf import _lib
+    from torch_mnf.models import MNFLeNet
+
+    torch.manual_seed(0)
+    m = MNFLeNet().cuda()
+    layers = [layer for layer in m if hasattr(layer, "kl_div")]
+    with torch.no_grad():
+        torch.manual_seed(5)
+        ref_terms = []
+        for layer in layers:
+            layer.kl_div()
+            ref_terms.append(layer.__dict__["_last_kl_terms"].clone())
+        ref = sum(t[0] for t in ref_terms)
+        torch.manual_seed(5)
+        _lib.launch_stats(reset=True)
+        got = m.kl_div()
+        sites = _lib.launch_stats()
+        assert sites == {"kl_flows_multi_kernel": 1, "kl_rows_multi_kernel": 1, "kl_final_multi_kernel": 1}, sites
+        torch.testing.assert_close(got, ref, rtol=1e-6, atol=0)
+        for layer, t in zip(layers, ref_terms):
+            torch.testing.assert_close(layer.__dict__["_last_kl_terms"], t, rtol=1e-6, atol=1e-6)
+        torch.manual_seed(5)
+        torch.testing.assert_close(copy.deepcopy(m).kl_div(), ref, rtol=1e-6, atol=0)
+    with torch.enable_grad():  # (this module's tests run with grad disabled: tests/conftest.py)
+        kl = m.kl_div()  # trainable parameters and grad enabled: the differentiable path
+    assert kl.requires_grad

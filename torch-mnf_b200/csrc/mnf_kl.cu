@@ -56,9 +56,7 @@ struct KlRowArgs {
     float *act;      // [rows]
 };
 
-__global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
-    __shared__ float red[96];
-    const int row = blockIdx.x;
+__device__ __forceinline__ void kl_rows_body(const KlRowArgs &a, int row, float *red) {
     const size_t base = (size_t)row * a.cols;
     const Philox rng(a.seed);
     float kl = 0.f, dot_mean = 0.f, dot_noise = 0.f;
@@ -117,6 +115,11 @@ __global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(256) kl_rows_kernel(const KlRowArgs a) {
+    __shared__ float red[96];
+    kl_rows_body(a, blockIdx.x, red);
+}
+
 struct KlFinalArgs {
     const float *kl_rows, *act;
     int rows;
@@ -134,8 +137,7 @@ struct KlFinalArgs {
     float *out;  // [1] result; out[1..4] = kl_W, kl_b, log_q, log_r for inspection
 };
 
-__global__ void __launch_bounds__(1024) kl_final_kernel(const KlFinalArgs a) {
-    __shared__ float red[32];
+__device__ __forceinline__ void kl_final_body(const KlFinalArgs &a, float *red) {
     float s = 0.f, sa = 0.f;
     for (int r = threadIdx.x; r < a.rows; r += blockDim.x) {
         s += a.kl_rows[r];
@@ -179,6 +181,11 @@ __global__ void __launch_bounds__(1024) kl_final_kernel(const KlFinalArgs a) {
 }
 
 
+__global__ void __launch_bounds__(1024) kl_final_kernel(const KlFinalArgs a) {
+    __shared__ float red[32];
+    kl_final_body(a, red);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // z0, flow_q and flow_r of one kl_div() call on their single row, in ONE launch (they were 1 + n_q + n_r launches
 // plus a copy): a thread-block cluster of 8 CTAs; per flow the CTAs split the conditioner outputs, meet at a cluster
@@ -199,7 +206,7 @@ struct KlFlowsArgs {
 };
 constexpr int kKlCluster = 8;
 
-__global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flows_kernel(const __grid_constant__ KlFlowsArgs a) {
+__device__ __forceinline__ void kl_flows_body(const KlFlowsArgs &a) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int c = (int)cluster.block_rank(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, dim = a.dim;
@@ -303,38 +310,55 @@ __global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flo
     }
 }
 
+__global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flows_kernel(const __grid_constant__ KlFlowsArgs a) {
+    kl_flows_body(a);
+}
 
-}  // namespace mnf
+// ---------------------------------------------------------------------------------------------------------
+// The kl_div() of SEVERAL layers in the same three launches (MNFLeNet.kl_div, mnf_lenet.py:28-32, sums four): the layers
+// are independent and each one's flow kernel is latency-bound on its 8 SMs, so cluster l of the grid runs layer l's
+// flows, grid row l of the weight pass layer l's rows, CTA l of the final kernel layer l's reduction.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kKlMultiMax = 4;
+struct KlFlowsMulti { KlFlowsArgs a[kKlMultiMax]; };
+struct KlRowsMulti { KlRowArgs a[kKlMultiMax]; };
+struct KlFinalMulti { KlFinalArgs a[kKlMultiMax]; };
 
-using namespace mnf;
+__global__ void __cluster_dims__(kKlCluster, 1, 1) __launch_bounds__(256) kl_flows_multi_kernel(const __grid_constant__ KlFlowsMulti m) {
+    kl_flows_body(m.a[blockIdx.x / kKlCluster]);
+}
+__global__ void __launch_bounds__(256) kl_rows_multi_kernel(const __grid_constant__ KlRowsMulti m) {
+    __shared__ float red[96];
+    const KlRowArgs &a = m.a[blockIdx.y];
+    if ((int)blockIdx.x >= a.rows) return;
+    kl_rows_body(a, blockIdx.x, red);
+}
+__global__ void __launch_bounds__(1024) kl_final_multi_kernel(const __grid_constant__ KlFinalMulti m) {
+    __shared__ float red[32];
+    kl_final_body(m.a[blockIdx.x], red);
+}
 
-extern "C" {
-
-int mnf_kl_div(const mnf_kl_args *a, void *stream) {
+// argument blocks of the three kernels from the ABI structs (shared by the one-layer and the multi-layer entry points)
+static int fill_rows_final(const mnf_kl_args *a, KlRowArgs &ra, KlFinalArgs &fa) {
     MNF_REQUIRE(a != nullptr, MNF_E_ARG, "args is NULL");
     MNF_REQUIRE(a->W_mean && a->W_log_var && a->z && a->zT && a->r0_c && a->r0_b1 && a->r0_b2 && a->b_log_var &&
                     a->q0_log_var && a->ld_q && a->ld_r && a->workspace && a->out,
                 MNF_E_ARG, "NULL pointer in mnf_kl_args");
     MNF_REQUIRE(a->n_out >= 1 && a->n_in >= 1 && a->ksize >= 1, MNF_E_ARG, "bad shape");
     MNF_REQUIRE(a->conv == 0 || a->conv == 1, MNF_E_ARG, "conv must be 0 or 1");
-    cudaStream_t st = (cudaStream_t)stream;
     const int fan = a->n_in * a->ksize * a->ksize;
     const int rows = a->conv ? fan : a->n_out;   // mnf_conv.py:107: view(-1, n_out)
     const int cols = a->conv ? a->n_out : fan;
     float *kl_rows = a->workspace, *act = a->workspace + rows;
-    KlRowArgs ra{a->W_mean, a->W_log_var, a->z, a->r0_c, a->eps_w, a->seed, a->noise_stream, rows, cols,
-                 a->conv, fan, kl_rows, act};
-    kl_rows_kernel<<<rows, 256, 0, st>>>(ra);
-    int rc = launch_status("kl_rows_kernel");
-    if (rc) return rc;
-    KlFinalArgs fa{kl_rows, act, rows, a->conv ? nullptr : a->b_mean, a->b_log_var, a->n_out, a->q0_log_var,
-                   a->r0_b1, a->r0_b2, a->zT, a->conv ? a->n_out : a->n_in, a->ld_q, a->ld_r, a->conv, a->r0_c,
-                   a->eps_b, a->seed, a->noise_stream + 1, a->out};
-    kl_final_kernel<<<1, 1024, 0, st>>>(fa);
-    return launch_status("kl_final_kernel");
+    ra = KlRowArgs{a->W_mean, a->W_log_var, a->z, a->r0_c, a->eps_w, a->seed, a->noise_stream, rows, cols,
+                   a->conv, fan, kl_rows, act};
+    fa = KlFinalArgs{kl_rows, act, rows, a->conv ? nullptr : a->b_mean, a->b_log_var, a->n_out, a->q0_log_var,
+                     a->r0_b1, a->r0_b2, a->zT, a->conv ? a->n_out : a->n_in, a->ld_q, a->ld_r, a->conv, a->r0_c,
+                     a->eps_b, a->seed, a->noise_stream + 1, a->out};
+    return 0;
 }
 
-int mnf_kl_div_fused(const mnf_kl_fused_args *a, void *stream) {
+static int fill_flows(const mnf_kl_fused_args *a, KlFlowsArgs &fa) {
     MNF_REQUIRE(a != nullptr, MNF_E_ARG, "args is NULL");
     const mnf_kl_args &k = a->kl;
     MNF_REQUIRE(k.z && k.zT && k.ld_q && k.ld_r && k.workspace && k.q0_log_var && a->q0_mean, MNF_E_ARG, "NULL pointer in mnf_kl_fused_args");
@@ -344,7 +368,7 @@ int mnf_kl_div_fused(const mnf_kl_fused_args *a, void *stream) {
     const int dim = k.conv ? k.n_out : k.n_in;
     MNF_REQUIRE(dim <= 11000, MNF_E_SHAPE, "dim=%d does not fit the one-row cluster kernel", dim);
     const int fan = k.n_in * k.ksize * k.ksize, rows = k.conv ? fan : k.n_out;
-    KlFlowsArgs fa{};
+    fa = KlFlowsArgs{};
     fa.nq = a->n_flows_q, fa.nr = a->n_flows_r, fa.dim = dim, fa.z_stream = a->z_stream, fa.seed = k.seed;
     fa.q0_mean = a->q0_mean, fa.q0_log_var = k.q0_log_var, fa.eps_z = a->eps_z;
     fa.z = const_cast<float *>(k.z), fa.zT = const_cast<float *>(k.zT);
@@ -358,12 +382,69 @@ int mnf_kl_div_fused(const mnf_kl_fused_args *a, void *stream) {
         MNF_REQUIRE(fl.net_w[0] && fl.net_b[0] && fl.t_w && fl.t_b && fl.s_w && fl.s_b, MNF_E_ARG, "NULL pointer in flow %d", f);
         fa.f[f] = KlFlowDev{fl.net_w[0], fl.net_b[0], fl.t_w, fl.t_b, fl.s_w, fl.s_b, a->masks[src], a->mask_streams[src], fl.net_sizes[0]};
     }
+    return 0;
+}
+
+
+}  // namespace mnf
+
+using namespace mnf;
+
+extern "C" {
+
+int mnf_kl_div(const mnf_kl_args *a, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KlRowArgs ra;
+    KlFinalArgs fa;
+    int rc = fill_rows_final(a, ra, fa);
+    if (rc) return rc;
+    kl_rows_kernel<<<ra.rows, 256, 0, st>>>(ra);
+    rc = launch_status("kl_rows_kernel");
+    if (rc) return rc;
+    kl_final_kernel<<<1, 1024, 0, st>>>(fa);
+    return launch_status("kl_final_kernel");
+}
+
+int mnf_kl_div_fused(const mnf_kl_fused_args *a, void *stream) {
+    KlFlowsArgs fa;
+    int rc = fill_flows(a, fa);
+    if (rc) return rc;
     // (a one-CTA, all-shared-memory form of this kernel was measured too: 462 us at dim 4096, 46-89 us on MNF-LeNet's
     // layers against 120 / 41-57 us for the cluster -- the time is cold-miss latency of the dependent weight reads)
-    kl_flows_kernel<<<kKlCluster, 256, sizeof(float) * (dim + 64 + 8), (cudaStream_t)stream>>>(fa);
-    int rc = launch_status("kl_flows_kernel");
+    kl_flows_kernel<<<kKlCluster, 256, sizeof(float) * (fa.dim + 64 + 8), (cudaStream_t)stream>>>(fa);
+    rc = launch_status("kl_flows_kernel");
     if (rc) return rc;
     return mnf_kl_div(&a->kl, stream);
+}
+
+int mnf_kl_div_fused_multi(const mnf_kl_fused_args *const *layers, int n_layers, void *stream) {
+    MNF_REQUIRE(layers != nullptr && n_layers >= 1, MNF_E_ARG, "no layers");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int first = 0; first < n_layers; first += kKlMultiMax) {  // groups of up to kKlMultiMax layers per launch triple
+        const int n = n_layers - first < kKlMultiMax ? n_layers - first : kKlMultiMax;
+        KlFlowsMulti fm{};
+        KlRowsMulti rm{};
+        KlFinalMulti lm{};
+        int max_dim = 0, max_rows = 0;
+        for (int l = 0; l < n; ++l) {
+            int rc = fill_flows(layers[first + l], fm.a[l]);
+            if (rc) return rc;
+            rc = fill_rows_final(&layers[first + l]->kl, rm.a[l], lm.a[l]);
+            if (rc) return rc;
+            max_dim = fm.a[l].dim > max_dim ? fm.a[l].dim : max_dim;
+            max_rows = rm.a[l].rows > max_rows ? rm.a[l].rows : max_rows;
+        }
+        kl_flows_multi_kernel<<<kKlCluster * n, 256, sizeof(float) * (max_dim + 64 + 8), st>>>(fm);
+        int rc = launch_status("kl_flows_multi_kernel");
+        if (rc) return rc;
+        kl_rows_multi_kernel<<<dim3((unsigned)max_rows, (unsigned)n), 256, 0, st>>>(rm);
+        rc = launch_status("kl_rows_multi_kernel");
+        if (rc) return rc;
+        kl_final_multi_kernel<<<n, 1024, 0, st>>>(lm);
+        rc = launch_status("kl_final_multi_kernel");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

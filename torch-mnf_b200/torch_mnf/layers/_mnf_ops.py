@@ -54,6 +54,7 @@ class KlFusedArgs(C.Structure):
 
 _lib.register({
     "mnf_kl_div_fused": (_int, [C.POINTER(KlFusedArgs), _vp]),
+    "mnf_kl_div_fused_multi": (_int, [C.POINTER(C.POINTER(KlFusedArgs)), _int, _vp]),
     "mnf_sample_z0": (_int, [_vp, _vp, _vp, _u64, _u32, _u64, _vp, _i64, _int, _vp]),
     "mnf_rnvp_forward": (_int, [C.POINTER(RnvpFlow), _int, _vp, _vp, C.POINTER(C.c_void_p), _u64, _u32, _u64,
                                 _i64, _int, _vp, _vp, _vp]),
@@ -481,6 +482,48 @@ def _kl_fused_plan(layer, conv, dev):
     return plan
 
 
+def _kl_philox_args(layer, plan, stream, out_ptr, dev):
+    """The layer's cached argument block pointed at this stream's scratch buffers, a fresh seed and `out_ptr` [5]."""
+    a, dim, fan, rows, nq, nr = plan
+    scratch = layer.__dict__["_kl_plan"][2]
+    buf = scratch.get(stream)
+    if buf is None:
+        buf = scratch[stream] = torch.empty(2 * dim + 8 + 2 * rows + 64, device=dev, dtype=torch.float32)
+    base = buf.data_ptr()
+    k = a.kl
+    k.z, k.zT, k.ld_q, k.ld_r = base, base + 4 * dim, base + 8 * dim, base + 8 * dim + 4
+    k.workspace, k.out = base + 4 * (2 * dim + 8), out_ptr
+    k.seed = int(torch.randint(0, 2**62, (1,)).item())  # follows torch.manual_seed
+    return a
+
+
+@torch.no_grad()
+def kl_div_multi(layers):
+    """Sum of kl_div() over several MNF layers in THREE launches (mnf_kl_div_fused_multi): same draws, same values as
+    calling the layers one after the other without a tape.  Returns None when a layer is outside the fused entry point's
+    shape class (the caller then loops)."""
+    from .mnf_conv import MNFConv2d
+
+    dev = layers[0].W_mean.device
+    if dev.type != "cuda" or torch.cuda.is_current_stream_capturing():
+        return None
+    plans = [_kl_fused_plan(layer, isinstance(layer, MNFConv2d), dev) for layer in layers]
+    if any(p is None for p in plans) or any(layer.W_mean.device != dev for layer in layers):
+        return None
+    stream = _lib.stream_ptr(dev)
+    out = torch.empty((len(layers), 5), device=dev, dtype=torch.float32)
+    ptrs = (C.POINTER(KlFusedArgs) * len(layers))()
+    for i, (layer, plan) in enumerate(zip(layers, plans)):
+        ptrs[i] = C.pointer(_kl_philox_args(layer, plan, stream, out.data_ptr() + 20 * i, dev))
+    with _lib.on_device(dev):
+        rc = _lib.lib().mnf_kl_div_fused_multi(ptrs, len(layers), stream)
+    _lib.check(rc, "mnf_kl_div_fused_multi")
+    _lib.launch_count += 3 * ((len(layers) + 3) // 4)
+    for i, layer in enumerate(layers):
+        layer.__dict__["_last_kl_terms"] = out[i]  # kl, kl_W, kl_b, log_q, log_r
+    return out[:, 0].sum()
+
+
 @torch.no_grad()
 def kl_div(layer, conv: bool, tape=None):
     """Shared driver of MNFLinear.kl_div / MNFConv2d.kl_div (draw order: SURVEY.md 8c)."""
@@ -492,18 +535,9 @@ def kl_div(layer, conv: bool, tape=None):
         # Philox mode, the common call: nothing but the seed and the result buffer changes between calls -- the noise
         # stream numbering (z0 = 0, flow_q masks 1.., eps_w, eps_b, flow_r masks) is fixed by the layer's shape and was
         # written into the cached argument block, the scratch buffers live with it (one set per CUDA stream)
-        a, dim, fan, rows, nq, nr = plan
         stream = _lib.stream_ptr(dev)
-        scratch = layer.__dict__["_kl_plan"][2]
-        buf = scratch.get(stream)
-        if buf is None:
-            buf = scratch[stream] = torch.empty(2 * dim + 8 + 2 * rows + 64, device=dev, dtype=torch.float32)
         out = torch.empty(5, device=dev, dtype=torch.float32)
-        base = buf.data_ptr()
-        k = a.kl
-        k.z, k.zT, k.ld_q, k.ld_r = base, base + 4 * dim, base + 8 * dim, base + 8 * dim + 4
-        k.workspace, k.out = base + 4 * (2 * dim + 8), out.data_ptr()
-        k.seed = int(torch.randint(0, 2**62, (1,)).item())  # follows torch.manual_seed
+        a = _kl_philox_args(layer, plan, stream, out.data_ptr(), dev)
         with _lib.on_device(dev):
             rc = _lib.lib().mnf_kl_div_fused(C.byref(a), stream)
         _lib.check(rc, "mnf_kl_div_fused")

@@ -139,5 +139,12 @@ class MNFLeNet(nn.Sequential):
         return sums if sample_range is not None else sums / n_samples
 
     def kl_div(self, noise=None):
-        """Sum of the MNF layers' KL estimates (mnf_lenet.py:28-32)."""
-        return sum(layer.kl_div(noise) for layer in self if hasattr(layer, "kl_div"))
+        """Sum of the MNF layers' KL estimates (mnf_lenet.py:28-32).  Without an injected tape and outside autograd the
+        four layers go through ONE call of three launches (mnf_kl_div_fused_multi: the layers are independent and each
+        one's flow kernel is latency-bound, so they run side by side) -- same draws and values as the loop."""
+        layers = [layer for layer in self if hasattr(layer, "kl_div")]
+        if noise is None and not _train.needs_grad(self):
+            total = ops.kl_div_multi(layers)
+            if total is not None:
+                return total
+        return sum(layer.kl_div(noise) for layer in layers)
