@@ -35,15 +35,19 @@ class NormalizingFlow(nn.Module):
 
     __getstate__ = state_without_caches  # copy.deepcopy / pickle drop the launch caches (ctypes descriptors)
 
+    def _flow_list(self) -> list:
+        """The flows as a plain list (read from the module dicts directly: nn.Module.__getattr__ is on every
+        small-batch call's critical path)."""
+        return list(self._modules["flows"]._modules.values())
+
     def _program(self) -> FlowProgram:
         prog = self.__dict__.get("_prog")
-        if prog is None or len(prog.flows) != len(self.flows) or any(
-            a is not b for a, b in zip(prog.flows, self.flows)
-        ):
-            for f in self.flows:
+        flows = self._flow_list()
+        if prog is None or prog.flows != flows:  # (list comparison: identity first, no __eq__ on nn.Module)
+            for f in flows:
                 if not isinstance(f, Flow):
                     raise TypeError(f"{type(f).__name__} is not a torch_mnf flow")
-            prog = FlowProgram(list(self.flows))
+            prog = FlowProgram(flows)
             self.__dict__["_prog"] = prog
         return prog
 
@@ -58,7 +62,7 @@ class NormalizingFlow(nn.Module):
         per-layer TF32 GEMM chain otherwise.  -> (outputs list, log_det, log_prob or None) or None."""
         from .maf import IAF, MAF, density_stack
 
-        flows = list(self.flows)
+        flows = self._flow_list()
         if not flows or not all(isinstance(f, MAF) for f in flows):
             return None
         if any(isinstance(f, IAF) != (not inverse) for f in flows):
@@ -82,7 +86,9 @@ class NormalizingFlow(nn.Module):
         """ActNorm initialises itself from the first batch IT sees, i.e. the output of the flows that run before
         it in this direction (affine_constant_flow.py:42-50 inside core.py:30-33's loop).  Flows with a pending
         init get that input from a one-off run of the preceding sub-stack."""
-        order = list(self.flows)[::-1] if inverse else list(self.flows)
+        order = self._flow_list()
+        if inverse:
+            order.reverse()
         for i, f in enumerate(order):
             pending = getattr(f, "_init_pending", None)
             if pending is None or not pending(inverse):
