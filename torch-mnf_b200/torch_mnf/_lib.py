@@ -162,7 +162,13 @@ class on_device:
         return False
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)  # no Stream object per call (a tenth of a small-batch call)
+
+
 def stream_ptr(device) -> int:
+    if _raw_stream is not None:
+        idx = device.index
+        return _raw_stream(idx if idx is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -227,12 +227,12 @@ class BoundLogProb:
                                         C.byref(self._handle))
         _lib.check(rc, "mnf_flow_handle_create")
         self._call = lib.mnf_flow_handle_log_prob
-        self._stream = torch.cuda.current_stream
+        self._stream = _lib.stream_ptr
 
     def __call__(self, x, out=None):
         if out is None:
             out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
-        rc = self._call(self._handle, x.data_ptr(), out.data_ptr(), x.shape[0], self._stream(x.device).cuda_stream)
+        rc = self._call(self._handle, x.data_ptr(), out.data_ptr(), x.shape[0], self._stream(x.device))
         if rc:
             _lib.check(rc, "mnf_flow_handle_log_prob")
         return out
