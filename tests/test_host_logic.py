@@ -320,3 +320,46 @@ def test_kl_fused_plan_numbering_matches_the_draw_order_and_follows_parameter_st
     # outside the fused entry point's shape class: two-layer conditioners -> the multi-launch path
     wide = MNFLinear(12, 7, h_sizes=(8, 8))
     assert ops._kl_fused_plan(wide, False, dev) is None
+
+
+def test_table_kernel_planning_and_buffer_sizes():
+    """Host side of csrc/flow_pl.cu (no launch): which programs have a piecewise-linear form, and that the staged image
+    of any of them fits the workspace mnf_flow_stack_workspace() asks callers to provide."""
+    from tests.helpers import build_flow
+    from torch_mnf import _lib
+    from torch_mnf._program import FlowProgram
+
+    lib = _lib.lib()
+    cpu = torch.device("cpu")
+
+    def prog_of(specs):
+        prog = FlowProgram([build_flow(s) for s in specs])
+        prog._build(cpu)
+        return prog
+
+    def stage_size(prog, dim=2):
+        return lib.mnf_flow_stack_stage_size(prog._ops, prog._n_ops, dim, prog._blob.numel())
+
+    nsf = lambda K, h: {"type": "NSF_CL", "dim": 2, "K": K, "B": 3, "n_h": h}  # noqa: E731
+    aff = lambda hs, p=False, scale=True, shift=True: {"type": "AffineHalfFlow", "dim": 2, "parity": p, "scale": scale,  # noqa: E731
+                                                       "shift": shift, "h_sizes": hs}
+    act = {"type": "ActNormFlow", "dim": 2, "scale": True, "shift": True}
+    glow = {"type": "AffineConstantFlow", "dim": 2, "scale": True, "shift": False}  # (Glow's blob is assembled by a kernel: no CPU build)
+    hdr, bp, rows = 256, 512, 512  # flow_pl.cu: header floats, padded breakpoints and rows per table
+    # config 2: six spline tables of stride 52 floats; config 1: nine (s, t) tables of stride 12
+    assert stage_size(prog_of([act, glow, nsf(8, 16)] * 3)) == hdr + 6 * (bp + rows * 52)
+    assert stage_size(prog_of([aff([24, 24, 24], bool(i % 2)) for i in range(9)])) == hdr + 9 * (bp + rows * 12)
+    # any depth 1..5 and width <= 64, every instantiated bin count; conditioner-free flows add no table
+    for specs in ([aff([40])], [aff([32, 16]), glow], [aff([64] * 5)], [nsf(4, 12)], [nsf(5, 8)], [nsf(16, 64)], [nsf(10, 20), act],
+                  [aff([16, 16, 16], scale=False), nsf(8, 16)]):
+        prog = prog_of(specs)
+        size = stage_size(prog)
+        assert size > hdr, specs
+        assert size <= lib.mnf_flow_stack_workspace(prog._n_ops, 1 << 20, 2), specs
+        assert prog.plan(cpu, 2) == 1, specs
+    # outside the table kernel: bins it is not instantiated for, widths above 64 (both still have other kernels or the
+    # interpreter), other dims
+    assert stage_size(prog_of([nsf(7, 16)])) == 0
+    assert stage_size(prog_of([aff([96, 96])])) == 0
+    wide = prog_of([{"type": "NSF_CL", "dim": 4, "K": 8, "B": 3, "n_h": 16}])
+    assert stage_size(wide, dim=4) == 0 and lib.mnf_flow_stack_workspace(1, 1 << 20, 4) == 0
