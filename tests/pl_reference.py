@@ -43,7 +43,7 @@ def breakpoints(nets):
                 al, be = pre_maps(Ws, bs, l - 1, m[i])
                 with np.errstate(divide="ignore", invalid="ignore"):
                     tz = -be / al
-                new += list(tz[(al != 0) & (tz > lo[i]) & (tz < hi[i])])
+                new += list(tz[(al != 0) & (tz > lo[i]) & (tz < hi[i]) & (np.abs(tz) < 3.0e38)])  # kinks inside the fp32 range
         bp = np.sort(np.concatenate([bp, new]))
     return bp
 

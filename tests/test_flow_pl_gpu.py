@@ -222,7 +222,7 @@ def test_cuda_builder_matches_numpy_restatement(name):
     _check_tables_against_numpy(load_flow_model(specs, sd), sd, specs)
 
 
-DEGENERATE = ["dead_units", "constant_net", "duplicate_units", "steep", "very_steep", "no_first_layer_kink", "all"]
+DEGENERATE = ["dead_units", "constant_net", "duplicate_units", "steep", "very_steep", "no_first_layer_kink", "kink_beyond_fp32", "all"]
 
 
 @pytest.mark.parametrize("case", DEGENERATE)
@@ -249,6 +249,9 @@ def test_pl_degenerate_conditioners(case):
         sd["flows.1.f2.0.weight"].mul_(1e2)
     if case == "very_steep":
         sd["flows.1.f2.0.weight"].mul_(1e4)
+    if case in ("kink_beyond_fp32", "all"):
+        sd["flows.0.s_net.0.weight"][7] = 1e-39   # -b/w ~ 1e38 .. 1e39: outside what fp32 can hold
+        sd["flows.0.s_net.0.weight"][8] = -3e-39
     if case in ("no_first_layer_kink", "all"):
         sd["flows.2.s_net.4.weight"].mul_(0.01)
         sd["flows.2.t_net.0.weight"].zero_()

@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(32 * BW) flow_pl_build_kernel(const __grid_con
                     const double a = s_va[warp][cur][k], b = s_vb[warp][cur][k];
                     if (a != 0.0) {
                         const double tz = -b / a;
-                        if (tz > lo && tz < hi) {
+                        // (a kink beyond the fp32 range -- a first-layer weight of ~1e-39 -- is no kink for any fp32 input,
+                        // and would give its piece an infinite origin)
+                        if (tz > lo && tz < hi && fabs(tz) < 3.0e38) {
                             const int pos = atomicAdd(&s_ncand, 1);
                             if (pos < 512) s_tmp[pos] = tz;
                         }
