@@ -196,6 +196,9 @@ int64_t mnf_flow_stack_workspace(int n_ops, int64_t n_rows, int dim);
  *   - otherwise the shared-memory layout of the nets for the register-resident kernel (variant 2), for runs of fewer
  *     than 65 536 rows: the kernel then starts with a plain vector copy. */
 int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
+/* Largest batch a MNF_RUN_STAGED run of this program accepts: INT64_MAX when the staged image holds the conditioner
+ * tables (any batch), 65535 when it is the shared-memory layout of the register-resident kernel, 0 without a staged form. */
+int64_t mnf_flow_stack_stage_max_rows(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params);
 int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,
                          float *staged, void *stream);
 

@@ -47,13 +47,15 @@ def test_pl_vs_golden(name):
 
 
 def test_default_path_is_the_table_kernel():
-    """Module calls of the BASELINE dim-2 stacks: staged tables below 65536 rows (one launch), tables built per call above."""
-    for name, rows, want in (("cfg1_shape", 4096, {"flow_pl_kernel": 1}), ("cfg2_shape", 1 << 16, {"flow_pl_build_kernel": 1, "flow_pl_kernel": 1})):
+    """Module calls of the BASELINE dim-2 stacks: the tables are staged once per parameter version, a call of any size is
+    ONE launch; an explicit variant request (no staging) builds them inside the call."""
+    for name, rows, want in (("cfg1_shape", 4096, {"flow_pl_kernel": 1}), ("cfg2_shape", 1 << 16, {"flow_pl_kernel": 1})):
         specs = ORACLE_CASES[name]
         model = load_flow_model(specs, random_flow_sd(specs, seed=1, scale=0.4), return_intermediates=False)
         x = torch.randn(rows, 2, device="cuda")
         model.log_prob(x)  # first call stages
         assert _launched(lambda: model.log_prob(x)) == want
+        assert _launched(lambda: model._program().run(x, True, log_prob_only=True, kernel=PL)) == {"flow_pl_build_kernel": 1, "flow_pl_kernel": 1}
 
 
 @pytest.mark.parametrize("name,scale", [("cfg2_shape", 0.6), ("cfg1_shape", 0.3), ("nsf_default", 0.6)])
@@ -113,11 +115,12 @@ def test_pl_shapes_match_interpreter(name, rows):
 
 
 def test_pl_staged_equals_built_per_call():
-    """The same points through the staged tables (module call, < 65536 rows) and through tables built inside the call."""
+    """The same points through the staged tables (module call) and through tables built inside the call (explicit variant)."""
     specs = ORACLE_CASES["cfg2_shape"]
     model = load_flow_model(specs, random_flow_sd(specs, seed=2, scale=0.6), return_intermediates=False)
     x = 1.5 * torch.randn(1 << 17, 2, device="cuda")
-    big = model.log_prob(x)
+    big = model._program().run(x, True, log_prob_only=True, kernel=PL)[3]
+    assert torch.equal(model.log_prob(x), big)
     small = torch.cat([model.log_prob(x[i:i + 30000].contiguous()) for i in range(0, x.size(0), 30000)])
     assert torch.equal(big, small)
     bound = model.log_prob_fn(1 << 17)

@@ -1,6 +1,7 @@
 // flow_stack.cu -- C-ABI entry points for flow stacks (dispatch: dim-2 register-resident
 // kernel when the program qualifies, generic interpreter otherwise) and the two small
 // parameter-side kernels (Glow assembly, ActNorm data-dependent init).
+#include <cstdint>
 #include <new>
 
 #include "common.cuh"
@@ -205,6 +206,12 @@ int mnf_flow_handle_log_prob(const mnf_flow_handle *h, const float *x, float *lo
 int64_t mnf_flow_stack_stage_size(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params) {
     if (validate_program(ops_host, n_ops, dim, n_params)) return 0;
     return flow_stage_size(ops_host, n_ops, dim);
+}
+
+int64_t mnf_flow_stack_stage_max_rows(const mnf_flow_op *ops_host, int n_ops, int dim, int64_t n_params) {
+    if (validate_program(ops_host, n_ops, dim, n_params)) return 0;
+    if (flow_pl_image_floats(ops_host, n_ops, dim) > 0) return INT64_MAX;
+    return flow_stage_size(ops_host, n_ops, dim) > 0 ? (1 << 16) - 1 : 0;
 }
 
 int mnf_flow_stack_stage(const mnf_flow_op *ops_host, int n_ops, const float *params, int64_t n_params, int dim,

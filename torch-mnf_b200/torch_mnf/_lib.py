@@ -71,6 +71,7 @@ _SIGS = {
          C.c_int64, C.c_int, C.c_int, C.c_void_p],
     ),
     "mnf_flow_stack_stage_size": (C.c_int64, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
+    "mnf_flow_stack_stage_max_rows": (C.c_int64, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),
     "mnf_flow_stack_stage": (C.c_int, [C.POINTER(FlowOp), C.c_int, _f32p, C.c_int64, C.c_int, _f32p, C.c_void_p]),
     "mnf_flow_stack_workspace": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "mnf_flow_stack_plan": (C.c_int, [C.POINTER(FlowOp), C.c_int, C.c_int, C.c_int64]),

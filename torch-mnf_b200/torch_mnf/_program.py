@@ -278,15 +278,16 @@ class FlowProgram:
         self._staged = {}  # dim -> pre-staged shared-memory image of the nets (or False), rebuilt with the blob
         self._key = key
 
-    STAGED_MAX_ROWS = (1 << 16) - 1  # above this the dim-2 spline stacks of the benchmark shape take the tensor-core kernel
-
     def _staged_image(self, lib, n_rows, dim, kernel):
-        """Pre-staged net image for small dim-2 batches (mnf_flow_stack_stage), cached until a parameter changes."""
-        if dim != 2 or n_rows > self.STAGED_MAX_ROWS or kernel is not None or not 0 < self._n_ops <= _lib.MAX_OPS:
+        """Per-parameter-version image of a dim-2 program (mnf_flow_stack_stage), cached until a parameter changes: the
+        conditioner tables of the piecewise-linear kernel (any batch size) or, for the shapes without them, the
+        shared-memory layout of the nets (batches below 65536 rows)."""
+        if dim != 2 or kernel is not None or not 0 < self._n_ops <= _lib.MAX_OPS:
             return None
         img = self._staged.get(dim)
         if img is None:
             size = lib.mnf_flow_stack_stage_size(self._ops, self._n_ops, dim, self._blob.numel())
+            self._staged["max_rows"] = lib.mnf_flow_stack_stage_max_rows(self._ops, self._n_ops, dim, self._blob.numel())
             img = False
             if size > 0:
                 img = torch.empty(size, device=self._blob.device, dtype=torch.float32)
@@ -295,7 +296,7 @@ class FlowProgram:
                                                   img.data_ptr(), _lib.stream_ptr(self._blob.device))
                 _lib.check(rc, "mnf_flow_stack_stage")
             self._staged[dim] = img
-        return img if img is not False else None
+        return img if img is not False and n_rows <= self._staged["max_rows"] else None
 
     @staticmethod
     def _workspace(lib, n_ops, n_rows, dim, dev, have_y=False, kernel=None):
